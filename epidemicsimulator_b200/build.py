@@ -1,0 +1,90 @@
+"""Build the native libraries in-tree.
+
+libesim_b200.so  - CUDA kernels + C ABI (include/esim.h), nvcc, sm_100a only.
+libesim_host.so  - host-side population generator / sharding (include/esim_popgen.h), g++.
+
+Both land next to this file so that they travel with the repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+INCLUDE = ROOT / "include"
+
+CUDA_LIB = PKG / "libesim_b200.so"
+HOST_LIB = PKG / "libesim_host.so"
+
+CUDA_SOURCES = ["esim_kernels.cu", "esim_api.cu"]
+HOST_SOURCES = ["popgen.cpp"]
+
+
+def _newer(target: Path, deps) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(d).stat().st_mtime <= t for d in deps)
+
+
+def _run(cmd):
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(map(str, cmd)), proc.stdout))
+    return proc.stdout
+
+
+def host_compiler() -> str:
+    # the image exports CXX=/opt/gcc/bin/g++ (no OpenMP spec file); prefer the distribution compiler
+    for cand in ("/usr/bin/g++", shutil.which("g++") or ""):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("no g++ found")
+
+
+def build_host(force: bool = False) -> Path:
+    srcs = [CSRC / s for s in HOST_SOURCES]
+    deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h"]
+    if not force and _newer(HOST_LIB, deps):
+        return HOST_LIB
+    _run([host_compiler(), "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", str(INCLUDE), "-o", str(HOST_LIB)]
+         + [str(s) for s in srcs])
+    return HOST_LIB
+
+
+def nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    srcs = [CSRC / s for s in CUDA_SOURCES]
+    deps = srcs + [INCLUDE / "esim.h"] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
+    if not force and _newer(CUDA_LIB, deps):
+        return CUDA_LIB
+    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-ccbin", host_compiler(),
+           "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(CUDA_LIB)]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [str(s) for s in srcs] + ["-lcudart", "-ldl"]
+    out = _run(cmd)
+    if verbose:
+        print(out)
+    return CUDA_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build_host(force), build_cuda(force, verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", HOST_LIB, CUDA_LIB)

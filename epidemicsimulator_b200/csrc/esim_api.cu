@@ -1,0 +1,726 @@
+// C ABI of libesim_b200.so (include/esim.h): owns device memory, the stream, the captured step graph; builds the
+// device layout from the imported population; steps / runs / reads back.  Host-side counterpart of
+// `impl From<SimulatorBuilder> for Simulator` + `Simulator::{step, simulate}` + `StatisticsRecorder::dump_to_file`.
+#include <cuda_runtime.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "esim.h"
+#include "esim_internal.h"
+#include "esim_rng.h"
+
+using namespace esim;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaError { cudaError_t e; const char* what; int line; };
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) throw CudaError{_e, #call, __LINE__}; \
+    } while (0)
+
+struct ApiError { int code; std::string msg; };
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+constexpr int GRAPH_DAY = 24;  // steps captured in the bulk graph
+
+}  // namespace
+
+struct EsimSim {
+    EsimConfig cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevView v{};
+    DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt, route_off, riders, pt_key, pt_bus, pt_buscnt,
+        rec_bus, rec_businf;
+    DevBuf<unsigned long long> thr;
+    DevBuf<Ctrl> ctrl;
+    DevBuf<EsimStepStats> stats;
+    Ctrl* h_ctrl = nullptr;             // pinned
+    EsimStepStats* h_stat = nullptr;    // pinned, one entry
+    std::vector<uint32_t> h_bldg_area, h_room_parent;
+    uint32_t n_areas = 0;
+    bool imported = false;
+    uint32_t steps_done = 0;            // steps executed (recorded) so far
+    bool finished = false;
+    cudaGraph_t graph1 = nullptr, graph_day = nullptr;
+    cudaGraphExec_t exec1 = nullptr, exec_day = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    EsimTimings timings{};
+    std::vector<float> step_total_ms;   // per recorded step, 0 when not measured
+    std::vector<float> step_phase_ms;   // 3 per recorded step
+    size_t device_bytes = 0;
+    std::string err;
+
+    ~EsimSim() {
+        if (device >= 0) cudaSetDevice(device);
+        if (exec1) cudaGraphExecDestroy(exec1);
+        if (exec_day) cudaGraphExecDestroy(exec_day);
+        if (graph1) cudaGraphDestroy(graph1);
+        if (graph_day) cudaGraphDestroy(graph_day);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt.release();
+        route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
+        rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release();
+        if (h_ctrl) cudaFreeHost(h_ctrl);
+        if (h_stat) cudaFreeHost(h_stat);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int fail(EsimSim* s, int code, const std::string& msg) {
+    if (s) s->err = msg; else g_create_error = msg;
+    return code;
+}
+
+template <class F>
+int guarded(EsimSim* s, F&& f) {
+    try {
+        return f();
+    } catch (const CudaError& e) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at esim_api.cu:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.line, e.what);
+        return fail(s, ESIM_ERR_CUDA, buf);
+    } catch (const ApiError& e) {
+        return fail(s, e.code, e.msg);
+    } catch (const std::bad_alloc&) {
+        return fail(s, ESIM_ERR_DEFAULT, "out of host memory");
+    } catch (...) {
+        return fail(s, ESIM_ERR_DEFAULT, "unknown error");
+    }
+}
+
+// Integer form of `RANDOM_DISTRUBUTION.sample(rng) < exposure_chance` (citizen.rs:242): the smallest 52-bit draw m
+// whose uniform value is >= prob, so that (u01(m) < prob) <=> (m < threshold).  u01 is monotone in m.
+unsigned long long threshold_for(double prob) {
+    unsigned long long lo = 0, hi = 1ull << 52;  // answer in [0, 2^52]
+    while (lo < hi) {
+        const unsigned long long mid = lo + (hi - lo) / 2;
+        if (u01_from_u52(mid) < prob) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+void build_thresholds(const EsimConfig& c, unsigned long long out[512]) {
+    // DiseaseModel::get_exposure_chance (disease.rs:131-154) for the two cases that can occur for a non-vaccinated
+    // citizen: effective MaskStatus::None / PublicTransport (-> chance) and Everywhere (-> chance - chance*eff).
+    double chance[2];
+    chance[0] = c.exposure_chance - 0.0 - 0.0;
+    chance[1] = c.exposure_chance - c.exposure_chance * c.mask_effectiveness - 0.0;
+    for (int m = 0; m < 2; ++m) {
+        if (std::signbit(chance[m])) chance[m] = 0.0;
+        for (int n = 0; n < 256; ++n) {
+            const double prob = 1.0 - std::pow(1.0 - chance[m], (double)n);  // binomial (citizen.rs:47-49)
+            out[m * 256 + n] = threshold_for(prob);
+        }
+    }
+}
+
+void enqueue_step(EsimSim* s) {
+    const DevView& v = s->v;
+    CK(cudaMemsetAsync(v.cnt, 0, (size_t)v.n_cells * sizeof(uint32_t), s->stream));
+    launch_update(v, s->stream);
+    launch_expose(v, s->stream);
+    launch_pt(v, s->stream);
+    launch_tail(v, s->stream);
+}
+
+void capture_graphs(EsimSim* s) {
+    for (int which = 0; which < 2; ++which) {
+        const int steps = which == 0 ? 1 : GRAPH_DAY;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < steps; ++i) enqueue_step(s);
+        CK(cudaStreamEndCapture(s->stream, &g));
+        cudaGraphExec_t e = nullptr;
+        CK(cudaGraphInstantiate(&e, g, 0));
+        if (which == 0) { s->graph1 = g; s->exec1 = e; } else { s->graph_day = g; s->exec_day = e; }
+    }
+}
+
+void fetch_ctrl(EsimSim* s) {
+    CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaGetLastError());
+}
+
+int after_steps(EsimSim* s) {
+    // h_ctrl is fresh: ctrl.t is the next step to execute
+    const uint32_t done = s->h_ctrl->t - 1;
+    s->step_total_ms.resize(done, 0.f);
+    s->step_phase_ms.resize((size_t)done * 3, 0.f);
+    s->steps_done = done;
+    s->finished = s->h_ctrl->finished != 0;
+    if (s->h_ctrl->error) return -(int)s->h_ctrl->error;
+    return 0;
+}
+
+void require_ready(EsimSim* s) {
+    if (!s) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null handle"};
+    if (!s->imported) throw ApiError{ESIM_ERR_INITIALIZATION, "Population has not been Initialized"};
+    CK(cudaSetDevice(s->device));
+}
+
+}  // namespace
+
+extern "C" {
+
+int esim_abi_version(void) { return ESIM_ABI_VERSION; }
+
+const char* esim_build_info(void) {
+    return "libesim_b200 abi " "1" " sm_100a cuda " __DATE__ " " __TIME__;
+}
+
+int esim_default_config(EsimConfig* c) {
+    if (!c) return ESIM_ERR_INVALID_ARGUMENT;
+    std::memset(c, 0, sizeof(*c));
+    c->exposure_chance = 0.00055;          // disease.rs:120
+    c->mask_effectiveness = 0.70;          // disease.rs:127
+    c->lockdown_threshold = 0.0034;        // interventions.rs:74
+    c->vaccination_threshold = 0.005;      // interventions.rs:75
+    c->mask_pt_threshold = 0.001;          // interventions.rs:54
+    c->mask_everywhere_threshold = 0.0022; // interventions.rs:55
+    c->exposed_time = 4 * 24;              // disease.rs:122
+    c->infected_time = 14 * 24;            // disease.rs:123
+    c->max_time_step = 5000;               // disease.rs:124
+    c->vaccination_rate = 85 * 18;         // disease.rs:125
+    c->bus_capacity = 20;                  // config.rs:37
+    c->flags = 0;
+    c->seed = 0;
+    c->device = 0;
+    return ESIM_OK;
+}
+
+int esim_create(const EsimConfig* cfg, EsimSim** out) {
+    if (!cfg || !out) return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (cfg->max_time_step == 0 || cfg->max_time_step > MAX_STEPS)
+        return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "max_time_step must be in [1, 64510]");
+    if (cfg->exposed_time + cfg->infected_time + 2 >= EXPOSURE_BIAS)
+        return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "exposed_time + infected_time must be below 1022");
+    if (cfg->bus_capacity == 0) return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "bus_capacity must be positive");
+    if (cfg->vaccination_rate > 4000) return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "vaccination_rate must be <= 4000");
+    if (!(cfg->exposure_chance >= 0.0 && cfg->exposure_chance <= 1.0))
+        return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "exposure_chance must be a probability");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, ESIM_ERR_NO_DEVICE, "no CUDA device: libesim_b200 has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, ESIM_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, ESIM_ERR_NO_DEVICE, "libesim_b200 is built for sm_100a (B200) only");
+    EsimSim* s = new (std::nothrow) EsimSim();
+    if (!s) return fail(nullptr, ESIM_ERR_DEFAULT, "out of host memory");
+    s->cfg = *cfg;
+    s->device = cfg->device;
+    const int rc = guarded(s, [&]() {
+        CK(cudaSetDevice(s->device));
+        CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
+        CK(cudaMallocHost(&s->h_stat, sizeof(EsimStepStats)));
+        for (auto& e : s->ev) CK(cudaEventCreate(&e));
+        CK((cudaError_t)configure_kernels());
+        return ESIM_OK;
+    });
+    if (rc < 0) { g_create_error = s->err; delete s; return rc; }
+    *out = s;
+    return ESIM_OK;
+}
+
+void esim_destroy(EsimSim* s) { delete s; }
+
+int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
+    if (!s) return ESIM_ERR_INVALID_ARGUMENT;
+    return guarded(s, [&]() -> int {
+        if (!p || !p->home_bldg || !p->work_bldg || !p->room || !p->bldg_area || !p->bldg_type || (p->n_rooms && !p->room_bldg))
+            throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population arrays missing"};
+        if (s->imported) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population already imported"};
+        CK(cudaSetDevice(s->device));
+        const uint32_t N = p->n_citizens, B = p->n_buildings, R = p->n_rooms, A = p->n_areas;
+        if (N == 0 || B == 0 || A == 0) throw ApiError{ESIM_ERR_INVALID_POPULATION, "empty population"};
+        if ((uint64_t)B + R >= 0xFFFFFFF0ull) throw ApiError{ESIM_ERR_INVALID_POPULATION, "too many buildings"};
+        if (p->n_shared_bldgs > B || p->n_shared_rooms > R) throw ApiError{ESIM_ERR_INVALID_POPULATION, "shared prefix larger than the arrays"};
+        const uint32_t n_pad = (N + 3u) & ~3u;
+        const uint32_t n_global = p->n_global_citizens ? p->n_global_citizens : N;
+        const uint32_t shard_lo = p->global_id ? p->global_id[0] : 0u;
+        if ((uint64_t)shard_lo + N > n_global) throw ApiError{ESIM_ERR_INVALID_POPULATION, "global ids exceed n_global_citizens"};
+        for (uint32_t b = 0; b < B; ++b)
+            if (p->bldg_area[b] >= A || p->bldg_type[b] > ESIM_BLDG_SCHOOL)
+                throw ApiError{ESIM_ERR_INVALID_POPULATION, "building with invalid area or type"};
+        for (uint32_t r = 0; r < R; ++r)
+            if (p->room_bldg[r] >= B || p->bldg_type[p->room_bldg[r]] != ESIM_BLDG_SCHOOL)
+                throw ApiError{ESIM_ERR_INVALID_POPULATION, "room whose building is not a school"};
+        const uint32_t te = s->cfg.exposed_time, ti = s->cfg.infected_time;
+
+        std::vector<uint32_t> cstate(n_pad, CS_ABSENT), home(n_pad, 0), work(n_pad, 0), gid(n_pad, 0);
+        std::vector<std::pair<uint64_t, uint32_t>> pt;  // (route key, citizen)
+        for (uint32_t i = 0; i < N; ++i) {
+            const uint32_t h = p->home_bldg[i], w = p->work_bldg[i], m = p->room[i];
+            if (h >= B || w >= B) throw ApiError{ESIM_ERR_MISSING_CITIZEN, "citizen references a building that does not exist"};
+            if (p->bldg_type[h] != ESIM_BLDG_HOUSEHOLD) throw ApiError{ESIM_ERR_INVALID_POPULATION, "household_code is not a Household"};
+            const bool school = p->bldg_type[w] == ESIM_BLDG_SCHOOL;
+            if (school != (m != ESIM_NO_ROOM) || (school && (m >= R || p->room_bldg[m] != w)) || (w == h && m != ESIM_NO_ROOM))
+                throw ApiError{ESIM_ERR_INVALID_POPULATION, "school membership and room assignment disagree"};
+            if (p->global_id && p->global_id[i] != shard_lo + i)
+                throw ApiError{ESIM_ERR_INVALID_POPULATION, "global_id must be contiguous and ascending inside a shard"};
+            const uint8_t f = p->flags ? p->flags[i] : 0;
+            uint32_t word = 0;
+            if (f & ESIM_FLAG_USES_PT) word |= CS_USES_PT;
+            if (f & ESIM_FLAG_MASK_COMPLIANT) word |= CS_COMPLIANT;
+            if (p->bldg_area[h] == p->bldg_area[w]) word |= CS_SAME_AREA;
+            const uint8_t st = p->status ? p->status[i] : (uint8_t)ESIM_STATUS_SUSCEPTIBLE;
+            const uint32_t tm = p->timer ? p->timer[i] : 0u;
+            // the hour of exposure that reproduces (status, timer) at time_step 0, see esim_internal.h
+            switch (st) {
+                case ESIM_STATUS_SUSCEPTIBLE: break;
+                case ESIM_STATUS_EXPOSED:
+                    if (tm > te) throw ApiError{ESIM_ERR_INVALID_POPULATION, "Exposed timer above exposed_time"};
+                    word |= EXPOSURE_BIAS - tm; break;
+                case ESIM_STATUS_INFECTED:
+                    if (tm > ti) throw ApiError{ESIM_ERR_INVALID_POPULATION, "Infected timer above infected_time"};
+                    word |= EXPOSURE_BIAS - (te + 1 + tm); break;
+                case ESIM_STATUS_RECOVERED: word |= EXPOSURE_BIAS - (te + ti + 2); break;
+                case ESIM_STATUS_VACCINATED: word |= CS_VACCINATED; break;
+                default: throw ApiError{ESIM_ERR_INVALID_POPULATION, "unknown disease status"};
+            }
+            cstate[i] = word;
+            home[i] = h;
+            work[i] = school ? B + m : w;
+            gid[i] = shard_lo + i;
+            if (f & ESIM_FLAG_USES_PT) pt.push_back({((uint64_t)p->bldg_area[h] << 32) | p->bldg_area[w], i});
+        }
+        // routes: riders grouped by (home area, work area); citizen order inside a route
+        if (!std::is_sorted(pt.begin(), pt.end())) {
+            bool by_area = true;
+            for (size_t k = 1; k < pt.size() && by_area; ++k) by_area = (pt[k - 1].first >> 32) <= (pt[k].first >> 32);
+            if (by_area) {
+                size_t b0 = 0;
+                for (size_t k = 1; k <= pt.size(); ++k)
+                    if (k == pt.size() || (pt[k].first >> 32) != (pt[b0].first >> 32)) { std::sort(pt.begin() + b0, pt.begin() + k); b0 = k; }
+            } else {
+                std::sort(pt.begin(), pt.end());
+            }
+        }
+        std::vector<uint32_t> route_off, riders(pt.size());
+        for (size_t k = 0; k < pt.size(); ++k) {
+            if (k == 0 || pt[k].first != pt[k - 1].first) route_off.push_back((uint32_t)k);
+            riders[k] = pt[k].second;
+        }
+        const uint32_t n_routes = (uint32_t)route_off.size();
+        route_off.push_back((uint32_t)pt.size());
+
+        unsigned long long thr[512];
+        build_thresholds(s->cfg, thr);
+
+        // ---- device allocation + upload ----
+        s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad); s->gid.alloc(n_pad);
+        s->room_parent.alloc(std::max<uint32_t>(R, 1)); s->cnt.alloc((size_t)B + R);
+        s->route_off.alloc(route_off.size()); s->riders.alloc(std::max<size_t>(riders.size(), 1));
+        s->pt_key.alloc(std::max<size_t>(riders.size(), 1)); s->pt_bus.alloc(std::max<size_t>(riders.size(), 1));
+        s->pt_buscnt.alloc(std::max<size_t>(riders.size(), 1));
+        const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
+        if (rec) { s->rec_bus.alloc(N); s->rec_businf.alloc(N); }
+        s->thr.alloc(512); s->ctrl.alloc(1); s->stats.alloc(s->cfg.max_time_step);
+        CK(cudaMemcpyAsync(s->cstate.p, cstate.data(), s->cstate.bytes(), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->home_cell.p, home.data(), s->home_cell.bytes(), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->work_cell.p, work.data(), s->work_cell.bytes(), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->gid.p, gid.data(), s->gid.bytes(), cudaMemcpyHostToDevice, s->stream));
+        if (R) CK(cudaMemcpyAsync(s->room_parent.p, p->room_bldg, (size_t)R * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->route_off.p, route_off.data(), s->route_off.bytes(), cudaMemcpyHostToDevice, s->stream));
+        if (!riders.empty()) CK(cudaMemcpyAsync(s->riders.p, riders.data(), riders.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->thr.p, thr, sizeof(thr), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemsetAsync(s->cnt.p, 0, s->cnt.bytes(), s->stream));
+        CK(cudaMemsetAsync(s->stats.p, 0, s->stats.bytes(), s->stream));
+        if (rec) {
+            CK(cudaMemsetAsync(s->rec_bus.p, 0xFF, s->rec_bus.bytes(), s->stream));
+            CK(cudaMemsetAsync(s->rec_businf.p, 0, s->rec_businf.bytes(), s->stream));
+        }
+        Ctrl c0;
+        std::memset(&c0, 0, sizeof(c0));
+        c0.t = 1;  // the first hour is 1 (statistics.rs:167); everybody starts at home, off public transport (citizen.rs:156-160)
+        std::memcpy(s->h_ctrl, &c0, sizeof(c0));
+        CK(cudaMemcpyAsync(s->ctrl.p, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+
+        s->h_bldg_area.assign(p->bldg_area, p->bldg_area + B);
+        if (R) s->h_room_parent.assign(p->room_bldg, p->room_bldg + R);
+        s->n_areas = A;
+
+        DevView& v = s->v;
+        v.n = N; v.n_pad = n_pad; v.n_bldg = B; v.n_rooms = R; v.n_cells = B + R;
+        v.n_routes = n_routes; v.n_riders = (uint32_t)riders.size(); v.record_buses = rec ? 1u : 0u;
+        v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
+        v.room_parent = s->room_parent.p; v.cnt = s->cnt.p; v.thr = s->thr.p;
+        v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
+        v.pt_buscnt = s->pt_buscnt.p; v.rec_bus = s->rec_bus.p; v.rec_businf = s->rec_businf.p;
+        v.ctrl = s->ctrl.p; v.stats = s->stats.p; v.max_steps = s->cfg.max_time_step;
+        v.mp.exposed_time = te; v.mp.infected_time = ti; v.mp.vaccination_rate = s->cfg.vaccination_rate;
+        v.mp.bus_capacity = s->cfg.bus_capacity;
+        v.mp.th_lockdown = s->cfg.lockdown_threshold; v.mp.th_vaccination = s->cfg.vaccination_threshold;
+        v.mp.th_mask_pt = s->cfg.mask_pt_threshold; v.mp.th_mask_everywhere = s->cfg.mask_everywhere_threshold;
+        v.mp.seed_lo = (uint32_t)s->cfg.seed; v.mp.seed_hi = (uint32_t)(s->cfg.seed >> 32);
+        v.mp.n_global_citizens = n_global; v.mp.shard_lo = shard_lo;
+
+        s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->gid.bytes() +
+                          s->room_parent.bytes() + s->cnt.bytes() + s->route_off.bytes() + s->riders.bytes() * 4 +
+                          s->rec_bus.bytes() * 2 + s->stats.bytes();
+        if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(s);
+        s->imported = true;
+        s->steps_done = 0;
+        s->finished = false;
+        return ESIM_OK;
+    });
+}
+
+static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (s->steps_done >= s->cfg.max_time_step && !s->finished)
+            throw ApiError{ESIM_ERR_SIMULATION, "max_time_step reached"};
+        const uint32_t before = s->steps_done;
+        if (timed) {
+            const DevView& v = s->v;
+            CK(cudaEventRecord(s->ev[0], s->stream));
+            CK(cudaMemsetAsync(v.cnt, 0, (size_t)v.n_cells * sizeof(uint32_t), s->stream));
+            launch_update(v, s->stream);
+            CK(cudaEventRecord(s->ev[1], s->stream));
+            launch_expose(v, s->stream);
+            CK(cudaEventRecord(s->ev[2], s->stream));
+            launch_pt(v, s->stream);
+            CK(cudaEventRecord(s->ev[3], s->stream));
+            launch_tail(v, s->stream);
+            CK(cudaEventRecord(s->ev[4], s->stream));
+        } else if (s->exec1) {
+            CK(cudaGraphLaunch(s->exec1, s->stream));
+        } else {
+            enqueue_step(s);
+        }
+        if (!s->finished && before < s->cfg.max_time_step)
+            CK(cudaMemcpyAsync(s->h_stat, s->stats.p + before, sizeof(EsimStepStats), cudaMemcpyDeviceToHost, s->stream));
+        fetch_ctrl(s);
+        const int rc = after_steps(s);
+        if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
+        if (timed && s->steps_done > before) {
+            float ms[4];
+            for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ms[k], s->ev[k], s->ev[k + 1]));
+            EsimTimings& T = s->timings;
+            T.k_update += ms[0] * 1e-3; T.k_expose += ms[1] * 1e-3; T.k_pt += ms[2] * 1e-3; T.k_tail += ms[3] * 1e-3;
+            T.generate_exposures += ms[0] * 1e-3;
+            T.apply_exposures += (ms[1] + ms[2]) * 1e-3;
+            T.apply_interventions += ms[3] * 1e-3;
+            T.total += (ms[0] + ms[1] + ms[2] + ms[3]) * 1e-3;
+            T.steps += 1;
+            s->step_total_ms[before] = ms[0] + ms[1] + ms[2] + ms[3];
+            s->step_phase_ms[(size_t)before * 3 + 0] = ms[0];
+            s->step_phase_ms[(size_t)before * 3 + 1] = ms[1] + ms[2];
+            s->step_phase_ms[(size_t)before * 3 + 2] = ms[3];
+        }
+        if (out) {
+            if (s->steps_done > before) *out = *s->h_stat;
+            else std::memset(out, 0, sizeof(*out));
+        }
+        return s->finished ? 0 : 1;
+    });
+}
+
+int esim_step(EsimSim* s, EsimStepStats* out) { return step_common(s, out, false); }
+int esim_step_timed(EsimSim* s, EsimStepStats* out) { return step_common(s, out, true); }
+
+int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
+    if (steps_done) *steps_done = 0;
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        const uint32_t start = s->steps_done;
+        uint32_t budget = std::min<uint32_t>(max_steps, s->cfg.max_time_step - std::min(s->cfg.max_time_step, start));
+        // the loop is device-resident: the host only looks at the control block every few simulated days
+        constexpr uint32_t CHUNK_DAYS = 8;
+        while (budget > 0 && !s->finished) {
+            uint32_t queued = 0;
+            if (s->exec_day)
+                for (uint32_t d = 0; d < CHUNK_DAYS && budget - queued >= (uint32_t)GRAPH_DAY; ++d) {
+                    CK(cudaGraphLaunch(s->exec_day, s->stream));
+                    queued += GRAPH_DAY;
+                }
+            if (queued == 0) {
+                const uint32_t n = std::min<uint32_t>(budget, GRAPH_DAY);
+                for (uint32_t k = 0; k < n; ++k) {
+                    if (s->exec1) CK(cudaGraphLaunch(s->exec1, s->stream)); else enqueue_step(s);
+                }
+                queued = n;
+            }
+            fetch_ctrl(s);
+            const int rc = after_steps(s);
+            if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
+            budget -= queued;
+        }
+        if (steps_done) *steps_done = s->steps_done - start;
+        return s->finished ? 0 : 1;
+    });
+}
+
+int esim_steps_done(EsimSim* s) { return s ? (int)s->steps_done : ESIM_ERR_INVALID_ARGUMENT; }
+
+int esim_read_stats(EsimSim* s, uint32_t first, uint32_t count, EsimStepStats* out) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (!out) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null output"};
+        if (first >= s->steps_done) return 0;
+        const uint32_t n = std::min(count, s->steps_done - first);
+        CK(cudaMemcpyAsync(out, s->stats.p + first, (size_t)n * sizeof(EsimStepStats), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return (int)n;
+    });
+}
+
+namespace {
+struct HostState {
+    std::vector<uint32_t> cstate, home, work;
+    Ctrl ctrl;
+};
+void download_state(EsimSim* s, HostState& h, bool cells) {
+    const uint32_t n_pad = s->v.n_pad;
+    h.cstate.resize(n_pad);
+    CK(cudaMemcpyAsync(h.cstate.data(), s->cstate.p, (size_t)n_pad * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (cells) {
+        h.home.resize(n_pad); h.work.resize(n_pad);
+        CK(cudaMemcpyAsync(h.home.data(), s->home_cell.p, (size_t)n_pad * 4, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(h.work.data(), s->work_cell.p, (size_t)n_pad * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    fetch_ctrl(s);
+    h.ctrl = *s->h_ctrl;
+}
+inline bool host_eligible(uint32_t w, const Ctrl& c) {
+    if (!c.vax_some) return false;
+    const uint32_t e = w & CS_E_MASK;
+    if (e == 0) return true;
+    return (int)e - (int)EXPOSURE_BIAS > (int)c.vax_start_step && !(w & CS_VIA_PT);
+}
+}  // namespace
+
+int esim_read_state(EsimSim* s, EsimStateView* view) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (!view) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null view"};
+        HostState h;
+        download_state(s, h, view->current_bldg != nullptr);
+        const Ctrl& c = h.ctrl;
+        // the control block already holds the schedule of the *next* step; the state after the last executed step is in
+        // the recorded statistics entry
+        uint32_t at_work = 0, pt_mode = ESIM_PT_NONE;
+        const uint32_t t_last = s->steps_done;  // state after this step's progression
+        if (t_last > 0) {
+            EsimStepStats last;
+            CK(cudaMemcpy(&last, s->stats.p + (t_last - 1), sizeof(last), cudaMemcpyDeviceToHost));
+            at_work = last.at_work; pt_mode = last.pt_mode;
+        }
+        const uint32_t te = s->cfg.exposed_time, ti = s->cfg.infected_time, B = s->v.n_bldg;
+        for (uint32_t i = 0; i < s->v.n; ++i) {
+            uint32_t w = h.cstate[i];
+            if (c.vax_all_pending && host_eligible(w, c)) w |= CS_VACCINATED;
+            uint8_t st; uint16_t tm = 0;
+            const uint32_t e = w & CS_E_MASK;
+            if (w & CS_VACCINATED) st = ESIM_STATUS_VACCINATED;
+            else if (e == 0) st = ESIM_STATUS_SUSCEPTIBLE;
+            else {
+                const int d = (int)t_last - ((int)e - (int)EXPOSURE_BIAS);
+                if (d <= (int)te) { st = ESIM_STATUS_EXPOSED; tm = (uint16_t)d; }
+                else if (d <= (int)(te + 1 + ti)) { st = ESIM_STATUS_INFECTED; tm = (uint16_t)(d - (int)te - 1); }
+                else st = ESIM_STATUS_RECOVERED;
+            }
+            if (view->status) view->status[i] = st;
+            if (view->timer) view->timer[i] = tm;
+            if (view->current_bldg) {
+                uint32_t cell = at_work ? h.work[i] : h.home[i];
+                if (cell >= B) cell = s->h_room_parent[cell - B];
+                view->current_bldg[i] = cell;
+            }
+            if (view->on_pt) view->on_pt[i] = (w & CS_USES_PT) ? (uint8_t)pt_mode : (uint8_t)ESIM_PT_NONE;
+            if (view->vax_eligible) view->vax_eligible[i] = host_eligible(w, c) ? 1 : 0;
+        }
+        return ESIM_OK;
+    });
+}
+
+int esim_read_building_counts(EsimSim* s, uint32_t* bldg, uint32_t* room) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (bldg) CK(cudaMemcpyAsync(bldg, s->cnt.p, (size_t)s->v.n_bldg * 4, cudaMemcpyDeviceToHost, s->stream));
+        if (room && s->v.n_rooms)
+            CK(cudaMemcpyAsync(room, s->cnt.p + s->v.n_bldg, (size_t)s->v.n_rooms * 4, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return ESIM_OK;
+    });
+}
+
+int esim_read_buses(EsimSim* s, uint32_t* bus_index, uint32_t* bus_infected) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (!s->v.record_buses) throw ApiError{ESIM_ERR_OPTION_RETRIEVAL, "ESIM_CFG_RECORD_BUSES was not set"};
+        if (bus_index) CK(cudaMemcpyAsync(bus_index, s->rec_bus.p, (size_t)s->v.n * 4, cudaMemcpyDeviceToHost, s->stream));
+        if (bus_infected) CK(cudaMemcpyAsync(bus_infected, s->rec_businf.p, (size_t)s->v.n * 4, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return ESIM_OK;
+    });
+}
+
+int esim_inject_rng(EsimSim* s, uint64_t seed) {
+    return guarded(s, [&]() -> int {
+        if (!s) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null handle"};
+        s->cfg.seed = seed;
+        if (s->imported) {
+            CK(cudaSetDevice(s->device));
+            CK(cudaStreamSynchronize(s->stream));
+            s->v.mp.seed_lo = (uint32_t)seed; s->v.mp.seed_hi = (uint32_t)(seed >> 32);
+            // kernel parameters are baked into the captured graphs: re-capture
+            if (s->exec1) { cudaGraphExecDestroy(s->exec1); s->exec1 = nullptr; }
+            if (s->exec_day) { cudaGraphExecDestroy(s->exec_day); s->exec_day = nullptr; }
+            if (s->graph1) { cudaGraphDestroy(s->graph1); s->graph1 = nullptr; }
+            if (s->graph_day) { cudaGraphDestroy(s->graph_day); s->graph_day = nullptr; }
+            if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(s);
+        }
+        return ESIM_OK;
+    });
+}
+
+int esim_get_timings(EsimSim* s, EsimTimings* out) {
+    if (!s || !out) return ESIM_ERR_INVALID_ARGUMENT;
+    *out = s->timings;
+    return ESIM_OK;
+}
+
+// StatisticsRecorder::dump_to_file (statistics.rs:113-150)
+int esim_dump_statistics(EsimSim* s, const char* directory, const char* const* area_codes) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (!directory) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null directory"};
+        const std::string dir(directory);
+        {   // fs::create_dir_all
+            std::string cur;
+            for (size_t k = 0; k < dir.size(); ++k) {
+                cur.push_back(dir[k]);
+                if (dir[k] == '/' && cur.size() > 1 && mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST)
+                    throw ApiError{ESIM_ERR_IO, "Failed to create statistics directory: '" + dir + "'"};
+            }
+        }
+        const uint32_t T = s->steps_done;
+        std::vector<EsimStepStats> st(T);
+        if (T) CK(cudaMemcpy(st.data(), s->stats.p, (size_t)T * sizeof(EsimStepStats), cudaMemcpyDeviceToHost));
+        HostState h;
+        download_state(s, h, true);
+        auto open = [&](const char* name) {
+            FILE* f = fopen((dir + name).c_str(), "w");
+            if (!f) throw ApiError{ESIM_ERR_IO, std::string("Failed to create results file: ") + name};
+            return f;
+        };
+        // exposures.json: per output area the non-zero per-step counts of building exposures, in step order
+        // (StatisticsRecorder::add_exposure statistics.rs:181-195, next() :161-164, dump :118-135).  A citizen exposed in a
+        // building at step x was standing in its workplace's area iff at_work(x), else in its household's area.
+        {
+            const uint32_t B = s->v.n_bldg;
+            std::vector<std::map<uint32_t, uint32_t>> per_area(s->n_areas);
+            for (uint32_t i = 0; i < s->v.n; ++i) {
+                const uint32_t w = h.cstate[i], e = w & CS_E_MASK;
+                if (e <= EXPOSURE_BIAS || (w & CS_VIA_PT)) continue;
+                const uint32_t x = e - EXPOSURE_BIAS;
+                if (x == 0 || x > T) continue;
+                uint32_t cell = st[x - 1].at_work ? h.work[i] : h.home[i];
+                if (cell >= B) cell = s->h_room_parent[cell - B];
+                per_area[s->h_bldg_area[cell]][x] += 1;
+            }
+            FILE* f = open("exposures.json");
+            fputc('{', f);
+            bool any = false;
+            int last_area = -1;
+            for (uint32_t a = 0; a < s->n_areas; ++a) if (!per_area[a].empty()) last_area = (int)a;
+            auto write_series = [&](const std::map<uint32_t, uint32_t>& m) {
+                fputc('[', f);
+                bool first = true;
+                for (auto& kv : m) { fprintf(f, first ? "%u" : ",%u", kv.second); first = false; }
+                fputc(']', f);
+            };
+            if (last_area >= 0) {
+                // "All" holds whichever place the reference's HashMap drained last: here the last output area
+                fputs("\"All\":{\"All\":", f);
+                write_series(per_area[last_area]);
+                fputs("},\"OutputArea\":{", f);
+                for (uint32_t a = 0; a < s->n_areas; ++a) {
+                    if (per_area[a].empty()) continue;
+                    if (any) fputc(',', f);
+                    any = true;
+                    if (area_codes && area_codes[a]) fprintf(f, "\"%s\":", area_codes[a]); else fprintf(f, "\"%u\":", a);
+                    write_series(per_area[a]);
+                }
+                fputc('}', f);
+                bool pt_any = false;
+                for (auto& e : st) pt_any = pt_any || e.exposures_pt;
+                if (pt_any) fputs(",\"PublicTransport\":{}", f);
+            }
+            fputc('}', f);
+            fclose(f);
+        }
+        {   // timings.json: one map per step (Timer::finished, statistics.rs:75-78)
+            FILE* f = open("timings.json");
+            fputc('[', f);
+            for (uint32_t k = 0; k < T; ++k) {
+                const float* ph = &s->step_phase_ms[(size_t)k * 3];
+                fprintf(f, "%s{\"Generate Exposures\":%.9g,\"Apply Exposures\":%.9g,\"Apply Interventions\":%.9g,\"total\":%.9g}",
+                        k ? "," : "", ph[0] * 1e-3, ph[1] * 1e-3, ph[2] * 1e-3, s->step_total_ms[k] * 1e-3);
+            }
+            fputc(']', f);
+            fclose(f);
+        }
+        {   // memory.json: get_memory_usage() per step (config.rs:42-47); here the device memory held by the handle
+            FILE* f = open("memory.json");
+            fputc('[', f);
+            const double gb = (double)(s->device_bytes / 1024 / 1024) / 1024.0;
+            for (uint32_t k = 0; k < T; ++k) fprintf(f, "%s\"%.2f GB\"", k ? "," : "", gb);
+            fputc(']', f);
+            fclose(f);
+        }
+        {   // global_stats.json: every entry plus the empty one pushed by the flush (statistics.rs:115,169)
+            FILE* f = open("global_stats.json");
+            fputc('[', f);
+            for (uint32_t k = 0; k < T; ++k)
+                fprintf(f, "%s{\"time_step\":%u,\"susceptible\":%u,\"exposed\":%u,\"infected\":%u,\"recovered\":%u,\"vaccinated\":%u}",
+                        k ? "," : "", st[k].time_step, st[k].susceptible, st[k].exposed, st[k].infected, st[k].recovered, st[k].vaccinated);
+            fprintf(f, "%s{\"time_step\":%u,\"susceptible\":0,\"exposed\":0,\"infected\":0,\"recovered\":0,\"vaccinated\":0}]", T ? "," : "", T + 1);
+            fclose(f);
+        }
+        return ESIM_OK;
+    });
+}
+
+const char* esim_last_error(EsimSim* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"

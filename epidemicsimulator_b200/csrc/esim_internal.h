@@ -1,0 +1,98 @@
+// Device data layout and kernel launch interface shared by esim_kernels.cu and esim_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "esim.h"
+
+namespace esim {
+
+// ---- packed per-citizen state word ---------------------------------------------------------------------
+// The reference stores DiseaseStatus::{Exposed(u16), Infected(u16)} and increments the timer of every exposed /
+// infected citizen every hour (disease.rs:47-71).  Both timers are pure functions of the hour of exposure, so the
+// state word stores that hour once and no citizen is rewritten while it progresses E -> I -> R:
+//
+//   bits  0..15  E = 0 (never exposed) or (time_step of the exposure + EXPOSURE_BIAS)
+//   bit   16     vaccinated (DiseaseStatus::Vaccinated overrides whatever E encodes, simulator.rs:551)
+//   bit   17     exposed on public transport (removed from citizens_eligible_for_vaccine, simulator.rs:447-449)
+//   bit   18     uses_public_transport       (static, citizen.rs:132)
+//   bit   19     is_mask_compliant           (static, citizen.rs:131)
+//   bit   20     household and workplace stand in the same output area (static; the simulator.rs:324 filter)
+//   bit   31     padding slot: not a citizen
+//
+// With d = time_step - (E - EXPOSURE_BIAS):  d <= exposed_time                     -> Exposed(d)
+//                                            d <= exposed_time + 1 + infected_time -> Infected(d - exposed_time - 1)
+//                                            otherwise                             -> Recovered
+constexpr uint32_t CS_E_MASK      = 0xFFFFu;
+constexpr uint32_t CS_VACCINATED  = 1u << 16;
+constexpr uint32_t CS_VIA_PT      = 1u << 17;
+constexpr uint32_t CS_USES_PT     = 1u << 18;
+constexpr uint32_t CS_COMPLIANT   = 1u << 19;
+constexpr uint32_t CS_SAME_AREA   = 1u << 20;
+constexpr uint32_t CS_ABSENT      = 1u << 31;
+constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 2
+constexpr uint32_t MAX_STEPS      = 0xFFFFu - EXPOSURE_BIAS - 1;
+
+// device-resident control block: the scalar part of Simulator / InterventionStatus / StatisticsRecorder
+struct Ctrl {
+    uint32_t t;              // time step being executed (1-based, statistics.rs:167)
+    uint32_t at_work;        // current_building_position == workplace_code for everyone (citizen.rs:186-201)
+    uint32_t pt_mode;        // ESIM_PT_* of every uses_public_transport citizen during step t
+    uint32_t lockdown_some, lockdown_hours;   // InterventionStatus::lockdown
+    uint32_t vax_some, vax_hours;             // InterventionStatus::vaccination
+    uint32_t mask_kind, mask_hours;           // InterventionStatus::mask_status
+    uint32_t vax_start_step; // step whose apply_interventions took the eligible snapshot
+    uint32_t n_elig;         // |citizens_eligible_for_vaccine|
+    uint32_t vax_all_pending;// every eligible citizen was chosen at the end of step t-1: applied by k_update
+    uint32_t finished;       // !disease_exists(): later launches are no-ops
+    uint32_t error;          // sticky ESIM_ERR_* raised on the device (as a positive number)
+    uint32_t tally[5];       // S,E,I,R,V of step t before the exposure adjustment (statistics.rs:256-272)
+    uint32_t new_exp_bldg;   // successful building exposures of step t
+    uint32_t new_exp_pt;     // successful public-transport exposures of step t
+    uint32_t vaccinated_now;
+    uint32_t pad[9];
+};
+
+struct ModelParams {
+    uint32_t exposed_time, infected_time, vaccination_rate, bus_capacity;
+    double th_lockdown, th_vaccination, th_mask_pt, th_mask_everywhere;
+    uint32_t seed_lo, seed_hi;
+    uint32_t n_global_citizens, shard_lo;
+};
+
+// everything a kernel needs, passed by value
+struct DevView {
+    uint32_t n;            // citizens of this shard
+    uint32_t n_pad;        // n rounded up to a multiple of 4
+    uint32_t n_bldg, n_rooms, n_cells;
+    uint32_t n_routes, n_riders;
+    uint32_t record_buses;
+    uint32_t* cstate;      // [n_pad]
+    const uint32_t* home_cell;   // [n_pad] building id
+    const uint32_t* work_cell;   // [n_pad] building id, or n_bldg + room id for school members
+    const uint32_t* global_id;   // [n_pad]
+    const uint32_t* room_parent; // [n_rooms] school building of a room
+    uint32_t* cnt;         // [n_cells] infected occupants present per building / room (zeroed every step)
+    const unsigned long long* thr;  // [2][256] integer trial thresholds
+    // public transport
+    const uint32_t* route_off;   // [n_routes + 1]
+    const uint32_t* riders;      // [n_riders] citizen index, grouped by route, ascending inside a route
+    uint32_t* pt_key;      // [n_riders] scratch: shuffle keys
+    uint32_t* pt_bus;      // [n_riders] scratch: bus of each rider
+    uint32_t* pt_buscnt;   // [n_riders] scratch: infected riders per bus (route_off[r] + bus)
+    uint32_t* rec_bus;     // [n] optional record: bus index per citizen
+    uint32_t* rec_businf;  // [n] optional record: infected on that bus
+    Ctrl* ctrl;
+    EsimStepStats* stats;  // [max_steps]
+    uint32_t max_steps;
+    ModelParams mp;
+};
+
+void launch_update(const DevView& v, cudaStream_t s);
+void launch_expose(const DevView& v, cudaStream_t s);
+void launch_pt(const DevView& v, cudaStream_t s);
+void launch_tail(const DevView& v, cudaStream_t s);
+int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as int
+int  sm_count();
+
+}  // namespace esim

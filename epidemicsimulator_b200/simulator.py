@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference's `Simulator` (sim/src/simulator.rs:87-152) over the C ABI of libesim_b200.so.
+
+    sim = Simulator.from_population(pop)      # impl From<SimulatorBuilder> for Simulator (simulator.rs:601-644)
+    alive = sim.step()                        # Simulator::step  (simulator.rs:131-152)
+    sim.simulate("statistics_results/x/")     # Simulator::simulate (simulator.rs:108-127), writes the 4 JSON dumps
+
+Everything is computed by the CUDA kernels; this module only marshals buffers.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _abi
+from ._lib import cuda_lib
+from .population import Population
+
+DEBUG_ITERATION_PRINT = 50  # sim/src/config.rs:34
+
+
+def default_config(**overrides) -> _abi.EsimConfig:
+    """DiseaseModel::covid() + default intervention thresholds (disease.rs:118-129, interventions.rs:50-57,71-78)."""
+    cfg = _abi.EsimConfig()
+    rc = cuda_lib().esim_default_config(C.byref(cfg))
+    if rc < 0:
+        raise _abi.SimError(rc, "esim_default_config")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError("unknown config field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class DiseaseModel:
+    """sim/src/disease.rs:97-129"""
+
+    @staticmethod
+    def covid(**overrides) -> _abi.EsimConfig:
+        return default_config(**overrides)
+
+
+class Simulator:
+    def __init__(self, cfg: Optional[_abi.EsimConfig] = None, **overrides):
+        self._lib = cuda_lib()
+        self.cfg = cfg if cfg is not None else default_config(**overrides)
+        self._h = C.c_void_p()
+        rc = self._lib.esim_create(C.byref(self.cfg), C.byref(self._h))
+        if rc < 0:
+            raise _abi.SimError(rc, (self._lib.esim_last_error(None) or b"").decode())
+        self.pop: Optional[Population] = None
+        self.last_stats: Optional[_abi.EsimStepStats] = None
+
+    # -- construction ---------------------------------------------------------------------------------
+    @classmethod
+    def from_population(cls, pop: Population, cfg: Optional[_abi.EsimConfig] = None, **overrides) -> "Simulator":
+        sim = cls(cfg, **overrides)
+        sim.import_population(pop)
+        return sim
+
+    def import_population(self, pop: Population) -> None:
+        soa = pop.as_soa()
+        self._check(self._lib.esim_import_population(self._h, C.byref(soa)))
+        self.pop = pop
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.esim_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise _abi.SimError(rc, (self._lib.esim_last_error(self._h) or b"").decode())
+        return rc
+
+    # -- stepping --------------------------------------------------------------------------------------
+    def step(self, timed: bool = False) -> bool:
+        """Applies a single time step; returns False once the disease has disappeared (simulator.rs:131-152)."""
+        s = _abi.EsimStepStats()
+        fn = self._lib.esim_step_timed if timed else self._lib.esim_step
+        rc = self._check(fn(self._h, C.byref(s)))
+        self.last_stats = s
+        return rc == 1
+
+    def run(self, max_steps: int) -> int:
+        """Up to `max_steps` steps without leaving the device; returns the number of steps executed."""
+        n = C.c_uint32(0)
+        self._check(self._lib.esim_run(self._h, int(max_steps), C.byref(n)))
+        return int(n.value)
+
+    def simulate(self, output_name: Optional[str] = None, area_codes=None, verbose: bool = True) -> None:
+        """Simulator::simulate (simulator.rs:108-127): until the disease is eradicated or max_time_step, then dump."""
+        start = time.time()
+        done = 0
+        while done < self.cfg.max_time_step:
+            n = self.run(min(DEBUG_ITERATION_PRINT, self.cfg.max_time_step - done))
+            done += n
+            if n == 0:
+                break
+            if verbose:
+                st = self.statistics(done - 1, 1)
+                print("Completed %3d time steps, in: %6s seconds  Statistics: %s" % (
+                    DEBUG_ITERATION_PRINT, "%.2f" % (time.time() - start), dict(zip(_abi.STATS_FIELDS[:6], st[0][:6]))))
+                start = time.time()
+            if n < DEBUG_ITERATION_PRINT:
+                break
+        if output_name is not None:
+            self.dump_statistics(output_name, area_codes)
+
+    @property
+    def steps_done(self) -> int:
+        return self._check(self._lib.esim_steps_done(self._h))
+
+    # -- read-outs ---------------------------------------------------------------------------------------
+    def statistics(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """StatisticsRecorder::global_stats (+ intervention state) as an int64 matrix, one row per step."""
+        if count is None:
+            count = max(self.steps_done - first, 0)
+        if count <= 0:
+            return np.zeros((0, len(_abi.STATS_FIELDS)), np.int64)
+        buf = np.zeros((count, len(_abi.STATS_FIELDS)), np.uint32)
+        n = self._check(self._lib.esim_read_stats(self._h, first, count, buf.ctypes.data_as(C.POINTER(_abi.EsimStepStats))))
+        return buf[:n].astype(np.int64)
+
+    def state(self) -> Dict[str, np.ndarray]:
+        n = self.pop.n_citizens
+        out = dict(status=np.zeros(n, np.uint8), timer=np.zeros(n, np.uint16), current_bldg=np.zeros(n, np.uint32),
+                   on_pt=np.zeros(n, np.uint8), vax_eligible=np.zeros(n, np.uint8))
+        v = _abi.EsimStateView()
+        v.status = out["status"].ctypes.data_as(_abi.u8p)
+        v.timer = out["timer"].ctypes.data_as(_abi.u16p)
+        v.current_bldg = out["current_bldg"].ctypes.data_as(_abi.u32p)
+        v.on_pt = out["on_pt"].ctypes.data_as(_abi.u8p)
+        v.vax_eligible = out["vax_eligible"].ctypes.data_as(_abi.u8p)
+        self._check(self._lib.esim_read_state(self._h, C.byref(v)))
+        return out
+
+    def building_counts(self):
+        b = np.zeros(self.pop.n_buildings, np.uint32)
+        r = np.zeros(max(self.pop.n_rooms, 1), np.uint32)
+        self._check(self._lib.esim_read_building_counts(self._h, b.ctypes.data_as(_abi.u32p), r.ctypes.data_as(_abi.u32p)))
+        return b, r[:self.pop.n_rooms]
+
+    def buses(self):
+        n = self.pop.n_citizens
+        idx = np.zeros(n, np.uint32)
+        inf = np.zeros(n, np.uint32)
+        self._check(self._lib.esim_read_buses(self._h, idx.ctypes.data_as(_abi.u32p), inf.ctypes.data_as(_abi.u32p)))
+        return idx, inf
+
+    def inject_rng(self, seed: int) -> None:
+        self._check(self._lib.esim_inject_rng(self._h, seed))
+
+    def timings(self) -> Dict[str, float]:
+        t = _abi.EsimTimings()
+        self._check(self._lib.esim_get_timings(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in _abi.EsimTimings._fields_ if n != "reserved"}
+
+    def dump_statistics(self, directory: str, area_codes=None) -> None:
+        """StatisticsRecorder::dump_to_file (statistics.rs:113-150); `directory` is used as a prefix like the reference's."""
+        codes = None
+        if area_codes is not None:
+            arr = (C.c_char_p * len(area_codes))(*[c.encode() for c in area_codes])
+            codes = arr
+        self._check(self._lib.esim_dump_statistics(self._h, directory.encode(), codes))

@@ -28,6 +28,7 @@ NO_ROOM = 0xFFFFFFFF
 NONE_U32 = 0xFFFFFFFF
 CFG_RECORD_BUSES = 0x1
 CFG_NO_GRAPH = 0x2
+CFG_FLUSH_L2 = 0x4
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)

@@ -61,6 +61,7 @@ struct EsimSim {
     DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt, route_off, riders, pt_key, pt_bus, pt_buscnt,
         rec_bus, rec_businf;
     DevBuf<unsigned long long> thr;
+    DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
     DevBuf<Ctrl> ctrl;
     DevBuf<EsimStepStats> stats;
     Ctrl* h_ctrl = nullptr;             // pinned
@@ -88,7 +89,7 @@ struct EsimSim {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
-        rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release();
+        rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
         if (h_ctrl) cudaFreeHost(h_ctrl);
         if (h_stat) cudaFreeHost(h_stat);
         if (stream) cudaStreamDestroy(stream);
@@ -352,6 +353,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
         if (rec) { s->rec_bus.alloc(N); s->rec_businf.alloc(N); }
         s->thr.alloc(512); s->ctrl.alloc(1); s->stats.alloc(s->cfg.max_time_step);
+        if (s->cfg.flags & ESIM_CFG_FLUSH_L2) s->l2_scratch.alloc((size_t)256 << 20);  // 2x the 126 MB L2
         CK(cudaMemcpyAsync(s->cstate.p, cstate.data(), s->cstate.bytes(), cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(s->home_cell.p, home.data(), s->home_cell.bytes(), cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(s->work_cell.p, work.data(), s->work_cell.bytes(), cudaMemcpyHostToDevice, s->stream));
@@ -411,6 +413,7 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
         const uint32_t before = s->steps_done;
         if (timed) {
             const DevView& v = s->v;
+            if (s->l2_scratch.p) CK(cudaMemsetAsync(s->l2_scratch.p, (int)(s->steps_done & 0xFF), s->l2_scratch.bytes(), s->stream));
             CK(cudaEventRecord(s->ev[0], s->stream));
             CK(cudaMemsetAsync(v.cnt, 0, (size_t)v.n_cells * sizeof(uint32_t), s->stream));
             launch_update(v, s->stream);

@@ -52,7 +52,7 @@ def build_host(force: bool = False) -> Path:
     deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h"]
     if not force and _newer(HOST_LIB, deps):
         return HOST_LIB
-    _run([host_compiler(), "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", str(INCLUDE), "-o", str(HOST_LIB)]
+    _run([host_compiler(), "-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-Wall", "-I", str(INCLUDE), "-o", str(HOST_LIB)]
          + [str(s) for s in srcs])
     return HOST_LIB
 
@@ -70,7 +70,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-ccbin", host_compiler(),
+           "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-ccbin", host_compiler(),
            "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(CUDA_LIB)]
     if verbose:
         cmd += ["-Xptxas", "-v"]

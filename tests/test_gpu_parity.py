@@ -93,3 +93,144 @@ def test_vaccinate_whole_eligible_set():
     pop = synthetic_population(n_areas=4, areas_per_school=2, initial_infected=30)
     seen = _lockstep(pop, 400, state_every=5, exposure_chance=0.05, vaccination_rate=1530, seed=5)
     assert seen["vax"]
+
+
+def _pop_infected_at(hour_of_onset, share=0.02, **kw):
+    pop = synthetic_population(n_areas=24, areas_per_school=6, initial_infected=0, **kw)
+    rng = np.random.default_rng(0)
+    pick = rng.random(pop.n_citizens) < share
+    pop.status[pick] = _abi.STATUS_EXPOSED
+    pop.timer[pick] = 96 - (hour_of_onset - 1)
+    return pop
+
+
+def test_lockdown_freezes_riders_on_the_bus():
+    # lockdown decided at the end of hour 8: riders stay on public transport and are re-shuffled every hour
+    seen = _lockstep(_pop_infected_at(8, cross_area_fraction=0.5), 120, state_every=6, exposure_chance=0.01, seed=21)
+    assert seen["lockdown"] and seen["pt_exp"]
+
+
+def test_lockdown_during_work_hours():
+    seen = _lockstep(_pop_infected_at(11), 120, state_every=6, exposure_chance=0.01, seed=22)
+    assert seen["lockdown"]
+
+
+def test_imported_mid_epidemic_state():
+    # every status with every legal timer value at import
+    pop = synthetic_population(n_areas=16, areas_per_school=4)
+    rng = np.random.default_rng(5)
+    pop.status[:] = rng.integers(0, 5, pop.n_citizens).astype(np.uint8)
+    pop.timer[:] = 0
+    e = pop.status == _abi.STATUS_EXPOSED
+    i = pop.status == _abi.STATUS_INFECTED
+    pop.timer[e] = rng.integers(0, 97, e.sum()).astype(np.uint16)
+    pop.timer[i] = rng.integers(0, 337, i.sum()).astype(np.uint16)
+    _lockstep(pop, 450, state_every=9, seed=9, lockdown_threshold=0.5)
+
+
+def test_york_shape_run_and_statistics_dump(tmp_path):
+    import json
+    pop = synthetic_population(n_areas=637)
+    cfg = dict(exposure_chance=0.003, seed=4)
+    sim = _sim(pop, **cfg)
+    orc = Oracle(pop, default_config(**cfg))
+    n = sim.run(900)
+    assert n == orc.run(900) == 900
+    st = sim.statistics()
+    assert np.array_equal(st, orc.stats())
+    _compare_state(sim, orc, n)
+    out = str(tmp_path / "stats") + "/"
+    sim.dump_statistics(out)
+    gs = json.load(open(out + "global_stats.json"))
+    assert len(gs) == n + 1 and gs[-1] == dict(time_step=n + 1, susceptible=0, exposed=0, infected=0, recovered=0, vaccinated=0)
+    assert list(gs[0].keys()) == ["time_step", "susceptible", "exposed", "infected", "recovered", "vaccinated"]
+    assert [g["infected"] for g in gs[:-1]] == st[:, 3].tolist()
+    ex = json.load(open(out + "exposures.json"))
+    for a in range(pop.n_areas):
+        want = orc.area_exposures(a).tolist()
+        assert ex["OutputArea"].get(str(a), []) == want, a
+    assert len(json.load(open(out + "timings.json"))) == n and len(json.load(open(out + "memory.json"))) == n
+    sim.close(); orc.close()
+
+
+def test_full_size_population_lockstep_with_oracle():
+    # BASELINE configs[1]: 3.5 M citizens; 30 hours cover the commute, work and return phases
+    pop = synthetic_population(n_areas=11300, areas_per_school=67)
+    cfg = dict(seed=0, exposure_chance=0.01)
+    sim = _sim(pop, **cfg)
+    orc = Oracle(pop, default_config(**cfg))
+    for k in range(30):
+        sim.step()
+        _, so = orc.step()
+        assert sim.last_stats.as_tuple() == so.as_tuple(), k
+    bg, rg = sim.building_counts()
+    bo, ro = orc.building_counts()
+    assert np.array_equal(bg, bo) and np.array_equal(rg, ro)
+    _compare_state(sim, orc, 30)
+    sim.close(); orc.close()
+
+
+def test_full_size_run_properties():
+    pop = synthetic_population(n_areas=11300, areas_per_school=67)
+    sim = _sim(pop, seed=1)
+    n = sim.run(5000)
+    st = sim.statistics()
+    assert n == 5000 and st.shape[0] == 5000
+    assert (st[:, 1:6].sum(1) == pop.n_citizens).all()                 # S+E+I+R+V conserved
+    assert (np.diff(st[:, 0]) == 1).all() and st[0, 0] == 1
+    s = sim.state()
+    assert np.bincount(s["status"], minlength=5).tolist() == st[-1, 1:6].tolist()  # tally == checksum of the final state
+    assert s["timer"][s["status"] == _abi.STATUS_EXPOSED].max(initial=0) <= 96
+    assert s["timer"][s["status"] == _abi.STATUS_INFECTED].max(initial=0) <= 336
+    again = _sim(pop, seed=1)
+    again.run(5000)
+    assert np.array_equal(again.statistics(), st)                       # deterministic for a seed
+    other = _sim(pop, seed=2)
+    other.run(600)
+    assert not np.array_equal(other.statistics(), st[:600])
+    sim.close(); again.close(); other.close()
+
+
+def test_error_paths():
+    from epidemicsimulator_b200.simulator import Simulator
+    sim = Simulator()
+    with pytest.raises(_abi.SimError) as e:
+        sim.step()
+    assert e.value.code == _abi.ERR_INITIALIZATION
+    pop = synthetic_population(n_areas=4, areas_per_school=2)
+    bad = pop.copy()
+    bad.room[:] = _abi.NO_ROOM                                          # students without a class
+    with pytest.raises(_abi.SimError) as e:
+        Simulator.from_population(bad)
+    assert e.value.code == _abi.ERR_INVALID_POPULATION
+    bad = pop.copy()
+    bad.work_bldg[0] = pop.n_buildings + 5
+    with pytest.raises(_abi.SimError) as e:
+        Simulator.from_population(bad)
+    assert e.value.code == _abi.ERR_MISSING_CITIZEN
+    with pytest.raises(_abi.SimError) as e:
+        Simulator(default_config(max_time_step=0))
+    assert e.value.code == _abi.ERR_INVALID_ARGUMENT
+    ok = Simulator.from_population(pop, default_config(max_time_step=5))
+    assert ok.run(100) == 5
+    with pytest.raises(_abi.SimError) as e:
+        ok.step()
+    assert e.value.code == _abi.ERR_SIMULATION
+    sim.close(); ok.close()
+
+
+def test_timed_steps_equal_graph_steps():
+    pop = synthetic_population(n_areas=50, areas_per_school=10)
+    cfg = dict(exposure_chance=0.01, seed=8)
+    a = _sim(pop, flags=_abi.CFG_FLUSH_L2, **cfg)
+    b = _sim(pop, **cfg)
+    c = _sim(pop, flags=_abi.CFG_NO_GRAPH, **cfg)
+    for _ in range(100):
+        a.step(timed=True)
+    b.run(100)
+    for _ in range(100):
+        c.step()
+    assert np.array_equal(a.statistics(), b.statistics()) and np.array_equal(a.statistics(), c.statistics())
+    t = a.timings()
+    assert t["steps"] == 100 and t["total"] > 0 and abs(t["generate_exposures"] + t["apply_exposures"] + t["apply_interventions"] - t["total"]) < 1e-6
+    a.close(); b.close(); c.close()

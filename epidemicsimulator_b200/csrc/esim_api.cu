@@ -312,7 +312,9 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
                     if (tm > ti) throw ApiError{ESIM_ERR_INVALID_POPULATION, "Infected timer above infected_time"};
                     word |= EXPOSURE_BIAS - (te + 1 + tm); break;
                 case ESIM_STATUS_RECOVERED: word |= EXPOSURE_BIAS - (te + ti + 2); break;
-                case ESIM_STATUS_VACCINATED: word |= CS_VACCINATED; break;
+                // vaccinated before the run: never Susceptible at the snapshot of the vaccination programme, so the
+                // exposure field is made non-zero (as for Recovered), which keeps it out of the eligible set
+                case ESIM_STATUS_VACCINATED: word |= CS_VACCINATED | (EXPOSURE_BIAS - (te + ti + 2)); break;
                 default: throw ApiError{ESIM_ERR_INVALID_POPULATION, "unknown disease status"};
             }
             cstate[i] = word;

@@ -29,6 +29,8 @@ NONE_U32 = 0xFFFFFFFF
 CFG_RECORD_BUSES = 0x1
 CFG_NO_GRAPH = 0x2
 CFG_FLUSH_L2 = 0x4
+EXCH_COUNTS = 0
+EXCH_TAIL = 1
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
@@ -64,7 +66,7 @@ class EsimPopulationSoA(C.Structure):
         ("n_global_citizens", C.c_uint32),
         ("n_shared_bldgs", C.c_uint32),
         ("n_shared_rooms", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("n_shards", C.c_uint32),
         ("home_bldg", u32p),
         ("work_bldg", u32p),
         ("room", u32p),

@@ -67,6 +67,14 @@ def cuda_lib() -> C.CDLL:
     lib.esim_inject_rng.argtypes = [vp, C.c_uint64]
     lib.esim_dump_statistics.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p)]
     lib.esim_get_timings.argtypes = [vp, C.POINTER(_abi.EsimTimings)]
+    lib.esim_comm_unique_id.argtypes = [_abi.u8p]
+    lib.esim_comm_init.argtypes = [vp, _abi.u8p, C.c_uint32, C.c_uint32]
+    lib.esim_shard_step_begin.argtypes = [vp]
+    lib.esim_shard_step_middle.argtypes = [vp]
+    lib.esim_shard_step_end.argtypes = [vp, C.POINTER(_abi.EsimStepStats)]
+    lib.esim_exchange_words.argtypes = [vp, C.c_int]
+    lib.esim_exchange_get.argtypes = [vp, C.c_int, _abi.u32p]
+    lib.esim_exchange_put.argtypes = [vp, C.c_int, _abi.u32p]
     lib.esim_last_error.argtypes = [vp]
     lib.esim_last_error.restype = C.c_char_p
     if lib.esim_abi_version() != _abi.ABI_VERSION:

@@ -2,12 +2,14 @@
 // device layout from the imported population; steps / runs / reads back.  Host-side counterpart of
 // `impl From<SimulatorBuilder> for Simulator` + `Simulator::{step, simulate}` + `StatisticsRecorder::dump_to_file`.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <sys/stat.h>
 
 #include <algorithm>
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -32,6 +34,11 @@ struct CudaError { cudaError_t e; const char* what; int line; };
     } while (0)
 
 struct ApiError { int code; std::string msg; };
+#define NCCLCK(call)                                                                                   \
+    do {                                                                                                \
+        int _r = (call);                                                                                \
+        if (_r != 0) throw ApiError{ESIM_ERR_COMM, std::string("NCCL: ") + (nccl_api() && nccl_api()->GetErrorString ? nccl_api()->GetErrorString(_r) : "error") + " in " #call}; \
+    } while (0)
 
 template <class T>
 struct DevBuf {
@@ -51,6 +58,43 @@ struct DevBuf {
 
 constexpr int GRAPH_DAY = 24;  // steps captured in the bulk graph
 
+// ---- NCCL through dlopen: the library is optional (single-GPU runs never touch it) ------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ struct UniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct UniqueId { char internal[128]; };
+constexpr int NCCL_UINT32 = 3, NCCL_SUM = 0;
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (api.lib) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+            if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.GroupStart || !api.GroupEnd) api.lib = nullptr;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+
 }  // namespace
 
 struct EsimSim {
@@ -58,10 +102,13 @@ struct EsimSim {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevView v{};
-    DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt, route_off, riders, pt_key, pt_bus, pt_buscnt,
+    DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt0, cnt1, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
         rec_bus, rec_businf;
     DevBuf<unsigned long long> thr;
     DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
+    DevBuf<uint32_t> exch, vax_cand;    // sharded runs
+    uint32_t world = 1, rank = 0, n_shared_bldgs = 0, n_shared_rooms = 0;
+    void* comm = nullptr;               // ncclComm_t
     DevBuf<Ctrl> ctrl;
     DevBuf<EsimStepStats> stats;
     Ctrl* h_ctrl = nullptr;             // pinned
@@ -71,8 +118,9 @@ struct EsimSim {
     bool imported = false;
     uint32_t steps_done = 0;            // steps executed (recorded) so far
     bool finished = false;
-    cudaGraph_t graph1 = nullptr, graph_day = nullptr;
-    cudaGraphExec_t exec1 = nullptr, exec_day = nullptr;
+    // index = parity of the first time step of the graph (the count buffers alternate, and NCCL needs fixed pointers)
+    cudaGraph_t graph1[2] = {nullptr, nullptr}, graph_day[2] = {nullptr, nullptr};
+    cudaGraphExec_t exec1[2] = {nullptr, nullptr}, exec_day[2] = {nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     EsimTimings timings{};
     std::vector<float> step_total_ms;   // per recorded step, 0 when not measured
@@ -80,14 +128,24 @@ struct EsimSim {
     size_t device_bytes = 0;
     std::string err;
 
+    void destroy_graphs() {
+        if (exec1[1] == exec1[0]) exec1[1] = nullptr;          // one graph serves both parities on a single shard
+        if (exec_day[1] == exec_day[0]) exec_day[1] = nullptr;
+        for (int p = 0; p < 2; ++p) {
+            if (exec1[p]) cudaGraphExecDestroy(exec1[p]);
+            if (exec_day[p]) cudaGraphExecDestroy(exec_day[p]);
+            if (graph1[p]) cudaGraphDestroy(graph1[p]);
+            if (graph_day[p]) cudaGraphDestroy(graph_day[p]);
+            exec1[p] = exec_day[p] = nullptr; graph1[p] = graph_day[p] = nullptr;
+        }
+    }
     ~EsimSim() {
         if (device >= 0) cudaSetDevice(device);
-        if (exec1) cudaGraphExecDestroy(exec1);
-        if (exec_day) cudaGraphExecDestroy(exec_day);
-        if (graph1) cudaGraphDestroy(graph1);
-        if (graph_day) cudaGraphDestroy(graph_day);
+        destroy_graphs();
+        if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
+        exch.release(); vax_cand.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt.release();
+        cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt0.release(); cnt1.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
         if (h_ctrl) cudaFreeHost(h_ctrl);
@@ -146,26 +204,49 @@ void build_thresholds(const EsimConfig& c, unsigned long long out[512]) {
     }
 }
 
-void enqueue_step(EsimSim* s) {
+// the two all-reduces of a sharded step, on the handle's stream
+void allreduce_counts(EsimSim* s, uint32_t parity) {
+    NcclApi* n = nccl_api();
+    uint32_t* cnt = s->v.cnt[parity];
+    NCCLCK(n->GroupStart());
+    if (s->n_shared_bldgs) NCCLCK(n->AllReduce(cnt, cnt, s->n_shared_bldgs, NCCL_UINT32, NCCL_SUM, s->comm, s->stream));
+    if (s->n_shared_rooms)
+        NCCLCK(n->AllReduce(cnt + s->v.n_bldg, cnt + s->v.n_bldg, s->n_shared_rooms, NCCL_UINT32, NCCL_SUM, s->comm, s->stream));
+    NCCLCK(n->GroupEnd());
+}
+void allreduce_tail(EsimSim* s) {
+    NCCLCK(nccl_api()->AllReduce(s->exch.p, s->exch.p, EXCH_WORDS, NCCL_UINT32, NCCL_SUM, s->comm, s->stream));
+}
+
+// one time step whose number has the given parity
+void enqueue_step(EsimSim* s, uint32_t parity) {
     const DevView& v = s->v;
-    CK(cudaMemsetAsync(v.cnt, 0, (size_t)v.n_cells * sizeof(uint32_t), s->stream));
     launch_update(v, s->stream);
+    if (s->world > 1 && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
     launch_expose(v, s->stream);
     launch_pt(v, s->stream);
+    if (s->world > 1) {
+        launch_vax_prepare(v, s->stream);
+        allreduce_tail(s);
+    }
     launch_tail(v, s->stream);
 }
 
 void capture_graphs(EsimSim* s) {
-    for (int which = 0; which < 2; ++which) {
-        const int steps = which == 0 ? 1 : GRAPH_DAY;
-        cudaGraph_t g = nullptr;
-        CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-        for (int i = 0; i < steps; ++i) enqueue_step(s);
-        CK(cudaStreamEndCapture(s->stream, &g));
-        cudaGraphExec_t e = nullptr;
-        CK(cudaGraphInstantiate(&e, g, 0));
-        if (which == 0) { s->graph1 = g; s->exec1 = e; } else { s->graph_day = g; s->exec_day = e; }
-    }
+    s->destroy_graphs();
+    const int variants = s->world > 1 ? 2 : 1;  // without NCCL the kernels pick the buffer themselves: one graph serves both
+    for (int parity = 0; parity < variants; ++parity)
+        for (int which = 0; which < 2; ++which) {
+            const int steps = which == 0 ? 1 : GRAPH_DAY;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < steps; ++i) enqueue_step(s, (uint32_t)(parity + i) & 1u);
+            CK(cudaStreamEndCapture(s->stream, &g));
+            cudaGraphExec_t e = nullptr;
+            CK(cudaGraphInstantiate(&e, g, 0));
+            if (which == 0) { s->graph1[parity] = g; s->exec1[parity] = e; } else { s->graph_day[parity] = g; s->exec_day[parity] = e; }
+        }
+    if (variants == 1) { s->exec1[1] = s->exec1[0]; s->exec_day[1] = s->exec_day[0]; }
 }
 
 void fetch_ctrl(EsimSim* s) {
@@ -348,12 +429,18 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
 
         // ---- device allocation + upload ----
         s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad); s->gid.alloc(n_pad);
-        s->room_parent.alloc(std::max<uint32_t>(R, 1)); s->cnt.alloc((size_t)B + R);
+        s->room_parent.alloc(std::max<uint32_t>(R, 1)); s->cnt0.alloc((size_t)B + R + 4); s->cnt1.alloc((size_t)B + R + 4);
         s->route_off.alloc(route_off.size()); s->riders.alloc(std::max<size_t>(riders.size(), 1));
         s->pt_key.alloc(std::max<size_t>(riders.size(), 1)); s->pt_bus.alloc(std::max<size_t>(riders.size(), 1));
         s->pt_buscnt.alloc(std::max<size_t>(riders.size(), 1));
         const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
         if (rec) { s->rec_bus.alloc(N); s->rec_businf.alloc(N); }
+        const uint32_t n_update_blocks = update_blocks(n_pad);
+        s->tally_partial.alloc((size_t)n_update_blocks * 8);
+        s->world = p->n_shards > 1 ? p->n_shards : 1;
+        s->n_shared_bldgs = p->n_shared_bldgs; s->n_shared_rooms = p->n_shared_rooms;
+        s->exch.alloc(EXCH_WORDS); s->vax_cand.alloc(ESIM_VAX_SHARD_DRAWS);
+        CK(cudaMemsetAsync(s->exch.p, 0, s->exch.bytes(), s->stream));
         s->thr.alloc(512); s->ctrl.alloc(1); s->stats.alloc(s->cfg.max_time_step);
         if (s->cfg.flags & ESIM_CFG_FLUSH_L2) s->l2_scratch.alloc((size_t)256 << 20);  // 2x the 126 MB L2
         CK(cudaMemcpyAsync(s->cstate.p, cstate.data(), s->cstate.bytes(), cudaMemcpyHostToDevice, s->stream));
@@ -364,7 +451,9 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         CK(cudaMemcpyAsync(s->route_off.p, route_off.data(), s->route_off.bytes(), cudaMemcpyHostToDevice, s->stream));
         if (!riders.empty()) CK(cudaMemcpyAsync(s->riders.p, riders.data(), riders.size() * 4, cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(s->thr.p, thr, sizeof(thr), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemsetAsync(s->cnt.p, 0, s->cnt.bytes(), s->stream));
+        CK(cudaMemsetAsync(s->cnt0.p, 0, s->cnt0.bytes(), s->stream));
+        CK(cudaMemsetAsync(s->tally_partial.p, 0, s->tally_partial.bytes(), s->stream));
+        CK(cudaMemsetAsync(s->cnt1.p, 0, s->cnt1.bytes(), s->stream));
         CK(cudaMemsetAsync(s->stats.p, 0, s->stats.bytes(), s->stream));
         if (rec) {
             CK(cudaMemsetAsync(s->rec_bus.p, 0xFF, s->rec_bus.bytes(), s->stream));
@@ -372,6 +461,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         }
         Ctrl c0;
         std::memset(&c0, 0, sizeof(c0));
+        c0.eager_expose = 1;
         c0.t = 1;  // the first hour is 1 (statistics.rs:167); everybody starts at home, off public transport (citizen.rs:156-160)
         std::memcpy(s->h_ctrl, &c0, sizeof(c0));
         CK(cudaMemcpyAsync(s->ctrl.p, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
@@ -385,9 +475,11 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.n = N; v.n_pad = n_pad; v.n_bldg = B; v.n_rooms = R; v.n_cells = B + R;
         v.n_routes = n_routes; v.n_riders = (uint32_t)riders.size(); v.record_buses = rec ? 1u : 0u;
         v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
-        v.room_parent = s->room_parent.p; v.cnt = s->cnt.p; v.thr = s->thr.p;
+        v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt0.p; v.cnt[1] = s->cnt1.p; v.thr = s->thr.p;
         v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
         v.pt_buscnt = s->pt_buscnt.p; v.rec_bus = s->rec_bus.p; v.rec_businf = s->rec_businf.p;
+        v.world = s->world; v.exch = s->exch.p; v.vax_cand = s->vax_cand.p;
+        v.tally_partial = s->tally_partial.p; v.n_update_blocks = n_update_blocks;
         v.ctrl = s->ctrl.p; v.stats = s->stats.p; v.max_steps = s->cfg.max_time_step;
         v.mp.exposed_time = te; v.mp.infected_time = ti; v.mp.vaccination_rate = s->cfg.vaccination_rate;
         v.mp.bus_capacity = s->cfg.bus_capacity;
@@ -397,9 +489,9 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.mp.n_global_citizens = n_global; v.mp.shard_lo = shard_lo;
 
         s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->gid.bytes() +
-                          s->room_parent.bytes() + s->cnt.bytes() + s->route_off.bytes() + s->riders.bytes() * 4 +
+                          s->room_parent.bytes() + s->cnt0.bytes() * 2 + s->route_off.bytes() + s->riders.bytes() * 4 +
                           s->rec_bus.bytes() * 2 + s->stats.bytes();
-        if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(s);
+        if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH) && s->world == 1) capture_graphs(s);  // sharded: captured by esim_comm_init
         s->imported = true;
         s->steps_done = 0;
         s->finished = false;
@@ -413,23 +505,27 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
         if (s->steps_done >= s->cfg.max_time_step && !s->finished)
             throw ApiError{ESIM_ERR_SIMULATION, "max_time_step reached"};
         const uint32_t before = s->steps_done;
+        const uint32_t parity = (before + 1u) & 1u;
+        if (s->world > 1 && !s->comm)
+            throw ApiError{ESIM_ERR_COMM, "sharded handle: attach a communicator (esim_comm_init) or drive the esim_shard_step_* phases"};
         if (timed) {
             const DevView& v = s->v;
             if (s->l2_scratch.p) CK(cudaMemsetAsync(s->l2_scratch.p, (int)(s->steps_done & 0xFF), s->l2_scratch.bytes(), s->stream));
             CK(cudaEventRecord(s->ev[0], s->stream));
-            CK(cudaMemsetAsync(v.cnt, 0, (size_t)v.n_cells * sizeof(uint32_t), s->stream));
             launch_update(v, s->stream);
+            if (s->world > 1 && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
             CK(cudaEventRecord(s->ev[1], s->stream));
             launch_expose(v, s->stream);
             CK(cudaEventRecord(s->ev[2], s->stream));
             launch_pt(v, s->stream);
             CK(cudaEventRecord(s->ev[3], s->stream));
+            if (s->world > 1) { launch_vax_prepare(v, s->stream); allreduce_tail(s); }
             launch_tail(v, s->stream);
             CK(cudaEventRecord(s->ev[4], s->stream));
-        } else if (s->exec1) {
-            CK(cudaGraphLaunch(s->exec1, s->stream));
+        } else if (s->exec1[parity]) {
+            CK(cudaGraphLaunch(s->exec1[parity], s->stream));
         } else {
-            enqueue_step(s);
+            enqueue_step(s, parity);
         }
         if (!s->finished && before < s->cfg.max_time_step)
             CK(cudaMemcpyAsync(s->h_stat, s->stats.p + before, sizeof(EsimStepStats), cudaMemcpyDeviceToHost, s->stream));
@@ -470,17 +566,21 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
         uint32_t budget = std::min<uint32_t>(max_steps, s->cfg.max_time_step - std::min(s->cfg.max_time_step, start));
         // the loop is device-resident: the host only looks at the control block every few simulated days
         constexpr uint32_t CHUNK_DAYS = 8;
+        if (s->world > 1 && !s->comm)
+            throw ApiError{ESIM_ERR_COMM, "sharded handle: attach a communicator (esim_comm_init) or drive the esim_shard_step_* phases"};
         while (budget > 0 && !s->finished) {
             uint32_t queued = 0;
-            if (s->exec_day)
+            const uint32_t parity = (s->steps_done + 1u) & 1u;   // GRAPH_DAY is even: the parity is the same for every day
+            if (s->exec_day[parity])
                 for (uint32_t d = 0; d < CHUNK_DAYS && budget - queued >= (uint32_t)GRAPH_DAY; ++d) {
-                    CK(cudaGraphLaunch(s->exec_day, s->stream));
+                    CK(cudaGraphLaunch(s->exec_day[parity], s->stream));
                     queued += GRAPH_DAY;
                 }
             if (queued == 0) {
                 const uint32_t n = std::min<uint32_t>(budget, GRAPH_DAY);
                 for (uint32_t k = 0; k < n; ++k) {
-                    if (s->exec1) CK(cudaGraphLaunch(s->exec1, s->stream)); else enqueue_step(s);
+                    const uint32_t pk = (parity + k) & 1u;
+                    if (s->exec1[pk]) CK(cudaGraphLaunch(s->exec1[pk], s->stream)); else enqueue_step(s, pk);
                 }
                 queued = n;
             }
@@ -580,9 +680,10 @@ int esim_read_state(EsimSim* s, EsimStateView* view) {
 int esim_read_building_counts(EsimSim* s, uint32_t* bldg, uint32_t* room) {
     return guarded(s, [&]() -> int {
         require_ready(s);
-        if (bldg) CK(cudaMemcpyAsync(bldg, s->cnt.p, (size_t)s->v.n_bldg * 4, cudaMemcpyDeviceToHost, s->stream));
+        const uint32_t* cnt = s->v.cnt[s->steps_done & 1u];  // step t accumulates into cnt[t & 1]
+        if (bldg) CK(cudaMemcpyAsync(bldg, cnt, (size_t)s->v.n_bldg * 4, cudaMemcpyDeviceToHost, s->stream));
         if (room && s->v.n_rooms)
-            CK(cudaMemcpyAsync(room, s->cnt.p + s->v.n_bldg, (size_t)s->v.n_rooms * 4, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaMemcpyAsync(room, cnt + s->v.n_bldg, (size_t)s->v.n_rooms * 4, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         return ESIM_OK;
     });
@@ -608,11 +709,9 @@ int esim_inject_rng(EsimSim* s, uint64_t seed) {
             CK(cudaStreamSynchronize(s->stream));
             s->v.mp.seed_lo = (uint32_t)seed; s->v.mp.seed_hi = (uint32_t)(seed >> 32);
             // kernel parameters are baked into the captured graphs: re-capture
-            if (s->exec1) { cudaGraphExecDestroy(s->exec1); s->exec1 = nullptr; }
-            if (s->exec_day) { cudaGraphExecDestroy(s->exec_day); s->exec_day = nullptr; }
-            if (s->graph1) { cudaGraphDestroy(s->graph1); s->graph1 = nullptr; }
-            if (s->graph_day) { cudaGraphDestroy(s->graph_day); s->graph_day = nullptr; }
-            if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(s);
+            const bool had = s->exec1[0] != nullptr;
+            s->destroy_graphs();
+            if (had) capture_graphs(s);
         }
         return ESIM_OK;
     });
@@ -725,6 +824,107 @@ int esim_dump_statistics(EsimSim* s, const char* directory, const char* const* a
         return ESIM_OK;
     });
 }
+
+// ---- sharded runs ----------------------------------------------------------------------------------------
+int esim_comm_unique_id(uint8_t id[128]) {
+    return guarded(nullptr, [&]() -> int {
+        NcclApi* n = nccl_api();
+        if (!n) throw ApiError{ESIM_ERR_COMM, "libnccl.so.2 not found"};
+        if (!id) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null id"};
+        UniqueId u;
+        NCCLCK(n->GetUniqueId(&u));
+        std::memcpy(id, u.internal, 128);
+        return ESIM_OK;
+    });
+}
+
+int esim_comm_init(EsimSim* s, const uint8_t id[128], uint32_t rank, uint32_t world) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        NcclApi* n = nccl_api();
+        if (!n) throw ApiError{ESIM_ERR_COMM, "libnccl.so.2 not found"};
+        if (!id || world != s->world || rank >= world) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "rank / world do not match the imported shard"};
+        if (s->comm) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "communicator already attached"};
+        UniqueId u;
+        std::memcpy(u.internal, id, 128);
+        NCCLCK(n->CommInitRank(&s->comm, (int)world, u, (int)rank));
+        s->rank = rank;
+        // one eager all-reduce so that NCCL sets up its channels outside graph capture
+        allreduce_tail(s);
+        CK(cudaStreamSynchronize(s->stream));
+        CK(cudaMemsetAsync(s->exch.p, 0, s->exch.bytes(), s->stream));
+        if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(s);
+        return ESIM_OK;
+    });
+}
+
+int esim_shard_step_begin(EsimSim* s) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (s->steps_done >= s->cfg.max_time_step && !s->finished) throw ApiError{ESIM_ERR_SIMULATION, "max_time_step reached"};
+        launch_update(s->v, s->stream);
+        CK(cudaStreamSynchronize(s->stream));
+        return ESIM_OK;
+    });
+}
+
+int esim_shard_step_middle(EsimSim* s) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        launch_expose(s->v, s->stream);
+        launch_pt(s->v, s->stream);
+        launch_vax_prepare(s->v, s->stream);
+        CK(cudaStreamSynchronize(s->stream));
+        return ESIM_OK;
+    });
+}
+
+int esim_shard_step_end(EsimSim* s, EsimStepStats* out) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        const uint32_t before = s->steps_done;
+        launch_tail(s->v, s->stream);
+        if (!s->finished && before < s->cfg.max_time_step)
+            CK(cudaMemcpyAsync(s->h_stat, s->stats.p + before, sizeof(EsimStepStats), cudaMemcpyDeviceToHost, s->stream));
+        fetch_ctrl(s);
+        const int rc = after_steps(s);
+        if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
+        if (out) { if (s->steps_done > before) *out = *s->h_stat; else std::memset(out, 0, sizeof(*out)); }
+        return s->finished ? 0 : 1;
+    });
+}
+
+int esim_exchange_words(EsimSim* s, int which) {
+    if (!s || !s->imported) return ESIM_ERR_INITIALIZATION;
+    if (which == ESIM_EXCH_COUNTS) return (int)(s->n_shared_bldgs + s->n_shared_rooms);
+    if (which == ESIM_EXCH_TAIL) return (int)EXCH_WORDS;
+    return ESIM_ERR_INVALID_ARGUMENT;
+}
+
+static int exchange_copy(EsimSim* s, int which, uint32_t* host, bool to_host) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (!host) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null buffer"};
+        const cudaMemcpyKind kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+        auto cp = [&](uint32_t* dev, uint32_t* h, size_t words) {
+            if (!words) return;
+            if (to_host) CK(cudaMemcpyAsync(h, dev, words * 4, kind, s->stream)); else CK(cudaMemcpyAsync(dev, h, words * 4, kind, s->stream));
+        };
+        if (which == ESIM_EXCH_COUNTS) {
+            uint32_t* cnt = s->v.cnt[(s->steps_done + 1u) & 1u];  // the step in flight accumulates into cnt[t & 1]
+            cp(cnt, host, s->n_shared_bldgs);
+            cp(cnt + s->v.n_bldg, host + s->n_shared_bldgs, s->n_shared_rooms);
+        } else if (which == ESIM_EXCH_TAIL) {
+            cp(s->exch.p, host, EXCH_WORDS);
+        } else {
+            throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "unknown exchange vector"};
+        }
+        CK(cudaStreamSynchronize(s->stream));
+        return ESIM_OK;
+    });
+}
+int esim_exchange_get(EsimSim* s, int which, uint32_t* out) { return exchange_copy(s, which, out, true); }
+int esim_exchange_put(EsimSim* s, int which, const uint32_t* in) { return exchange_copy(s, which, const_cast<uint32_t*>(in), false); }
 
 const char* esim_last_error(EsimSim* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
 

@@ -32,6 +32,8 @@ constexpr uint32_t CS_SAME_AREA   = 1u << 20;
 constexpr uint32_t CS_ABSENT      = 1u << 31;
 constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 2
 constexpr uint32_t MAX_STEPS      = 0xFFFFu - EXPOSURE_BIAS - 1;
+#define ESIM_VAX_SHARD_DRAWS 8192u   // vaccination candidate draws a sharded run examines per step
+constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer, see k_vax_prepare
 
 // device-resident control block: the scalar part of Simulator / InterventionStatus / StatisticsRecorder
 struct Ctrl {
@@ -50,7 +52,9 @@ struct Ctrl {
     uint32_t new_exp_bldg;   // successful building exposures of step t
     uint32_t new_exp_pt;     // successful public-transport exposures of step t
     uint32_t vaccinated_now;
-    uint32_t pad[9];
+    uint32_t blocks_done;    // spare
+    uint32_t eager_expose;   // more than a quarter of the citizens are susceptible: k_expose loads cell ids eagerly
+    uint32_t pad[7];
 };
 
 struct ModelParams {
@@ -72,7 +76,8 @@ struct DevView {
     const uint32_t* work_cell;   // [n_pad] building id, or n_bldg + room id for school members
     const uint32_t* global_id;   // [n_pad]
     const uint32_t* room_parent; // [n_rooms] school building of a room
-    uint32_t* cnt;         // [n_cells] infected occupants present per building / room (zeroed every step)
+    uint32_t* cnt[2];      // [n_cells] x 2: infected occupants present per building / room.  Step t accumulates into
+                           // cnt[t & 1] while k_update zeroes cnt[(t + 1) & 1] for the next step.
     const unsigned long long* thr;  // [2][256] integer trial thresholds
     // public transport
     const uint32_t* route_off;   // [n_routes + 1]
@@ -82,6 +87,11 @@ struct DevView {
     uint32_t* pt_buscnt;   // [n_riders] scratch: infected riders per bus (route_off[r] + bus)
     uint32_t* rec_bus;     // [n] optional record: bus index per citizen
     uint32_t* rec_businf;  // [n] optional record: infected on that bus
+    uint32_t world;              // number of shards (1 = the whole population is here)
+    uint32_t* exch;              // [EXCH_WORDS] second exchange buffer of a sharded step
+    uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] candidate citizen of every draw of this step
+    uint32_t* tally_partial;     // [n_update_blocks * 8] per-block S,E,I,R,V partial sums of k_update
+    uint32_t n_update_blocks;
     Ctrl* ctrl;
     EsimStepStats* stats;  // [max_steps]
     uint32_t max_steps;
@@ -92,7 +102,9 @@ void launch_update(const DevView& v, cudaStream_t s);
 void launch_expose(const DevView& v, cudaStream_t s);
 void launch_pt(const DevView& v, cudaStream_t s);
 void launch_tail(const DevView& v, cudaStream_t s);
+void launch_vax_prepare(const DevView& v, cudaStream_t s);  // sharded runs only
 int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as int
 int  sm_count();
+uint32_t update_blocks(uint32_t n_pad);
 
 }  // namespace esim

@@ -7,7 +7,7 @@
 //   k_pt      = apply_exposures, public transport part (simulator.rs:359-401): shuffle -> buses of 20 -> trials
 //   k_tail    = statistics adjustment + apply_interventions (simulator.rs:455-556) + next hour's schedule
 //
-// All four are HBM/L2-bandwidth or latency bound integer kernels: no tensor-core work exists on this path.
+// All are HBM/L2-bandwidth or latency bound integer kernels: no tensor-core work exists on this path.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -44,46 +44,64 @@ __device__ __forceinline__ bool vax_eligible(uint32_t w, uint32_t vax_start_step
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t x) { return __reduce_add_sync(0xffffffffu, x); }
-
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+constexpr uint32_t NOT_SUSCEPTIBLE = CS_E_MASK | CS_VACCINATED | CS_ABSENT;
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
-// k_update: one thread per 4 citizens (128-bit loads of the state words), grid-stride.
-__global__ void __launch_bounds__(256) k_update(const DevView v) {
+// k_update: persistent grid (one wave), every thread keeps four 128-bit loads of state words in flight.  It also zeroes
+// the count buffer of the next step (a coalesced stream of 128-bit stores).  The S/E/I/R/V tallies leave the kernel as one
+// partial sum per block (no atomics): the tail adds them up.
+constexpr int UPDATE_THREADS = 256;
+constexpr int UPDATE_UNROLL = 4;
+
+__global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     const Ctrl* __restrict__ c = v.ctrl;
+    const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_quads = v.n_pad >> 2;
+    const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
+    const uint4 absent4 = make_uint4(CS_ABSENT, CS_ABSENT, CS_ABSENT, CS_ABSENT);
     if (c->finished) return;
     const uint32_t t = c->t, at_work = c->at_work, pt_active = c->pt_mode != ESIM_PT_NONE;
     const uint32_t vax_all = c->vax_all_pending, vax_start = c->vax_start_step;
     const uint32_t te = v.mp.exposed_time, ti = v.mp.infected_time;
     const uint32_t* __restrict__ pos = at_work ? v.work_cell : v.home_cell;
-    uint32_t n_s = 0, n_e = 0, n_i = 0, n_r = 0, n_v = 0;
+    uint32_t* __restrict__ cnt = v.cnt[t & 1u];
+    uint4* __restrict__ cnt_next = reinterpret_cast<uint4*>(v.cnt[(t + 1u) & 1u]);
 
-    const uint32_t n_quads = v.n_pad >> 2;
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x) {
-        const uint4 w4 = reinterpret_cast<const uint4*>(v.cstate)[q];
-        uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_next[z] = make_uint4(0u, 0u, 0u, 0u);
+
+    uint32_t n_s = 0, n_e = 0, n_i = 0, n_r = 0, n_v = 0;
+    for (uint32_t q0 = gtid; q0 < n_quads; q0 += UPDATE_UNROLL * T) {
+        uint4 cur[UPDATE_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (w[k] & CS_ABSENT) continue;
-            const uint32_t i = (q << 2) + k;
-            if (vax_all && !(w[k] & CS_VACCINATED) && vax_eligible(w[k], vax_start)) {
-                w[k] |= CS_VACCINATED;  // choose_multiple took the whole eligible set (simulator.rs:525-552)
-                v.cstate[i] = w[k];
-            }
-            const int st = status_at(w[k], t, te, ti);
-            // StatisticEntry::add_citizen (statistics.rs:256-272)
-            n_s += st == ST_S; n_e += st == ST_E; n_i += st == ST_I; n_r += st == ST_R; n_v += st == ST_V;
-            // a rider only counts on its bus; otherwise an infected citizen marks its current building (simulator.rs:181-198)
-            if (st == ST_I && !(pt_active && (w[k] & CS_USES_PT))) {
-                const uint32_t cell = pos[i];
-                atomicAdd(&v.cnt[cell], 1u);
-                if (cell >= v.n_bldg) atomicAdd(&v.cnt[v.room_parent[cell - v.n_bldg]], 1u);
+        for (int u = 0; u < UPDATE_UNROLL; ++u) { const uint32_t q = q0 + u * T; cur[u] = q < n_quads ? cs4[q] : absent4; }
+#pragma unroll
+        for (int u = 0; u < UPDATE_UNROLL; ++u) {
+            uint32_t w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (w[k] & CS_ABSENT) continue;
+                const uint32_t i = ((q0 + u * T) << 2) + (uint32_t)k;
+                if (vax_all && !(w[k] & CS_VACCINATED) && vax_eligible(w[k], vax_start)) {
+                    w[k] |= CS_VACCINATED;  // choose_multiple took the whole eligible set (simulator.rs:525-552)
+                    v.cstate[i] = w[k];
+                }
+                const int st = status_at(w[k], t, te, ti);
+                // StatisticEntry::add_citizen (statistics.rs:256-272)
+                n_s += st == ST_S; n_e += st == ST_E; n_i += st == ST_I; n_r += st == ST_R; n_v += st == ST_V;
+                // a rider only counts on its bus; otherwise an infected citizen marks its current building (simulator.rs:181-198)
+                if (st == ST_I && !(pt_active && (w[k] & CS_USES_PT))) {
+                    const uint32_t cell = pos[i];
+                    atomicAdd(&cnt[cell], 1u);
+                    if (cell >= v.n_bldg) atomicAdd(&cnt[v.room_parent[cell - v.n_bldg]], 1u);
+                }
             }
         }
     }
-    // block reduction of the five counters
+    // block reduction of the five counters -> tally_partial[block]
     __shared__ uint32_t s_cnt[5];
     if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -94,163 +112,265 @@ __global__ void __launch_bounds__(256) k_update(const DevView v) {
             if (cnt5[k]) atomicAdd(&s_cnt[k], cnt5[k]);
     }
     __syncthreads();
-    if (threadIdx.x < 5 && s_cnt[threadIdx.x]) atomicAdd(&v.ctrl->tally[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 5 ? s_cnt[threadIdx.x] : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_expose
-__device__ __forceinline__ bool building_trials(const DevView& v, uint32_t w, uint32_t i, uint32_t hc, uint32_t wc,
-                                                uint32_t t, uint32_t at_work, uint32_t mask_everywhere) {
-    // Citizen::expose (citizen.rs:228-232): a compliant citizen is treated as MaskStatus::None, everybody else gets the
-    // global status, and only MaskStatus::Everywhere changes the chance (disease.rs:131-154).
-    const uint32_t mc = (mask_everywhere && !(w & CS_COMPLIANT)) ? 256u : 0u;
-    const bool same_area = (w & CS_SAME_AREA) != 0;
-    unsigned long long thr_h = 0, thr_w = 0;
-    uint32_t k_w = 0;
-    // household: find_exposures returns every resident (building.rs:202-204); the simulator.rs:324 filter keeps the
-    // citizens whose current output area is the household's
-    if (!at_work || same_area) {
-        const uint32_t n_h = v.cnt[hc];
-        if (n_h) thr_h = __ldg(&v.thr[mc + (n_h & 255u)]);  // `exposure_total as u8` (citizen.rs:239)
-    }
-    if (wc != hc && (at_work || same_area)) {
-        if (wc >= v.n_bldg) {
-            // School::find_exposures (building.rs:494-522): one trial per infected member of the citizen's own room,
-            // each with n = infected present in the whole school
-            k_w = v.cnt[wc];
-            if (k_w) thr_w = __ldg(&v.thr[mc + (v.cnt[v.room_parent[wc - v.n_bldg]] & 255u)]);
-        } else {
-            const uint32_t n_w = v.cnt[wc];  // Workplace::find_exposures (building.rs:278-280)
-            if (n_w) { k_w = 1; thr_w = __ldg(&v.thr[mc + (n_w & 255u)]); }
-        }
-        if (thr_w == 0) k_w = 0;
-    }
-    if (thr_h == 0 && k_w == 0) return false;
-    const uint32_t gid = v.global_id[i];
-    Philox4 p = philox4x32_10(gid, t, 0u, DOM_BUILDING, v.mp.seed_lo, v.mp.seed_hi);
-    if (thr_h && u52_from(p, 0) < thr_h) return true;      // slot 0
-    if (k_w && u52_from(p, 1) < thr_w) return true;        // slot 1
-    for (uint32_t j = 1; j < k_w; ++j) {                   // slots 2..k_w
+// k_expose: one thread per quad.  The streaming part (state words, cell ids, count gathers) is branch-light so that
+// all loads of a thread are in flight together; the Philox trials are rare and live in a separate function.
+constexpr int EXPOSE_THREADS = 256;
+
+// Citizen::expose for one susceptible citizen with a household trial threshold and k_w workplace / room trials.
+__device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long long thr_w, uint32_t k_w, uint32_t gid,
+                                        uint32_t t, uint32_t seed_lo, uint32_t seed_hi) {
+    Philox4 p = philox4x32_10(gid, t, 0u, DOM_BUILDING, seed_lo, seed_hi);
+    if (thr_h && u52_from(p, 0) < thr_h) return true;      // slot 0: Household
+    if (k_w && u52_from(p, 1) < thr_w) return true;        // slot 1: Workplace, or first infected room member
+    for (uint32_t j = 1; j < k_w; ++j) {                   // slots 2..k_w: the other infected room members
         const uint32_t slot = 1u + j;
-        if ((slot & 1u) == 0u) p = philox4x32_10(gid, t, slot >> 1, DOM_BUILDING, v.mp.seed_lo, v.mp.seed_hi);
+        if ((slot & 1u) == 0u) p = philox4x32_10(gid, t, slot >> 1, DOM_BUILDING, seed_lo, seed_hi);
         if (u52_from(p, slot & 1u) < thr_w) return true;
     }
     return false;
 }
 
-__global__ void __launch_bounds__(256) k_expose(const DevView v) {
-    const Ctrl* __restrict__ c = v.ctrl;
-    if (c->finished) return;
-    const uint32_t t = c->t, at_work = c->at_work;
-    const uint32_t mask_everywhere = c->mask_kind == ESIM_MASK_EVERYWHERE;
-    uint32_t n_exposed = 0;
-    const uint32_t n_quads = v.n_pad >> 2;
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x) {
-        const uint4 w4 = reinterpret_cast<const uint4*>(v.cstate)[q];
-        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-        // susceptible <=> never exposed, not vaccinated, a real citizen
-        constexpr uint32_t NOT_S = CS_E_MASK | CS_VACCINATED | CS_ABSENT;
-        const bool s0 = !(w[0] & NOT_S), s1 = !(w[1] & NOT_S), s2 = !(w[2] & NOT_S), s3 = !(w[3] & NOT_S);
-        if (!(s0 | s1 | s2 | s3)) continue;
-        const uint4 h4 = reinterpret_cast<const uint4*>(v.home_cell)[q];
-        const uint4 k4 = reinterpret_cast<const uint4*>(v.work_cell)[q];
-        const uint32_t hc[4] = {h4.x, h4.y, h4.z, h4.w};
-        const uint32_t wc[4] = {k4.x, k4.y, k4.z, k4.w};
-        const bool sus[4] = {s0, s1, s2, s3};
+__device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, const uint4 w4,
+                                                const uint4 h4, const uint4 k4, uint32_t t, uint32_t at_work, uint32_t mask_everywhere) {
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+    const uint32_t hc[4] = {h4.x, h4.y, h4.z, h4.w};
+    const uint32_t wc[4] = {k4.x, k4.y, k4.z, k4.w};
+    const uint32_t n_bldg = v.n_bldg;
+    // gather the counts of all sources first: the household (building.rs:202-204) and the workplace / own room
+    // (building.rs:278-280, 494-522), each only if the simulator.rs:324 filter lets the citizen be exposed there
+    uint32_t n_h[4], n_w[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!sus[k]) continue;
-            const uint32_t i = (q << 2) + k;
-            if (building_trials(v, w[k], i, hc[k], wc[k], t, at_work, mask_everywhere)) {
-                v.cstate[i] = w[k] | (t + EXPOSURE_BIAS);  // DiseaseStatus::Exposed(0) (citizen.rs:244)
-                ++n_exposed;
-            }
+    for (int k = 0; k < 4; ++k) {
+        const bool sus = !(w[k] & NOT_SUSCEPTIBLE);
+        const bool same_area = (w[k] & CS_SAME_AREA) != 0;
+        const bool home_ok = sus && (!at_work || same_area);
+        const bool work_ok = sus && wc[k] != hc[k] && (at_work || same_area);
+        n_h[k] = home_ok ? __ldg(&cnt[hc[k]]) : 0u;
+        n_w[k] = work_ok ? __ldg(&cnt[wc[k]]) : 0u;
+    }
+    if (!(n_h[0] | n_h[1] | n_h[2] | n_h[3] | n_w[0] | n_w[1] | n_w[2] | n_w[3])) return 0u;
+    uint32_t n_exposed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!(n_h[k] | n_w[k])) continue;
+        // Citizen::expose (citizen.rs:228-232): a compliant citizen is evaluated with MaskStatus::None, the others
+        // with the global status, and only MaskStatus::Everywhere changes the chance (disease.rs:131-154)
+        const uint32_t mc = (mask_everywhere && !(w[k] & CS_COMPLIANT)) ? 256u : 0u;
+        unsigned long long thr_h = 0, thr_w = 0;
+        uint32_t k_w = 0;
+        if (n_h[k]) thr_h = __ldg(&v.thr[mc + (n_h[k] & 255u)]);  // `exposure_total as u8` (citizen.rs:239)
+        if (n_w[k]) {
+            // a room member gets one trial per infected member of its own room, each with n = infected in the school
+            const uint32_t n_total = wc[k] >= n_bldg ? __ldg(&cnt[__ldg(&v.room_parent[wc[k] - n_bldg])]) : n_w[k];
+            thr_w = __ldg(&v.thr[mc + (n_total & 255u)]);
+            k_w = thr_w ? (wc[k] >= n_bldg ? n_w[k] : 1u) : 0u;
+        }
+        if (thr_h == 0 && k_w == 0) continue;
+        const uint32_t i = (q << 2) + (uint32_t)k;
+        if (run_trials(thr_h, thr_w, k_w, __ldg(&v.global_id[i]), t, v.mp.seed_lo, v.mp.seed_hi)) {
+            v.cstate[i] = w[k] | (t + EXPOSURE_BIAS);  // DiseaseStatus::Exposed(0) (citizen.rs:244)
+            ++n_exposed;
         }
     }
+    return n_exposed;
+}
+
+__device__ __forceinline__ bool any_susceptible(const uint4 w) {
+    return !(w.x & NOT_SUSCEPTIBLE) || !(w.y & NOT_SUSCEPTIBLE) || !(w.z & NOT_SUSCEPTIBLE) || !(w.w & NOT_SUSCEPTIBLE);
+}
+
+// EAGER: request the household / workplace ids together with the state words (one memory round trip less per quad);
+// used while more than a quarter of the shard is susceptible, when nearly every quad needs them anyway.
+template <bool EAGER>
+__device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* __restrict__ c) {
+    const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_quads = v.n_pad >> 2;
+    const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
+    const uint4* __restrict__ hc4 = reinterpret_cast<const uint4*>(v.home_cell);
+    const uint4* __restrict__ wc4 = reinterpret_cast<const uint4*>(v.work_cell);
+    const uint32_t t = c->t, at_work = c->at_work;
+    const uint32_t mask_everywhere = c->mask_kind == ESIM_MASK_EVERYWHERE;
+    const uint32_t* __restrict__ cnt = v.cnt[t & 1u];
+    const uint4 absent4 = make_uint4(CS_ABSENT, CS_ABSENT, CS_ABSENT, CS_ABSENT);
+    uint32_t n_exposed = 0;
+    for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
+        const uint32_t q1 = q0 + T;
+        const bool have1 = q1 < n_quads;
+        const uint4 wa = cs4[q0];
+        const uint4 wb = have1 ? cs4[q1] : absent4;
+        uint4 ha, ka, hb, kb;
+        if (EAGER) {
+            ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0);
+            if (have1) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); } else { hb = kb = make_uint4(0u, 0u, 0u, 0u); }
+        }
+        const bool sa = any_susceptible(wa), sb = any_susceptible(wb);
+        if (!EAGER) {
+            if (sa) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
+            if (sb) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
+        }
+        if (sa) n_exposed += expose_quad(v, cnt, q0, wa, ha, ka, t, at_work, mask_everywhere);
+        if (sb) n_exposed += expose_quad(v, cnt, q1, wb, hb, kb, t, at_work, mask_everywhere);
+    }
+    return n_exposed;
+}
+
+__global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
+    const Ctrl* __restrict__ c = v.ctrl;
+    if (c->finished) return;
+    // tally_partial of this step's k_update is complete: block 0's partial is enough to pick the load strategy
+    const bool eager = c->eager_expose != 0;
+    const uint32_t n_exposed = eager ? expose_stream<true>(v, c) : expose_stream<false>(v, c);
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_pt: one warp per route (source area, destination area).  Everybody who uses public transport rides at the same
-// hours (citizen.rs:179-195), so the riders of a route are static and stored as a CSR built at import.
+// Public transport: one warp per route (source area, destination area).  Everybody who uses public transport rides at
+// the same hours (citizen.rs:179-195), so the riders of a route are static and stored as a CSR built at import.
 //   shuffle (simulator.rs:362)      = ascending order of (Philox key, position in the route list)
-//   pop from the end (:364-388)     = bus b holds ranks [n - 20(b+1), n - 20b)
-__global__ void __launch_bounds__(128) k_pt(const DevView v) {
-    const Ctrl* __restrict__ c = v.ctrl;
-    if (c->finished || c->pt_mode == ESIM_PT_NONE) return;
-    const uint32_t t = c->t;
-    const uint32_t mask_everywhere = c->mask_kind == ESIM_MASK_EVERYWHERE;
-    const uint32_t vax_some = c->vax_some;
+//   pop from the end (:364-388)     = bus b holds ranks [n - cap(b+1), n - cap b)
+constexpr int PT_MAX_FAST = 128;            // riders of a route handled in registers + shared memory
+constexpr int PT_PER_LANE = PT_MAX_FAST / 32;
+struct PtWarpSmem {
+    uint32_t key[PT_MAX_FAST];
+    uint32_t buscnt[PT_MAX_FAST];
+};
+
+// slow path for routes with more than PT_MAX_FAST riders: global scratch, same arithmetic
+__device__ __noinline__ uint32_t pt_route_slow(const DevView& v, uint32_t off, uint32_t n, uint32_t t, uint32_t mask_everywhere) {
+    const uint32_t te = v.mp.exposed_time, ti = v.mp.infected_time, cap = v.mp.bus_capacity, lane = lane_id();
+    const uint32_t n_buses = (n + cap - 1) / cap;
+    uint32_t n_exposed = 0;
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint32_t i = v.riders[off + j];
+        const uint32_t w = __ldcg(&v.cstate[i]);
+        const Philox4 p = philox4x32_10(v.global_id[i], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
+        v.pt_key[off + j] = p.v[0];
+        v.pt_bus[off + j] = (status_at(w, t, te, ti) == ST_I) ? 0x80000000u : 0u;
+        if (j < n_buses) v.pt_buscnt[off + j] = 0;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint32_t kj = v.pt_key[off + j];
+        uint32_t rank = 0;
+        for (uint32_t m = 0; m < n; ++m) {
+            const uint32_t km = v.pt_key[off + m];
+            rank += (km < kj) || (km == kj && m < j);
+        }
+        const uint32_t bus = (n - 1 - rank) / cap;
+        const uint32_t inf = v.pt_bus[off + j] & 0x80000000u;
+        v.pt_bus[off + j] = inf | bus;
+        if (inf) atomicAdd(&v.pt_buscnt[off + bus], 1u);
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint32_t i = v.riders[off + j];
+        const uint32_t bus = v.pt_bus[off + j] & 0x7FFFFFFFu;
+        const uint32_t n_b = v.pt_buscnt[off + bus];
+        if (v.record_buses) { v.rec_bus[i] = bus; v.rec_businf[i] = n_b; }
+        if (n_b == 0) continue;
+        const uint32_t w = __ldcg(&v.cstate[i]);
+        if (w & NOT_SUSCEPTIBLE) continue;
+        const uint32_t mc = (mask_everywhere && !(w & CS_COMPLIANT)) ? 256u : 0u;
+        const unsigned long long thr = __ldg(&v.thr[mc + (n_b & 255u)]);
+        if (thr == 0) continue;
+        const Philox4 p = philox4x32_10(v.global_id[i], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
+        if (u52_from(p, 1) < thr) {
+            v.cstate[i] = w | (t + EXPOSURE_BIAS) | CS_VIA_PT;
+            ++n_exposed;
+        }
+    }
+    __syncwarp();
+    return n_exposed;
+}
+
+// All routes, grid-stride by warp.  `ws` is this warp's shared-memory staging area.
+__device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint32_t t, uint32_t mask_everywhere) {
     const uint32_t te = v.mp.exposed_time, ti = v.mp.infected_time, cap = v.mp.bus_capacity;
     const uint32_t lane = lane_id();
     const uint32_t warps_per_block = blockDim.x >> 5;
     uint32_t n_exposed = 0;
     for (uint32_t r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < v.n_routes; r += gridDim.x * warps_per_block) {
-        const uint32_t off = v.route_off[r], n = v.route_off[r + 1] - off;
-        const uint32_t n_buses = (n + cap - 1) / cap;
-        // pass 1: shuffle keys, infected flag in the top bit of pt_bus, zero the bus counters
-        for (uint32_t j = lane; j < n; j += 32) {
-            const uint32_t i = v.riders[off + j];
-            const uint32_t w = v.cstate[i];
-            const Philox4 p = philox4x32_10(v.global_id[i], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
-            v.pt_key[off + j] = p.v[0];
-            v.pt_bus[off + j] = (status_at(w, t, te, ti) == ST_I) ? 0x80000000u : 0u;
-            if (j < n_buses) v.pt_buscnt[off + j] = 0;
+        const uint32_t off = __ldg(&v.route_off[r]), n = __ldg(&v.route_off[r + 1]) - off;
+        if (n > PT_MAX_FAST) { n_exposed += pt_route_slow(v, off, n, t, mask_everywhere); continue; }
+        // pass 1: everything a rider needs, all loads of the lane's riders in flight together
+        uint32_t idx[PT_PER_LANE], w[PT_PER_LANE], gid[PT_PER_LANE];
+#pragma unroll
+        for (int s = 0; s < PT_PER_LANE; ++s) {
+            const uint32_t j = lane + 32u * s;
+            idx[s] = j < n ? __ldg(&v.riders[off + j]) : 0xFFFFFFFFu;
         }
-        __syncwarp();
-        // pass 2: rank of every rider in the shuffled order -> bus; count the infected riders per bus
-        for (uint32_t j = lane; j < n; j += 32) {
-            const uint32_t kj = v.pt_key[off + j];
-            uint32_t rank = 0;
-            for (uint32_t m = 0; m < n; ++m) {
-                const uint32_t km = v.pt_key[off + m];
-                rank += (km < kj) || (km == kj && m < j);
+#pragma unroll
+        for (int s = 0; s < PT_PER_LANE; ++s) {
+            w[s] = idx[s] != 0xFFFFFFFFu ? __ldcg(&v.cstate[idx[s]]) : CS_ABSENT;
+            gid[s] = idx[s] != 0xFFFFFFFFu ? __ldg(&v.global_id[idx[s]]) : 0u;
+        }
+        uint32_t key[PT_PER_LANE], u_lo[PT_PER_LANE], u_hi[PT_PER_LANE];
+#pragma unroll
+        for (int s = 0; s < PT_PER_LANE; ++s) {
+            const uint32_t j = lane + 32u * s;
+            if (j < n) {
+                const Philox4 p = philox4x32_10(gid[s], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
+                key[s] = p.v[0]; u_lo[s] = p.v[2]; u_hi[s] = p.v[3];
+                ws->key[j] = key[s];
             }
-            const uint32_t bus = (n - 1 - rank) / cap;
-            const uint32_t inf = v.pt_bus[off + j] & 0x80000000u;
-            v.pt_bus[off + j] = inf | bus;
-            if (inf) atomicAdd(&v.pt_buscnt[off + bus], 1u);  // PublicTransport::exposure_count (simulator.rs:385-387)
+            ws->buscnt[j] = 0;
         }
         __syncwarp();
-        // pass 3: every rider of a bus with infected riders is exposed with n = infected on that bus (simulator.rs:407-453)
-        for (uint32_t j = lane; j < n; j += 32) {
-            const uint32_t i = v.riders[off + j];
-            const uint32_t bus = v.pt_bus[off + j] & 0x7FFFFFFFu;
-            const uint32_t n_b = v.pt_buscnt[off + bus];
-            if (v.record_buses) { v.rec_bus[i] = bus; v.rec_businf[i] = n_b; }
-            if (n_b == 0) continue;
-            const uint32_t w = v.cstate[i];
-            if (w & (CS_E_MASK | CS_VACCINATED)) continue;  // not susceptible
-            const uint32_t mc = (mask_everywhere && !(w & CS_COMPLIANT)) ? 256u : 0u;
+        // pass 2: rank in the shuffled order -> bus; infected riders per bus (PublicTransport::exposure_count)
+        uint32_t bus[PT_PER_LANE];
+#pragma unroll
+        for (int s = 0; s < PT_PER_LANE; ++s) {
+            const uint32_t j = lane + 32u * s;
+            bus[s] = 0;
+            if (j < n) {
+                uint32_t rank = 0;
+                for (uint32_t m = 0; m < n; ++m) {
+                    const uint32_t km = ws->key[m];
+                    rank += (km < key[s]) || (km == key[s] && m < j);
+                }
+                bus[s] = (n - 1 - rank) / cap;
+                if (status_at(w[s], t, te, ti) == ST_I) atomicAdd(&ws->buscnt[bus[s]], 1u);
+            }
+        }
+        __syncwarp();
+        // pass 3: every susceptible rider of a bus with infected riders is exposed with n = infected on that bus
+#pragma unroll
+        for (int s = 0; s < PT_PER_LANE; ++s) {
+            const uint32_t j = lane + 32u * s;
+            if (j >= n) continue;
+            const uint32_t n_b = ws->buscnt[bus[s]];
+            if (v.record_buses) { v.rec_bus[idx[s]] = bus[s]; v.rec_businf[idx[s]] = n_b; }
+            if (n_b == 0 || (w[s] & NOT_SUSCEPTIBLE)) continue;
+            const uint32_t mc = (mask_everywhere && !(w[s] & CS_COMPLIANT)) ? 256u : 0u;
             const unsigned long long thr = __ldg(&v.thr[mc + (n_b & 255u)]);
-            if (thr == 0) continue;
-            const Philox4 p = philox4x32_10(v.global_id[i], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
-            if (u52_from(p, 1) < thr) {
-                v.cstate[i] = w | (t + EXPOSURE_BIAS) | CS_VIA_PT;
+            const uint64_t m52 = (((uint64_t)u_hi[s] << 32) | (uint64_t)u_lo[s]) >> 12;
+            if (m52 < thr) {
+                v.cstate[idx[s]] = w[s] | (t + EXPOSURE_BIAS) | CS_VIA_PT;
                 ++n_exposed;
             }
         }
         __syncwarp();
     }
     const uint32_t s = warp_sum(n_exposed);
-    if (lane == 0 && s) {
-        atomicAdd(&v.ctrl->new_exp_pt, s);
-        if (vax_some) atomicSub(&v.ctrl->n_elig, s);  // vaccine_list.remove(&citizen_id) (simulator.rs:447-449)
-    }
+    if (lane == 0 && s) atomicAdd(&v.ctrl->new_exp_pt, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_tail: one block.  Thread 0 runs the scalar state machines; the whole block draws the vaccination picks.
+// Tail: one block of 1024 threads.  Thread 0 runs the scalar state machines; the whole block draws the vaccination picks.
 constexpr int TAIL_THREADS = 1024;
 constexpr uint32_t VAX_BATCH = 2 * TAIL_THREADS;
-constexpr uint32_t HT_SIZE = 8192;  // power of two, > 2 * max(VAX_BATCH, supported picks per step / 2)
+constexpr uint32_t HT_SIZE = 8192;  // power of two
 constexpr uint32_t HT_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t MAX_VAX_PER_STEP = 4000;  // accepted-pick table capacity (HT_SIZE / 2)
+constexpr uint32_t MAX_VAX_PER_STEP = 4000;  // accepted-pick table stays below half of HT_SIZE
+constexpr uint32_t VAX_SHARD_DRAWS = ESIM_VAX_SHARD_DRAWS;  // candidate draws examined per step by a sharded run
 
 __device__ __forceinline__ uint32_t ht_hash(uint32_t k) { return (k * 2654435761u) >> 19; }  // 13 bits
 
-// insert key, return slot
 __device__ __forceinline__ uint32_t ht_insert(uint32_t* keys, uint32_t key) {
     uint32_t h = ht_hash(key) & (HT_SIZE - 1);
     while (true) {
@@ -300,66 +420,134 @@ __device__ bool update_interventions(Ctrl* c, const ModelParams& mp, double p) {
     return vaccination_event;
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
-    Ctrl* c = v.ctrl;
-    if (c->finished) return;
-    extern __shared__ uint32_t smem[];
-    uint32_t* acc_keys = smem;                  // [HT_SIZE] citizens chosen in this step
-    uint32_t* bat_keys = smem + HT_SIZE;        // [HT_SIZE] candidates of the current batch
-    uint32_t* bat_minj = smem + 2 * HT_SIZE;    // [HT_SIZE] first draw index of each candidate
-    __shared__ uint32_t s_scan[TAIL_THREADS / 32];
-    __shared__ uint32_t s_k, s_accepted, s_batch_total;
-    __shared__ EsimStepStats s_stats;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const uint32_t t = c->t;
+struct TailSmem {
+    Ctrl c;                      // working copy of the control block
+    EsimStepStats stats;
+    uint32_t scan[TAIL_THREADS / 32];
+    uint32_t tally[8];
+    uint32_t k, accepted, batch_total;
+};
 
+// `ht` = 3 * HT_SIZE words of shared memory.  Must be called by all TAIL_THREADS threads of one block, after every
+// other writer of the control block and of the citizens' state words of this step has finished.
+__device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailSmem& sm) {
+    uint32_t* acc_keys = ht;                  // citizens chosen in this step
+    uint32_t* bat_keys = ht + HT_SIZE;        // candidates of the current batch
+    uint32_t* bat_minj = ht + 2 * HT_SIZE;    // first draw index of each candidate
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    // one coalesced read of the control block (L2: other blocks updated it with atomics)
+    if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + tid);
+    if (tid < 8) sm.tally[tid] = 0;
+    __syncthreads();
+    const bool sharded = v.world > 1;
+    if (sharded) {
+        // k_vax_prepare + the all-reduce left the global tallies and exposure counts in the exchange buffer
+        if (tid < 5) sm.tally[tid] = __ldcg(&v.exch[tid]);
+        if (tid == 5) sm.c.new_exp_bldg = __ldcg(&v.exch[5]);
+        if (tid == 6) sm.c.new_exp_pt = __ldcg(&v.exch[6]);
+    } else {   // S/E/I/R/V = sum of k_update's per-block partials (8 words per block, 5 used)
+        uint32_t part = 0;
+        for (uint32_t z = tid; z < v.n_update_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
+        // threads tid, tid+8, ... hold the same counter: TAIL_THREADS is a multiple of 8
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        part += __shfl_xor_sync(0xffffffffu, part, 16);
+        if (lane < 8 && part) atomicAdd(&sm.tally[lane], part);
+    }
+    __syncthreads();
+    const uint32_t t = sm.c.t;
     if (tid == 0) {
+        Ctrl* c = &sm.c;
         c->vax_all_pending = 0;  // consumed by this step's k_update
         // statistics.rs:275-287: every successful exposure moves one citizen from susceptible to exposed
         const uint32_t new_exp = c->new_exp_bldg + c->new_exp_pt;
         EsimStepStats s;
         s.time_step = t;
-        s.susceptible = c->tally[0] - new_exp;
-        s.exposed = c->tally[1] + new_exp;
-        s.infected = c->tally[2];
-        s.recovered = c->tally[3];
-        s.vaccinated = c->tally[4];
+        s.susceptible = sm.tally[0] - new_exp;
+        s.exposed = sm.tally[1] + new_exp;
+        s.infected = sm.tally[2];
+        s.recovered = sm.tally[3];
+        s.vaccinated = sm.tally[4];
         s.exposures_building = c->new_exp_bldg;
         s.exposures_pt = c->new_exp_pt;
         const uint32_t total = s.susceptible + s.exposed + s.infected + s.recovered + s.vaccinated;
         const double p = (double)s.infected / (double)total;  // StatisticEntry::infected_percentage (statistics.rs:252-254)
+        // citizens exposed on public transport leave the eligible set if it exists (simulator.rs:447-449)
+        if (c->vax_some) c->n_elig -= c->new_exp_pt;
         if (update_interventions(c, v.mp, p)) {
             c->vax_start_step = t;
             c->n_elig = s.susceptible;  // everybody Susceptible right now (simulator.rs:487-513)
         }
-        s_stats = s;
-        s_k = c->vax_some ? min(v.mp.vaccination_rate, c->n_elig) : 0u;
-        s_accepted = 0;
+        sm.stats = s;
+        sm.k = c->vax_some ? min(v.mp.vaccination_rate, c->n_elig) : 0u;
+        sm.accepted = 0;
     }
-    for (uint32_t h = tid; h < HT_SIZE; h += TAIL_THREADS) acc_keys[h] = HT_EMPTY;
     __syncthreads();
 
     // ---- vaccination: choose_multiple(rate) over the eligible set, then status = Vaccinated (simulator.rs:524-553)
-    const uint32_t K = s_k;
-    const uint32_t vax_start = c->vax_start_step;
+    const uint32_t K = sm.k;
     if (K > 0) {
-        if (K == c->n_elig || K > MAX_VAX_PER_STEP) {
+        const uint32_t vax_start = sm.c.vax_start_step;
+        if (sharded && !(K == sm.c.n_elig || K > MAX_VAX_PER_STEP)) {
+            // every shard marked, in the all-reduced mask, the draws whose candidate it owns and that are eligible first
+            // occurrences; the first K set bits are the picks, and each shard applies the ones it owns
+            const uint32_t* mask = v.exch + 8;
+            uint32_t pc = 0;
+            if (tid < VAX_SHARD_DRAWS / 32) pc = __popc(__ldcg(&mask[tid]));
+            uint32_t incl = pc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += y;
+            }
+            if (lane == 31) sm.scan[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                const uint32_t x = sm.scan[lane];
+                uint32_t inc2 = x;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, inc2, d);
+                    if (lane >= (uint32_t)d) inc2 += y;
+                }
+                sm.scan[lane] = inc2 - x;
+                if (lane == 31) sm.batch_total = inc2;
+            }
+            __syncthreads();
+            if (tid < VAX_SHARD_DRAWS / 32) {
+                uint32_t bits = __ldcg(&mask[tid]);
+                uint32_t rank = sm.scan[wid] + (incl - pc);   // set bits before this word
+                while (bits && rank < K) {
+                    const uint32_t b = __ffs(bits) - 1u;
+                    bits &= bits - 1u;
+                    const uint32_t local = __ldcg(&v.vax_cand[tid * 32u + b]) - v.mp.shard_lo;
+                    if (local < v.n) atomicOr(&v.cstate[local], CS_VACCINATED);
+                    ++rank;
+                }
+            }
+            if (tid == 0) {
+                if (sm.batch_total < K) sm.c.error = (uint32_t)(-ESIM_ERR_SIMULATION);  // more than VAX_SHARD_DRAWS draws needed
+                sm.accepted = min(K, sm.batch_total);
+            }
+        } else if (K == sm.c.n_elig || K > MAX_VAX_PER_STEP) {
             // the whole eligible set is chosen: k_update of the next step marks it while it streams the citizens
             if (tid == 0) {
-                if (K != c->n_elig) c->error = (uint32_t)(-ESIM_ERR_INVALID_ARGUMENT);
-                c->vax_all_pending = 1;
-                s_accepted = K;
+                if (K != sm.c.n_elig) sm.c.error = (uint32_t)(-ESIM_ERR_INVALID_ARGUMENT);
+                sm.c.vax_all_pending = 1;
+                sm.accepted = K;
             }
         } else {
+            for (uint32_t h = tid; h < HT_SIZE; h += TAIL_THREADS) acc_keys[h] = HT_EMPTY;
             uint32_t base = 0;
             for (uint32_t guard = 0; guard < (1u << 20); ++guard) {
                 for (uint32_t h = tid; h < HT_SIZE; h += TAIL_THREADS) { bat_keys[h] = HT_EMPTY; bat_minj[h] = 0xFFFFFFFFu; }
                 __syncthreads();
-                uint32_t cand[2], slot[2];
+                uint32_t cand[2], slot[2], wv[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const uint32_t j = base + 2 * tid + q;
                     cand[q] = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
+                    const uint32_t local = cand[q] - v.mp.shard_lo;
+                    wv[q] = local < v.n ? __ldcg(&v.cstate[local]) : CS_ABSENT;   // issued before the hash traffic
                     slot[q] = ht_insert(bat_keys, cand[q]);
                     atomicMin(&bat_minj[slot[q]], j);
                 }
@@ -368,9 +556,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const uint32_t j = base + 2 * tid + q;
-                    bool ok = bat_minj[slot[q]] == j && !ht_contains(acc_keys, cand[q]);
-                    const uint32_t local = cand[q] - v.mp.shard_lo;
-                    ok = ok && local < v.n && vax_eligible(v.cstate[local], vax_start);
+                    const bool ok = bat_minj[slot[q]] == j && !ht_contains(acc_keys, cand[q]) && vax_eligible(wv[q], vax_start);
                     flag[q] = ok ? 1u : 0u;
                 }
                 // exclusive scan of the flags in draw order
@@ -381,22 +567,22 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
                     const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= (uint32_t)d) incl += y;
                 }
-                if (lane == 31) s_scan[wid] = incl;
+                if (lane == 31) sm.scan[wid] = incl;
                 __syncthreads();
                 if (wid == 0) {
-                    uint32_t x = lane < TAIL_THREADS / 32 ? s_scan[lane] : 0u;
+                    const uint32_t x = sm.scan[lane];
                     uint32_t inc2 = x;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const uint32_t y = __shfl_up_sync(0xffffffffu, inc2, d);
                         if (lane >= (uint32_t)d) inc2 += y;
                     }
-                    s_scan[lane] = inc2 - x;
-                    if (lane == 31) s_batch_total = inc2;
+                    sm.scan[lane] = inc2 - x;
+                    if (lane == 31) sm.batch_total = inc2;
                 }
                 __syncthreads();
-                const uint32_t accepted_before = s_accepted;
-                uint32_t rank = accepted_before + s_scan[wid] + (incl - mine);
+                const uint32_t accepted_before = sm.accepted;
+                uint32_t rank = accepted_before + sm.scan[wid] + (incl - mine);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (flag[q]) {
@@ -408,9 +594,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
                     }
                 }
                 __syncthreads();
-                if (tid == 0) s_accepted = min(K, accepted_before + s_batch_total);
+                if (tid == 0) sm.accepted = min(K, accepted_before + sm.batch_total);
                 __syncthreads();
-                if (s_accepted >= K) break;
+                if (sm.accepted >= K) break;
                 base += VAX_BATCH;
             }
         }
@@ -418,7 +604,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
     __syncthreads();
 
     if (tid == 0) {
-        EsimStepStats s = s_stats;
+        Ctrl* c = &sm.c;
+        EsimStepStats s = sm.stats;
         s.lockdown_hours = c->lockdown_some ? c->lockdown_hours : ESIM_NONE_U32;
         s.vaccination_hours = c->vax_some ? c->vax_hours : ESIM_NONE_U32;
         s.mask_status = c->mask_kind;
@@ -426,8 +613,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
         s.at_work = c->at_work;
         s.pt_mode = v.n_riders ? c->pt_mode : (uint32_t)ESIM_PT_NONE;
         s.vaccine_eligible = c->vax_some ? c->n_elig : 0u;
-        s.vaccinated_now = s_accepted;
-        if (t - 1 < v.max_steps) v.stats[t - 1] = s;
+        s.vaccinated_now = sm.accepted;
+        sm.stats = s;
         // StatisticEntry::disease_exists (statistics.rs:289-291)
         if (!(s.exposed != 0 || s.infected != 0 || s.susceptible != 0)) c->finished = 1;
         // schedule of the next hour (citizen.rs:176-205): frozen while lockdown is enabled
@@ -443,8 +630,103 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
         c->t = nt;
         c->tally[0] = c->tally[1] = c->tally[2] = c->tally[3] = c->tally[4] = 0;
         c->new_exp_bldg = 0; c->new_exp_pt = 0;
-        c->vaccinated_now = s_accepted;
+        c->vaccinated_now = sm.accepted;
+        c->blocks_done = 0;
+        // k_expose requests the cell ids together with the state words while most citizens are susceptible
+        c->eager_expose = (uint64_t)s.susceptible * 4u > (uint64_t)(s.susceptible + s.exposed + s.infected + s.recovered + s.vaccinated) ? 1u : 0u;
     }
+    __syncthreads();
+    // write the control block and the statistics entry back, coalesced
+    if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(v.ctrl)[tid] = reinterpret_cast<const uint32_t*>(&sm.c)[tid];
+    if (tid >= 64 && tid < 64 + sizeof(EsimStepStats) / 4 && t - 1 < v.max_steps)
+        reinterpret_cast<uint32_t*>(&v.stats[t - 1])[tid - 64] = reinterpret_cast<const uint32_t*>(&sm.stats)[tid - 64];
+}
+
+// Sharded runs, between the public-transport kernel and the tail: fills the second exchange buffer
+//   exch[0..4] S,E,I,R,V of this shard   exch[5..6] building / public-transport exposures of this shard
+//   exch[8 + j/32] bit j%32: draw j of the vaccination candidate stream is owned by this shard, eligible, and the first
+//   occurrence of its citizen.  Duplicates of a citizen are owned by the same shard, so de-duplication is local.
+constexpr uint32_t VP_HT = 2 * VAX_SHARD_DRAWS;  // hash slots (power of two)
+__global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
+    extern __shared__ uint32_t dyn_smem[];
+    uint32_t* keys = dyn_smem;                 // [VP_HT]
+    uint32_t* minj = dyn_smem + VP_HT;         // [VP_HT]
+    uint32_t* mask = dyn_smem + 2 * VP_HT;     // [VAX_SHARD_DRAWS / 32]
+    __shared__ uint32_t s_tally[8];
+    const Ctrl* __restrict__ c = v.ctrl;
+    if (c->finished) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t t = c->t;
+    if (tid < 8) s_tally[tid] = 0;
+    for (uint32_t h = tid; h < VP_HT; h += TAIL_THREADS) { keys[h] = HT_EMPTY; minj[h] = 0xFFFFFFFFu; }
+    for (uint32_t h = tid; h < VAX_SHARD_DRAWS / 32; h += TAIL_THREADS) mask[h] = 0;
+    __syncthreads();
+    {
+        uint32_t part = 0;
+        for (uint32_t z = tid; z < v.n_update_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        part += __shfl_xor_sync(0xffffffffu, part, 16);
+        if (lane < 8 && part) atomicAdd(&s_tally[lane], part);
+    }
+    // the programme may start in this very step: then everybody Susceptible now is eligible, which is what
+    // vax_eligible(w, t) says (nobody can have been exposed after step t yet)
+    const bool may_vaccinate = v.mp.th_vaccination >= 0.0;
+    const uint32_t vax_start = c->vax_some ? c->vax_start_step : t;
+    constexpr int PER = VAX_SHARD_DRAWS / TAIL_THREADS;
+    uint32_t wv[PER], slot[PER];
+    if (may_vaccinate) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const uint32_t j = tid * PER + q;
+            const uint32_t cand = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
+            v.vax_cand[j] = cand;
+            const uint32_t local = cand - v.mp.shard_lo;
+            wv[q] = CS_ABSENT; slot[q] = 0;
+            if (local < v.n) {
+                wv[q] = __ldcg(&v.cstate[local]);
+                uint32_t h = (cand * 2654435761u) >> 18 & (VP_HT - 1);
+                while (true) {
+                    const uint32_t prev = atomicCAS(&keys[h], HT_EMPTY, cand);
+                    if (prev == HT_EMPTY || prev == cand) break;
+                    h = (h + 1) & (VP_HT - 1);
+                }
+                slot[q] = h;
+                atomicMin(&minj[h], j);
+            }
+        }
+    }
+    __syncthreads();
+    if (may_vaccinate) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const uint32_t j = tid * PER + q;
+            if (!(wv[q] & CS_ABSENT) && minj[slot[q]] == j && vax_eligible(wv[q], vax_start)) atomicOr(&mask[j >> 5], 1u << (j & 31u));
+        }
+    }
+    __syncthreads();
+    if (tid < 5) v.exch[tid] = s_tally[tid];
+    if (tid == 5) v.exch[5] = c->new_exp_bldg;
+    if (tid == 6) v.exch[6] = c->new_exp_pt;
+    if (tid == 7) v.exch[7] = 0;
+    for (uint32_t h = tid; h < VAX_SHARD_DRAWS / 32; h += TAIL_THREADS) v.exch[8 + h] = mask[h];
+}
+constexpr size_t VP_SMEM = (2 * VP_HT + VAX_SHARD_DRAWS / 32) * sizeof(uint32_t);
+
+constexpr size_t HT_BYTES = 3 * HT_SIZE * sizeof(uint32_t);
+constexpr int PT_THREADS = 128;  // 4 routes per block: small blocks start (and, on idle hours, retire) quickly
+
+__global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
+    __shared__ PtWarpSmem ws[PT_THREADS / 32];
+    const Ctrl* __restrict__ c = v.ctrl;
+    if (c->finished || c->pt_mode == ESIM_PT_NONE) return;
+    pt_phase(v, &ws[threadIdx.x >> 5], c->t, c->mask_kind == ESIM_MASK_EVERYWHERE);
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
+    extern __shared__ uint32_t dyn_smem[];
+    __shared__ TailSmem sm;
+    if (v.ctrl->finished) return;
+    tail_phase(v, dyn_smem, sm);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -460,30 +742,38 @@ int sm_count() {
     return g_sm_count;
 }
 
-constexpr size_t TAIL_SMEM = 3 * HT_SIZE * sizeof(uint32_t);
-
 int configure_kernels() {
-    return (int)cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vax_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM);
+    return (int)e;
 }
 
-static inline uint32_t stream_grid(uint32_t n_threads_needed, uint32_t block, uint32_t blocks_per_sm) {
-    const uint32_t want = (n_threads_needed + block - 1) / block;
-    const uint32_t cap = (uint32_t)sm_count() * blocks_per_sm;
-    return want < cap ? (want ? want : 1u) : cap;
+static inline uint32_t blocks_for(uint64_t items, uint32_t per_block, uint32_t cap) {
+    uint64_t b = (items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    return (uint32_t)(b < cap ? b : cap);
 }
 
+uint32_t update_blocks(uint32_t n_pad) {
+    // one resident wave: 6 blocks of 256 threads per SM
+    return blocks_for(n_pad >> 2, UPDATE_THREADS, (uint32_t)sm_count() * 6u);
+}
 void launch_update(const DevView& v, cudaStream_t s) {
-    k_update<<<stream_grid(v.n_pad >> 2, 256, 8), 256, 0, s>>>(v);
+    k_update<<<v.n_update_blocks, UPDATE_THREADS, 0, s>>>(v);
 }
 void launch_expose(const DevView& v, cudaStream_t s) {
-    k_expose<<<stream_grid(v.n_pad >> 2, 256, 8), 256, 0, s>>>(v);
+    k_expose<<<blocks_for(v.n_pad >> 2, EXPOSE_THREADS, (uint32_t)sm_count() * 4u), EXPOSE_THREADS, 0, s>>>(v);
 }
 void launch_pt(const DevView& v, cudaStream_t s) {
     if (v.n_routes == 0) return;
-    k_pt<<<stream_grid(v.n_routes * 32u, 128, 16), 128, 0, s>>>(v);
+    // one warp per route, grid-stride; at most 8 resident blocks per SM
+    k_pt<<<blocks_for(v.n_routes, PT_THREADS / 32, (uint32_t)sm_count() * 8u), PT_THREADS, 0, s>>>(v);
 }
 void launch_tail(const DevView& v, cudaStream_t s) {
-    k_tail<<<1, TAIL_THREADS, TAIL_SMEM, s>>>(v);
+    k_tail<<<1, TAIL_THREADS, HT_BYTES, s>>>(v);
+}
+void launch_vax_prepare(const DevView& v, cudaStream_t s) {
+    k_vax_prepare<<<1, TAIL_THREADS, VP_SMEM, s>>>(v);
 }
 
 }  // namespace esim

@@ -401,7 +401,7 @@ int esim_shard_create(const EsimPopulationSoA* w, const uint32_t* area_off, uint
         std::memset(&p, 0, sizeof(p));
         p.n_citizens = n; p.n_areas = A; p.n_buildings = nb; p.n_rooms = nr;
         p.n_global_citizens = w->n_global_citizens ? w->n_global_citizens : N;
-        p.n_shared_bldgs = n_shared_b; p.n_shared_rooms = n_shared_r;
+        p.n_shared_bldgs = n_shared_b; p.n_shared_rooms = n_shared_r; p.n_shards = world;
         p.home_bldg = s->home.data(); p.work_bldg = s->work.data(); p.room = s->room.data();
         p.age = s->age.data(); p.occupation = s->occ.data(); p.flags = s->flags.data();
         p.status = s->status.data(); p.timer = s->timer.data(); p.global_id = s->gid.data();

@@ -41,6 +41,7 @@ class Population:
     n_global_citizens: int = 0
     n_shared_bldgs: int = 0
     n_shared_rooms: int = 0
+    n_shards: int = 0
     bldg_global: Optional[np.ndarray] = None  # shard-local -> whole-population ids
     room_global: Optional[np.ndarray] = None
     _keep: list = field(default_factory=list, repr=False)
@@ -67,6 +68,7 @@ class Population:
         s.n_global_citizens = self.n_global_citizens or self.n_citizens
         s.n_shared_bldgs = self.n_shared_bldgs
         s.n_shared_rooms = self.n_shared_rooms
+        s.n_shards = self.n_shards
         s.home_bldg = _ptr(self.home_bldg, C.c_uint32)
         s.work_bldg = _ptr(self.work_bldg, C.c_uint32)
         s.room = _ptr(self.room, C.c_uint32)
@@ -118,7 +120,7 @@ def _from_soa(s: _abi.EsimPopulationSoA, area_offsets=None, **extra) -> Populati
         area_offsets=area_offsets,
         global_id=arr(s.global_id, n, np.uint32) if s.global_id else None,
         n_global_citizens=int(s.n_global_citizens), n_shared_bldgs=int(s.n_shared_bldgs),
-        n_shared_rooms=int(s.n_shared_rooms), **extra)
+        n_shared_rooms=int(s.n_shared_rooms), n_shards=int(s.n_shards), **extra)
 
 
 def synthetic_population(n_areas: int = 637, pop_seed: int = 20110327, areas_per_school: int = 25,

@@ -125,6 +125,47 @@ class Simulator:
     def steps_done(self) -> int:
         return self._check(self._lib.esim_steps_done(self._h))
 
+    # -- sharded runs (one Simulator per GPU / rank) -------------------------------------------------------
+    def attach_comm(self, dist) -> None:
+        """Create the NCCL communicator of this shard group; `dist` is an initialised torch.distributed (any backend
+        that can broadcast 128 bytes).  Afterwards step() / run() issue the two all-reduces of a step themselves."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            self._check(self._lib.esim_comm_unique_id(ident))
+        dev = torch.device("cuda", self.cfg.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        self._check(self._lib.esim_comm_init(self._h, ident, rank, world))
+
+    def shard_step_begin(self) -> None:
+        self._check(self._lib.esim_shard_step_begin(self._h))
+
+    def shard_step_middle(self) -> None:
+        self._check(self._lib.esim_shard_step_middle(self._h))
+
+    def shard_step_end(self) -> bool:
+        s = _abi.EsimStepStats()
+        rc = self._check(self._lib.esim_shard_step_end(self._h, C.byref(s)))
+        self.last_stats = s
+        return rc == 1
+
+    def exchange_get(self, which: int) -> np.ndarray:
+        n = self._check(self._lib.esim_exchange_words(self._h, which))
+        out = np.zeros(max(n, 1), np.uint32)
+        if n:
+            self._check(self._lib.esim_exchange_get(self._h, which, out.ctypes.data_as(_abi.u32p)))
+        return out[:n]
+
+    def exchange_put(self, which: int, data: np.ndarray) -> None:
+        n = self._check(self._lib.esim_exchange_words(self._h, which))
+        data = np.ascontiguousarray(data, dtype=np.uint32)
+        assert data.shape[0] == n
+        if n:
+            self._check(self._lib.esim_exchange_put(self._h, which, data.ctypes.data_as(_abi.u32p)))
+
     # -- read-outs ---------------------------------------------------------------------------------------
     def statistics(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         """StatisticsRecorder::global_stats (+ intervention state) as an int64 matrix, one row per step."""

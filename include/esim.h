@@ -124,7 +124,7 @@ typedef struct EsimPopulationSoA {
     uint32_t n_global_citizens; /* 0 = n_citizens (single shard) */
     uint32_t n_shared_bldgs;    /* 0 for a single shard */
     uint32_t n_shared_rooms;    /* 0 for a single shard */
-    uint32_t reserved;
+    uint32_t n_shards;          /* 0 or 1 = the whole population; otherwise the number of shards of the run */
     /* per citizen */
     const uint32_t* home_bldg;  /* Citizen::household_code  (citizen.rs:116) */
     const uint32_t* work_bldg;  /* Citizen::workplace_code  (citizen.rs:118); == home_bldg: stays home */
@@ -232,6 +232,28 @@ int esim_inject_rng(EsimSim* sim, uint64_t seed);
 int esim_dump_statistics(EsimSim* sim, const char* directory, const char* const* area_codes);
 
 int esim_get_timings(EsimSim* sim, EsimTimings* out);
+
+/*
+ * Sharded runs: one handle per GPU, each holding the citizens of a contiguous range of output areas
+ * (esim_shard_create in esim_popgen.h).  A step has two exchange points, both a SUM over all shards of a small
+ * uint32 vector that is identical in layout on every shard:
+ *   ESIM_EXCH_COUNTS  after the update kernel: infected occupants present in the shared buildings, then the shared rooms
+ *                     (the per-building exposure counts of simulator.rs:56 for buildings used from several shards);
+ *   ESIM_EXCH_TAIL    before the tail: S/E/I/R/V, exposure counts, and the bit mask of the vaccination draws that are
+ *                     acceptable on their owner shard (choose_multiple, simulator.rs:525-527).
+ * Either attach an NCCL communicator (esim_comm_init: esim_step / esim_run then issue the two all-reduces on the
+ * handle's stream, inside the captured graph), or drive the three phases and move the vectors yourself.
+ */
+#define ESIM_EXCH_COUNTS 0
+#define ESIM_EXCH_TAIL   1
+int esim_comm_unique_id(uint8_t id[128]);                    /* ncclGetUniqueId, call on rank 0 and broadcast */
+int esim_comm_init(EsimSim* sim, const uint8_t id[128], uint32_t rank, uint32_t world);
+int esim_shard_step_begin(EsimSim* sim);                     /* update kernel; ESIM_EXCH_COUNTS holds this shard's part */
+int esim_shard_step_middle(EsimSim* sim);                    /* building + public-transport exposures; ESIM_EXCH_TAIL ready */
+int esim_shard_step_end(EsimSim* sim, EsimStepStats* out);   /* tail; same return value as esim_step */
+int esim_exchange_words(EsimSim* sim, int which);            /* length of the vector in uint32 words */
+int esim_exchange_get(EsimSim* sim, int which, uint32_t* out);
+int esim_exchange_put(EsimSim* sim, int which, const uint32_t* in);
 
 const char* esim_last_error(EsimSim* sim /* NULL = creation errors */);
 

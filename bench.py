@@ -55,18 +55,16 @@ def parse_args():
 
 
 def workload(args, world):
-    """configs[1] on one GPU; for N>1 the weak-scaling sweep of configs[4] (about 8.4 M citizens per GPU, x = 0.9)
-    unless --areas/--cross override it."""
-    if world == 1:
-        areas = args.areas or 11300
-        cross = args.cross if args.cross >= 0 else 0.0
-        name = "3.5M-citizen synthetic census-shaped population, 5000 hourly steps" if not args.areas else "synthetic"
+    """configs[1] on one GPU.  For N > 1 the same per-GPU workload is replicated N times along the output-area axis
+    (weak scaling: 11 300 areas ~ 3.45 M citizens per GPU), sharded by output area; --areas / --cross select the other
+    BASELINE configurations (e.g. --areas 27500 --cross 0.9 = configs[4], ~8.4 M citizens per GPU with dense mixing)."""
+    per_gpu = args.areas or 11300
+    cross = args.cross if args.cross >= 0 else 0.0
+    if world == 1 and not args.areas and cross == 0.0:
+        name = "3.5M-citizen synthetic census-shaped population, 5000 hourly steps"
     else:
-        per_gpu = args.areas or 27500
-        areas = per_gpu * world
-        cross = args.cross if args.cross >= 0 else 0.9
-        name = "UK-scale weak scaling, %d output areas (~8.4M citizens) per GPU, dense mixing x=%.2f" % (per_gpu, cross)
-    return dict(name=name, n_areas=areas, areas_per_school=67, cross_area_fraction=cross)
+        name = "synthetic census-shaped population, %d output areas per GPU x %d GPU(s), cross-area fraction %.2f" % (per_gpu, world, cross)
+    return dict(name=name, n_areas=per_gpu * world, areas_per_school=67, cross_area_fraction=cross)
 
 
 class ClockSampler:

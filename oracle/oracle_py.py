@@ -18,8 +18,8 @@ LIB = HERE / "liboracle.so"
 
 
 def build(force: bool = False) -> Path:
-    src = HERE / "oracle_push.cpp"
-    if force or not LIB.exists() or LIB.stat().st_mtime < src.stat().st_mtime:
+    srcs = [HERE / "oracle_push.cpp", HERE / "oracle_pull.cpp", HERE / "Makefile"]
+    if force or not LIB.exists() or any(LIB.stat().st_mtime < s.stat().st_mtime for s in srcs):
         proc = subprocess.run(["make", "-C", str(HERE), "-B" if force else "-s", "all"], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT, text=True)
         if proc.returncode != 0:
@@ -62,6 +62,18 @@ def lib() -> C.CDLL:
         L.oracle_disease_step.restype = C.c_uint32
         L.oracle_update_interventions.argtypes = [C.POINTER(_abi.EsimConfig), _abi.u32p, C.c_double]
         L.oracle_update_interventions.restype = C.c_uint32
+        L.pull_create.argtypes = [C.POINTER(_abi.EsimConfig), C.POINTER(_abi.EsimPopulationSoA), C.POINTER(vp)]
+        L.pull_destroy.argtypes = [vp]
+        L.pull_destroy.restype = None
+        L.pull_begin.argtypes = [vp]
+        L.pull_middle.argtypes = [vp]
+        L.pull_end.argtypes = [vp, _abi.u32p, C.POINTER(_abi.EsimStepStats)]
+        L.pull_exchange_words.argtypes = [vp, C.c_int]
+        L.pull_exchange_get.argtypes = [vp, C.c_int, _abi.u32p]
+        L.pull_exchange_put.argtypes = [vp, C.c_int, _abi.u32p]
+        L.pull_read_state.argtypes = [vp, C.POINTER(_abi.EsimStateView)]
+        L.pull_read_counts.argtypes = [vp, _abi.u32p, _abi.u32p]
+        L.pull_read_buses.argtypes = [vp, _abi.u32p, _abi.u32p]
         _lib = L
     return _lib
 
@@ -164,3 +176,74 @@ class Oracle:
         out = np.zeros(max(n, 1), np.uint32)
         self._L.oracle_read_area_exposures(self._h, area, out.ctypes.data_as(_abi.u32p), n)
         return out[:n]
+
+
+class PullShard:
+    """One shard of the pull-form CPU model (oracle/oracle_pull.cpp).  `allreduce(vector) -> vector` sums an exchange
+    vector over the shards; the default is the identity (a single shard)."""
+
+    def __init__(self, pop, cfg: _abi.EsimConfig | None = None, allreduce=None, **overrides):
+        self._L = lib()
+        self.cfg = cfg if cfg is not None else default_config(**overrides)
+        self.pop = pop
+        self.allreduce = allreduce or (lambda v: v)
+        self._h = C.c_void_p()
+        soa = pop.as_soa()
+        rc = self._L.pull_create(C.byref(self.cfg), C.byref(soa), C.byref(self._h))
+        if rc < 0:
+            raise _abi.SimError(rc, "pull_create")
+        self.rows = []
+
+    def close(self):
+        if self._h:
+            self._L.pull_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def _get(self, which):
+        n = self._L.pull_exchange_words(self._h, which)
+        out = np.zeros(max(n, 1), np.uint32)
+        self._L.pull_exchange_get(self._h, which, out.ctypes.data_as(_abi.u32p))
+        return out[:n]
+
+    def step(self):
+        self._L.pull_begin(self._h)
+        counts = np.ascontiguousarray(self.allreduce(self._get(0)), dtype=np.uint32)
+        if counts.size:
+            self._L.pull_exchange_put(self._h, 0, counts.ctypes.data_as(_abi.u32p))
+        self._L.pull_middle(self._h)
+        tail = np.ascontiguousarray(self.allreduce(self._get(1)), dtype=np.uint32)
+        s = _abi.EsimStepStats()
+        rc = self._L.pull_end(self._h, tail.ctypes.data_as(_abi.u32p), C.byref(s))
+        if rc < 0:
+            raise _abi.SimError(rc, "pull_end")
+        self.rows.append(s.as_tuple())
+        return rc == 1, s
+
+    def stats(self):
+        return np.array(self.rows, dtype=np.int64).reshape(len(self.rows), len(_abi.STATS_FIELDS))
+
+    def state(self):
+        n = self.pop.n_citizens
+        out = dict(status=np.zeros(n, np.uint8), timer=np.zeros(n, np.uint16), current_bldg=np.zeros(n, np.uint32),
+                   on_pt=np.zeros(n, np.uint8), vax_eligible=np.zeros(n, np.uint8))
+        v = _abi.EsimStateView()
+        v.status = out["status"].ctypes.data_as(_abi.u8p)
+        v.timer = out["timer"].ctypes.data_as(_abi.u16p)
+        v.current_bldg = out["current_bldg"].ctypes.data_as(_abi.u32p)
+        v.on_pt = out["on_pt"].ctypes.data_as(_abi.u8p)
+        v.vax_eligible = out["vax_eligible"].ctypes.data_as(_abi.u8p)
+        self._L.pull_read_state(self._h, C.byref(v))
+        return out
+
+    def building_counts(self):
+        b = np.zeros(self.pop.n_buildings, np.uint32)
+        r = np.zeros(max(self.pop.n_rooms, 1), np.uint32)
+        self._L.pull_read_counts(self._h, b.ctypes.data_as(_abi.u32p), r.ctypes.data_as(_abi.u32p))
+        return b, r[:self.pop.n_rooms]
+
+    def buses(self):
+        n = self.pop.n_citizens
+        idx = np.zeros(n, np.uint32)
+        inf = np.zeros(n, np.uint32)
+        self._L.pull_read_buses(self._h, idx.ctypes.data_as(_abi.u32p), inf.ctypes.data_as(_abi.u32p))
+        return idx, inf

@@ -140,6 +140,8 @@ def algorithmic_bytes(stats, n_citizens, n_cells):
 
 def cpu_baseline(pop, cfg_kwargs, seconds, min_steps=8):
     from oracle.oracle_py import Oracle, default_config
+    if int(os.environ.get("OMP_NUM_THREADS", "0") or 0) <= 1:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     orc = Oracle(pop, default_config(**cfg_kwargs))
     orc.run(2)  # touch every page once
     t0 = time.perf_counter()
@@ -159,6 +161,8 @@ def run_reference(args, wl, rank, world):
     """The reference's CPU implementation of the path: the oracle port on all host threads (rank 0 only)."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread it can get
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from epidemicsimulator_b200 import synthetic_population
     from oracle.oracle_py import Oracle, default_config
     pop = synthetic_population(wl["n_areas"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"])
@@ -203,7 +207,7 @@ def main():
     import torch
     import torch.distributed as dist
     from epidemicsimulator_b200 import _abi, build, synthetic_population, shard_population
-    from epidemicsimulator_b200.simulator import Simulator, default_config
+    from epidemicsimulator_b200.simulator import Simulator, default_config, pin_population
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
@@ -218,6 +222,7 @@ def main():
 
     whole = synthetic_population(wl["n_areas"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"])
     pop = whole if world == 1 else shard_population(whole, rank, world)
+    pop = pin_population(pop)   # page-locked host arrays: the host -> device copies of the import run at link speed
     n_total = whole.n_citizens
     cfg_kwargs = dict(seed=args.sim_seed, device=local_rank, max_time_step=max(5000, args.steps + args.warmup))
 
@@ -264,12 +269,13 @@ def main():
     sim.close()
 
     # ---- end to end through the public API with host buffers ------------------------------------------------------
+    state_out = Simulator.state_buffers(pop.n_citizens, pinned=True)   # caller-owned page-locked result buffers
     barrier()
     t0 = time.perf_counter()
     sim = make_sim()
     n_e2e = sim.run(args.steps)
     st_e2e = sim.statistics()
-    state = sim.state()
+    state = sim.state(out=state_out)
     barrier()
     e2e_seconds = time.perf_counter() - t0
     h2d = pop.input_bytes()

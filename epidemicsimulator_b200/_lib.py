@@ -75,6 +75,10 @@ def cuda_lib() -> C.CDLL:
     lib.esim_exchange_words.argtypes = [vp, C.c_int]
     lib.esim_exchange_get.argtypes = [vp, C.c_int, _abi.u32p]
     lib.esim_exchange_put.argtypes = [vp, C.c_int, _abi.u32p]
+    lib.esim_alloc_pinned.argtypes = [C.c_size_t]
+    lib.esim_alloc_pinned.restype = C.c_void_p
+    lib.esim_free_pinned.argtypes = [C.c_void_p]
+    lib.esim_free_pinned.restype = None
     lib.esim_last_error.argtypes = [vp]
     lib.esim_last_error.restype = C.c_char_p
     if lib.esim_abi_version() != _abi.ABI_VERSION:

@@ -21,7 +21,7 @@ INCLUDE = ROOT / "include"
 CUDA_LIB = PKG / "libesim_b200.so"
 HOST_LIB = PKG / "libesim_host.so"
 
-CUDA_SOURCES = ["esim_kernels.cu", "esim_api.cu"]
+CUDA_SOURCES = ["esim_kernels.cu", "esim_import.cu", "esim_api.cu"]
 HOST_SOURCES = ["popgen.cpp"]
 
 

@@ -7,16 +7,19 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "esim.h"
+#include "esim_import.h"
 #include "esim_internal.h"
 #include "esim_rng.h"
 
@@ -40,23 +43,45 @@ struct ApiError { int code; std::string msg; };
         if (_r != 0) throw ApiError{ESIM_ERR_COMM, std::string("NCCL: ") + (nccl_api() && nccl_api()->GetErrorString ? nccl_api()->GetErrorString(_r) : "error") + " in " #call}; \
     } while (0)
 
+// Device buffers come from the stream-ordered memory pool of the device (cudaMallocAsync): the pool keeps freed blocks, so
+// creating the next handle in the same process does not pay for cudaMalloc again.
+cudaStream_t g_pool_stream = nullptr;   // set by esim_create before any allocation of the handle
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    cudaStream_t stream = nullptr;
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+        stream = g_pool_stream;
+        if (count) CK(cudaMallocAsync(&p, count * sizeof(T), stream));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, stream);
         p = nullptr; n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }
 };
 
 constexpr int GRAPH_DAY = 24;  // steps captured in the bulk graph
+
+// Page-locked mailbox slots (control block + one statistics entry per handle) come from one process-wide arena:
+// cudaMallocHost costs milliseconds, a handle should not pay it.
+constexpr int MAILBOX_SLOTS = 64;
+constexpr size_t MAILBOX_BYTES = 512;
+struct MailboxArena {
+    unsigned char* base = nullptr;
+    bool used[MAILBOX_SLOTS] = {};
+    unsigned char* take() {
+        if (!base && cudaMallocHost(&base, MAILBOX_SLOTS * MAILBOX_BYTES) != cudaSuccess) { cudaGetLastError(); base = nullptr; return nullptr; }
+        for (int i = 0; i < MAILBOX_SLOTS; ++i)
+            if (!used[i]) { used[i] = true; return base + (size_t)i * MAILBOX_BYTES; }
+        return nullptr;
+    }
+    void give(unsigned char* p) { if (p && base) used[(p - base) / MAILBOX_BYTES] = false; }
+} g_mailboxes;
 
 // ---- NCCL through dlopen: the library is optional (single-GPU runs never touch it) ------------------------
 struct NcclApi {
@@ -111,6 +136,8 @@ struct EsimSim {
     void* comm = nullptr;               // ncclComm_t
     DevBuf<Ctrl> ctrl;
     DevBuf<EsimStepStats> stats;
+    unsigned char* mailbox = nullptr;   // slot of the pinned arena (or a private cudaMallocHost block when the arena is full)
+    bool mailbox_private = false;
     Ctrl* h_ctrl = nullptr;             // pinned
     EsimStepStats* h_stat = nullptr;    // pinned, one entry
     std::vector<uint32_t> h_bldg_area, h_room_parent;
@@ -148,8 +175,8 @@ struct EsimSim {
         cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt0.release(); cnt1.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
-        if (h_ctrl) cudaFreeHost(h_ctrl);
-        if (h_stat) cudaFreeHost(h_stat);
+        if (stream) cudaStreamSynchronize(stream);
+        if (mailbox_private) cudaFreeHost(mailbox); else g_mailboxes.give(mailbox);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -177,6 +204,20 @@ int guarded(EsimSim* s, F&& f) {
         return fail(s, ESIM_ERR_DEFAULT, "unknown error");
     }
 }
+
+// ESIM_TRACE=1 prints the wall-clock split of esim_import_population to stderr
+struct Tracer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Tracer() : on(getenv("ESIM_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what, cudaStream_t st = nullptr) {
+        if (!on) return;
+        if (st) cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[esim] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // Integer form of `RANDOM_DISTRUBUTION.sample(rng) < exposure_chance` (citizen.rs:242): the smallest 52-bit draw m
 // whose uniform value is >= prob, so that (u01(m) < prob) <=> (m < threshold).  u01 is monotone in m.
@@ -270,6 +311,7 @@ void require_ready(EsimSim* s) {
     if (!s) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null handle"};
     if (!s->imported) throw ApiError{ESIM_ERR_INITIALIZATION, "Population has not been Initialized"};
     CK(cudaSetDevice(s->device));
+    g_pool_stream = s->stream;
 }
 
 }  // namespace
@@ -319,8 +361,8 @@ int esim_create(const EsimConfig* cfg, EsimSim** out) {
         return fail(nullptr, ESIM_ERR_NO_DEVICE, "no CUDA device: libesim_b200 has no CPU fallback");
     }
     if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, ESIM_ERR_NO_DEVICE, "device ordinal out of range");
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    int cc_major = 0;   // (cudaGetDeviceProperties can take a hundred milliseconds; one attribute is all that is needed)
+    if (cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, cfg->device) != cudaSuccess || cc_major != 10)
         return fail(nullptr, ESIM_ERR_NO_DEVICE, "libesim_b200 is built for sm_100a (B200) only");
     EsimSim* s = new (std::nothrow) EsimSim();
     if (!s) return fail(nullptr, ESIM_ERR_DEFAULT, "out of host memory");
@@ -329,8 +371,17 @@ int esim_create(const EsimConfig* cfg, EsimSim** out) {
     const int rc = guarded(s, [&]() {
         CK(cudaSetDevice(s->device));
         CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-        CK(cudaMallocHost(&s->h_ctrl, sizeof(Ctrl)));
-        CK(cudaMallocHost(&s->h_stat, sizeof(EsimStepStats)));
+        {
+            cudaMemPool_t pool;
+            CK(cudaDeviceGetDefaultMemPool(&pool, s->device));
+            unsigned long long keep = ~0ull;   // keep freed blocks for the next handle instead of returning them to the driver
+            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        static_assert(sizeof(Ctrl) + sizeof(EsimStepStats) <= MAILBOX_BYTES, "mailbox slot too small");
+        s->mailbox = g_mailboxes.take();
+        if (!s->mailbox) { CK(cudaMallocHost(&s->mailbox, MAILBOX_BYTES)); s->mailbox_private = true; }
+        s->h_ctrl = reinterpret_cast<Ctrl*>(s->mailbox);
+        s->h_stat = reinterpret_cast<EsimStepStats*>(s->mailbox + 256);
         for (auto& e : s->ev) CK(cudaEventCreate(&e));
         CK((cudaError_t)configure_kernels());
         return ESIM_OK;
@@ -349,6 +400,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
             throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population arrays missing"};
         if (s->imported) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population already imported"};
         CK(cudaSetDevice(s->device));
+        g_pool_stream = s->stream;
         const uint32_t N = p->n_citizens, B = p->n_buildings, R = p->n_rooms, A = p->n_areas;
         if (N == 0 || B == 0 || A == 0) throw ApiError{ESIM_ERR_INVALID_POPULATION, "empty population"};
         if ((uint64_t)B + R >= 0xFFFFFFF0ull) throw ApiError{ESIM_ERR_INVALID_POPULATION, "too many buildings"};
@@ -357,82 +409,90 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         const uint32_t n_global = p->n_global_citizens ? p->n_global_citizens : N;
         const uint32_t shard_lo = p->global_id ? p->global_id[0] : 0u;
         if ((uint64_t)shard_lo + N > n_global) throw ApiError{ESIM_ERR_INVALID_POPULATION, "global ids exceed n_global_citizens"};
-        for (uint32_t b = 0; b < B; ++b)
-            if (p->bldg_area[b] >= A || p->bldg_type[b] > ESIM_BLDG_SCHOOL)
-                throw ApiError{ESIM_ERR_INVALID_POPULATION, "building with invalid area or type"};
-        for (uint32_t r = 0; r < R; ++r)
-            if (p->room_bldg[r] >= B || p->bldg_type[p->room_bldg[r]] != ESIM_BLDG_SCHOOL)
-                throw ApiError{ESIM_ERR_INVALID_POPULATION, "room whose building is not a school"};
         const uint32_t te = s->cfg.exposed_time, ti = s->cfg.infected_time;
+        cudaStream_t st = s->stream;
+        Tracer tr;
 
-        std::vector<uint32_t> cstate(n_pad, CS_ABSENT), home(n_pad, 0), work(n_pad, 0), gid(n_pad, 0);
-        std::vector<std::pair<uint64_t, uint32_t>> pt;  // (route key, citizen)
-        for (uint32_t i = 0; i < N; ++i) {
-            const uint32_t h = p->home_bldg[i], w = p->work_bldg[i], m = p->room[i];
-            if (h >= B || w >= B) throw ApiError{ESIM_ERR_MISSING_CITIZEN, "citizen references a building that does not exist"};
-            if (p->bldg_type[h] != ESIM_BLDG_HOUSEHOLD) throw ApiError{ESIM_ERR_INVALID_POPULATION, "household_code is not a Household"};
-            const bool school = p->bldg_type[w] == ESIM_BLDG_SCHOOL;
-            if (school != (m != ESIM_NO_ROOM) || (school && (m >= R || p->room_bldg[m] != w)) || (w == h && m != ESIM_NO_ROOM))
-                throw ApiError{ESIM_ERR_INVALID_POPULATION, "school membership and room assignment disagree"};
-            if (p->global_id && p->global_id[i] != shard_lo + i)
-                throw ApiError{ESIM_ERR_INVALID_POPULATION, "global_id must be contiguous and ascending inside a shard"};
-            const uint8_t f = p->flags ? p->flags[i] : 0;
-            uint32_t word = 0;
-            if (f & ESIM_FLAG_USES_PT) word |= CS_USES_PT;
-            if (f & ESIM_FLAG_MASK_COMPLIANT) word |= CS_COMPLIANT;
-            if (p->bldg_area[h] == p->bldg_area[w]) word |= CS_SAME_AREA;
-            const uint8_t st = p->status ? p->status[i] : (uint8_t)ESIM_STATUS_SUSCEPTIBLE;
-            const uint32_t tm = p->timer ? p->timer[i] : 0u;
-            // the hour of exposure that reproduces (status, timer) at time_step 0, see esim_internal.h
-            switch (st) {
-                case ESIM_STATUS_SUSCEPTIBLE: break;
-                case ESIM_STATUS_EXPOSED:
-                    if (tm > te) throw ApiError{ESIM_ERR_INVALID_POPULATION, "Exposed timer above exposed_time"};
-                    word |= EXPOSURE_BIAS - tm; break;
-                case ESIM_STATUS_INFECTED:
-                    if (tm > ti) throw ApiError{ESIM_ERR_INVALID_POPULATION, "Infected timer above infected_time"};
-                    word |= EXPOSURE_BIAS - (te + 1 + tm); break;
-                case ESIM_STATUS_RECOVERED: word |= EXPOSURE_BIAS - (te + ti + 2); break;
-                // vaccinated before the run: never Susceptible at the snapshot of the vaccination programme, so the
-                // exposure field is made non-zero (as for Recovered), which keeps it out of the eligible set
-                case ESIM_STATUS_VACCINATED: word |= CS_VACCINATED | (EXPOSURE_BIAS - (te + ti + 2)); break;
-                default: throw ApiError{ESIM_ERR_INVALID_POPULATION, "unknown disease status"};
-            }
-            cstate[i] = word;
-            home[i] = h;
-            work[i] = school ? B + m : w;
-            gid[i] = shard_lo + i;
-            if (f & ESIM_FLAG_USES_PT) pt.push_back({((uint64_t)p->bldg_area[h] << 32) | p->bldg_area[w], i});
+        // ---- raw arrays: one host -> device copy each (asynchronous when the caller's memory is pinned) ----
+        DevBuf<uint32_t> r_home, r_work, r_room, r_gid, r_area;
+        DevBuf<uint8_t> r_flags, r_status, r_btype, is_rider, head;
+        DevBuf<uint16_t> r_timer;
+        DevBuf<unsigned long long> route_key, keys_in, keys_out;
+        DevBuf<uint32_t> rider_idx, d_small;
+        DevBuf<unsigned char> temp;
+        struct Cleanup {
+            std::vector<std::function<void()>> f;
+            ~Cleanup() { for (auto& g : f) g(); }
+        } cleanup;
+        auto up = [&](auto& buf, const auto* host, size_t count) {
+            buf.alloc(count);
+            cleanup.f.push_back([&buf] { buf.release(); });
+            CK(cudaMemcpyAsync(buf.p, host, buf.bytes(), cudaMemcpyHostToDevice, st));
+        };
+        up(r_home, p->home_bldg, N); up(r_work, p->work_bldg, N); up(r_room, p->room, N);
+        if (p->global_id) up(r_gid, p->global_id, N);
+        if (p->flags) up(r_flags, p->flags, N);
+        if (p->status) up(r_status, p->status, N);
+        if (p->timer) up(r_timer, p->timer, N);
+        up(r_area, p->bldg_area, B); up(r_btype, p->bldg_type, B);
+        s->room_parent.alloc(std::max<uint32_t>(R, 1));
+        if (R) CK(cudaMemcpyAsync(s->room_parent.p, p->room_bldg, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+
+        tr.mark("upload raw arrays", st);
+        s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad); s->gid.alloc(n_pad);
+        is_rider.alloc(n_pad); route_key.alloc(n_pad); d_small.alloc(8);
+        cleanup.f.push_back([&] { is_rider.release(); route_key.release(); d_small.release(); keys_in.release(); keys_out.release();
+                                  rider_idx.release(); head.release(); temp.release(); });
+        CK(cudaMemsetAsync(d_small.p, 0, d_small.bytes(), st));
+        ImportRaw raw{};
+        raw.n = N; raw.n_areas = A; raw.n_bldg = B; raw.n_rooms = R; raw.shard_lo = shard_lo; raw.exposed_time = te; raw.infected_time = ti;
+        raw.home = r_home.p; raw.work = r_work.p; raw.room = r_room.p; raw.global_id = r_gid.p; raw.bldg_area = r_area.p;
+        raw.room_bldg = s->room_parent.p; raw.flags = r_flags.p; raw.status = r_status.p; raw.bldg_type = r_btype.p; raw.timer = r_timer.p;
+        ImportOut out{};
+        out.n_pad = n_pad; out.cstate = s->cstate.p; out.home_cell = s->home_cell.p; out.work_cell = s->work_cell.p; out.gid = s->gid.p;
+        out.is_rider = is_rider.p; out.route_key = route_key.p;
+        uint32_t* d_err = d_small.p;        // [0] code, [1] index
+        uint32_t* d_count = d_small.p + 4;  // [4] riders, [5] routes
+        CK(import_convert(raw, out, d_err, st));
+        tr.mark("convert kernels", st);
+
+        // ---- routes: riders grouped by (home area, work area), citizen order inside a route ----
+        const size_t temp_bytes = route_build_temp_bytes(n_pad);
+        temp.alloc(temp_bytes); rider_idx.alloc(n_pad);
+        CK(route_select_riders(out, n_pad, rider_idx.p, d_count, temp.p, temp_bytes, st));
+        uint32_t h_small[8];
+        CK(cudaMemcpyAsync(h_small, d_small.p, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_small[0]) {
+            static const char* what[] = {"", "building with invalid area or type", "room whose building is not a school",
+                                         "citizen references a building that does not exist", "household_code is not a Household",
+                                         "school membership and room assignment disagree",
+                                         "global_id must be contiguous and ascending inside a shard", "timer above its disease-model limit",
+                                         "unknown disease status"};
+            const uint32_t code = h_small[0] < 9 ? h_small[0] : 0;
+            throw ApiError{code == IMPORT_ERR_MISSING_BUILDING ? ESIM_ERR_MISSING_CITIZEN : ESIM_ERR_INVALID_POPULATION,
+                           std::string(what[code]) + " (index " + std::to_string(h_small[1]) + ")"};
         }
-        // routes: riders grouped by (home area, work area); citizen order inside a route
-        if (!std::is_sorted(pt.begin(), pt.end())) {
-            bool by_area = true;
-            for (size_t k = 1; k < pt.size() && by_area; ++k) by_area = (pt[k - 1].first >> 32) <= (pt[k].first >> 32);
-            if (by_area) {
-                size_t b0 = 0;
-                for (size_t k = 1; k <= pt.size(); ++k)
-                    if (k == pt.size() || (pt[k].first >> 32) != (pt[b0].first >> 32)) { std::sort(pt.begin() + b0, pt.begin() + k); b0 = k; }
-            } else {
-                std::sort(pt.begin(), pt.end());
-            }
+        const uint32_t n_riders = h_small[4];
+        s->riders.alloc(std::max<uint32_t>(n_riders, 1)); s->route_off.alloc((size_t)n_riders + 2);
+        uint32_t n_routes = 0;
+        if (n_riders) {
+            keys_in.alloc(n_riders); keys_out.alloc(n_riders); head.alloc(n_riders);
+            CK(route_sort_and_heads(out, rider_idx.p, n_riders, keys_in.p, keys_out.p, s->riders.p, head.p, s->route_off.p, d_count + 1,
+                                    temp.p, temp_bytes, st));
+            CK(cudaMemcpyAsync(h_small, d_small.p, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            n_routes = h_small[5];
         }
-        std::vector<uint32_t> route_off, riders(pt.size());
-        for (size_t k = 0; k < pt.size(); ++k) {
-            if (k == 0 || pt[k].first != pt[k - 1].first) route_off.push_back((uint32_t)k);
-            riders[k] = pt[k].second;
-        }
-        const uint32_t n_routes = (uint32_t)route_off.size();
-        route_off.push_back((uint32_t)pt.size());
+        CK(cudaMemcpyAsync(s->route_off.p + n_routes, &n_riders, 4, cudaMemcpyHostToDevice, st));  // closing offset
+        tr.mark("routes (select, sort, heads)", st);
 
         unsigned long long thr[512];
         build_thresholds(s->cfg, thr);
 
-        // ---- device allocation + upload ----
-        s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad); s->gid.alloc(n_pad);
-        s->room_parent.alloc(std::max<uint32_t>(R, 1)); s->cnt0.alloc((size_t)B + R + 4); s->cnt1.alloc((size_t)B + R + 4);
-        s->route_off.alloc(route_off.size()); s->riders.alloc(std::max<size_t>(riders.size(), 1));
-        s->pt_key.alloc(std::max<size_t>(riders.size(), 1)); s->pt_bus.alloc(std::max<size_t>(riders.size(), 1));
-        s->pt_buscnt.alloc(std::max<size_t>(riders.size(), 1));
+        s->cnt0.alloc((size_t)B + R + 4); s->cnt1.alloc((size_t)B + R + 4);
+        s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
+        s->pt_buscnt.alloc(std::max<uint32_t>(n_riders, 1));
         const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
         if (rec) { s->rec_bus.alloc(N); s->rec_businf.alloc(N); }
         const uint32_t n_update_blocks = update_blocks(n_pad);
@@ -440,40 +500,33 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         s->world = p->n_shards > 1 ? p->n_shards : 1;
         s->n_shared_bldgs = p->n_shared_bldgs; s->n_shared_rooms = p->n_shared_rooms;
         s->exch.alloc(EXCH_WORDS); s->vax_cand.alloc(ESIM_VAX_SHARD_DRAWS);
-        CK(cudaMemsetAsync(s->exch.p, 0, s->exch.bytes(), s->stream));
+        CK(cudaMemsetAsync(s->exch.p, 0, s->exch.bytes(), st));
         s->thr.alloc(512); s->ctrl.alloc(1); s->stats.alloc(s->cfg.max_time_step);
         if (s->cfg.flags & ESIM_CFG_FLUSH_L2) s->l2_scratch.alloc((size_t)256 << 20);  // 2x the 126 MB L2
-        CK(cudaMemcpyAsync(s->cstate.p, cstate.data(), s->cstate.bytes(), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemcpyAsync(s->home_cell.p, home.data(), s->home_cell.bytes(), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemcpyAsync(s->work_cell.p, work.data(), s->work_cell.bytes(), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemcpyAsync(s->gid.p, gid.data(), s->gid.bytes(), cudaMemcpyHostToDevice, s->stream));
-        if (R) CK(cudaMemcpyAsync(s->room_parent.p, p->room_bldg, (size_t)R * 4, cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemcpyAsync(s->route_off.p, route_off.data(), s->route_off.bytes(), cudaMemcpyHostToDevice, s->stream));
-        if (!riders.empty()) CK(cudaMemcpyAsync(s->riders.p, riders.data(), riders.size() * 4, cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemcpyAsync(s->thr.p, thr, sizeof(thr), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaMemsetAsync(s->cnt0.p, 0, s->cnt0.bytes(), s->stream));
-        CK(cudaMemsetAsync(s->tally_partial.p, 0, s->tally_partial.bytes(), s->stream));
-        CK(cudaMemsetAsync(s->cnt1.p, 0, s->cnt1.bytes(), s->stream));
-        CK(cudaMemsetAsync(s->stats.p, 0, s->stats.bytes(), s->stream));
+        CK(cudaMemcpyAsync(s->thr.p, thr, sizeof(thr), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(s->cnt0.p, 0, s->cnt0.bytes(), st));
+        CK(cudaMemsetAsync(s->tally_partial.p, 0, s->tally_partial.bytes(), st));
+        CK(cudaMemsetAsync(s->cnt1.p, 0, s->cnt1.bytes(), st));
         if (rec) {
-            CK(cudaMemsetAsync(s->rec_bus.p, 0xFF, s->rec_bus.bytes(), s->stream));
-            CK(cudaMemsetAsync(s->rec_businf.p, 0, s->rec_businf.bytes(), s->stream));
+            CK(cudaMemsetAsync(s->rec_bus.p, 0xFF, s->rec_bus.bytes(), st));
+            CK(cudaMemsetAsync(s->rec_businf.p, 0, s->rec_businf.bytes(), st));
         }
         Ctrl c0;
         std::memset(&c0, 0, sizeof(c0));
         c0.eager_expose = 1;
         c0.t = 1;  // the first hour is 1 (statistics.rs:167); everybody starts at home, off public transport (citizen.rs:156-160)
         std::memcpy(s->h_ctrl, &c0, sizeof(c0));
-        CK(cudaMemcpyAsync(s->ctrl.p, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaStreamSynchronize(s->stream));
+        CK(cudaMemcpyAsync(s->ctrl.p, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+        tr.mark("thresholds, allocations, memsets", st);
 
         s->h_bldg_area.assign(p->bldg_area, p->bldg_area + B);
         if (R) s->h_room_parent.assign(p->room_bldg, p->room_bldg + R);
         s->n_areas = A;
 
+        tr.mark("host copies of area tables");
         DevView& v = s->v;
         v.n = N; v.n_pad = n_pad; v.n_bldg = B; v.n_rooms = R; v.n_cells = B + R;
-        v.n_routes = n_routes; v.n_riders = (uint32_t)riders.size(); v.record_buses = rec ? 1u : 0u;
+        v.n_routes = n_routes; v.n_riders = n_riders; v.record_buses = rec ? 1u : 0u;
         v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
         v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt0.p; v.cnt[1] = s->cnt1.p; v.thr = s->thr.p;
         v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
@@ -492,6 +545,8 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
                           s->room_parent.bytes() + s->cnt0.bytes() * 2 + s->route_off.bytes() + s->riders.bytes() * 4 +
                           s->rec_bus.bytes() * 2 + s->stats.bytes();
         if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH) && s->world == 1) capture_graphs(s);  // sharded: captured by esim_comm_init
+        tr.mark("graph capture", st);
+        CK(cudaStreamSynchronize(st));
         s->imported = true;
         s->steps_done = 0;
         s->finished = false;
@@ -637,42 +692,39 @@ int esim_read_state(EsimSim* s, EsimStateView* view) {
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (!view) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null view"};
-        HostState h;
-        download_state(s, h, view->current_bldg != nullptr);
-        const Ctrl& c = h.ctrl;
-        // the control block already holds the schedule of the *next* step; the state after the last executed step is in
-        // the recorded statistics entry
-        uint32_t at_work = 0, pt_mode = ESIM_PT_NONE;
-        const uint32_t t_last = s->steps_done;  // state after this step's progression
-        if (t_last > 0) {
+        fetch_ctrl(s);
+        const Ctrl c = *s->h_ctrl;
+        // the control block already holds the schedule of the *next* step; the position after the last executed step is in
+        // that step's statistics entry
+        ExportArgs a{};
+        a.n = s->v.n; a.n_bldg = s->v.n_bldg; a.t_last = s->steps_done;
+        if (s->steps_done > 0) {
             EsimStepStats last;
-            CK(cudaMemcpy(&last, s->stats.p + (t_last - 1), sizeof(last), cudaMemcpyDeviceToHost));
-            at_work = last.at_work; pt_mode = last.pt_mode;
+            CK(cudaMemcpyAsync(&last, s->stats.p + (s->steps_done - 1), sizeof(last), cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            a.at_work = last.at_work; a.pt_mode = last.pt_mode;
         }
-        const uint32_t te = s->cfg.exposed_time, ti = s->cfg.infected_time, B = s->v.n_bldg;
-        for (uint32_t i = 0; i < s->v.n; ++i) {
-            uint32_t w = h.cstate[i];
-            if (c.vax_all_pending && host_eligible(w, c)) w |= CS_VACCINATED;
-            uint8_t st; uint16_t tm = 0;
-            const uint32_t e = w & CS_E_MASK;
-            if (w & CS_VACCINATED) st = ESIM_STATUS_VACCINATED;
-            else if (e == 0) st = ESIM_STATUS_SUSCEPTIBLE;
-            else {
-                const int d = (int)t_last - ((int)e - (int)EXPOSURE_BIAS);
-                if (d <= (int)te) { st = ESIM_STATUS_EXPOSED; tm = (uint16_t)d; }
-                else if (d <= (int)(te + 1 + ti)) { st = ESIM_STATUS_INFECTED; tm = (uint16_t)(d - (int)te - 1); }
-                else st = ESIM_STATUS_RECOVERED;
-            }
-            if (view->status) view->status[i] = st;
-            if (view->timer) view->timer[i] = tm;
-            if (view->current_bldg) {
-                uint32_t cell = at_work ? h.work[i] : h.home[i];
-                if (cell >= B) cell = s->h_room_parent[cell - B];
-                view->current_bldg[i] = cell;
-            }
-            if (view->on_pt) view->on_pt[i] = (w & CS_USES_PT) ? (uint8_t)pt_mode : (uint8_t)ESIM_PT_NONE;
-            if (view->vax_eligible) view->vax_eligible[i] = host_eligible(w, c) ? 1 : 0;
-        }
+        a.vax_some = c.vax_some; a.vax_start_step = c.vax_start_step; a.vax_all_pending = c.vax_all_pending;
+        a.exposed_time = s->cfg.exposed_time; a.infected_time = s->cfg.infected_time;
+        a.cstate = s->cstate.p; a.home_cell = s->home_cell.p; a.work_cell = s->work_cell.p; a.room_parent = s->room_parent.p;
+        const size_t n = s->v.n;
+        DevBuf<uint8_t> d_status, d_on_pt, d_elig;
+        DevBuf<uint16_t> d_timer;
+        DevBuf<uint32_t> d_cur;
+        struct Rel { DevBuf<uint8_t>&a, &b, &c; DevBuf<uint16_t>& d; DevBuf<uint32_t>& e;
+                     ~Rel() { a.release(); b.release(); c.release(); d.release(); e.release(); } } rel{d_status, d_on_pt, d_elig, d_timer, d_cur};
+        if (view->status) { d_status.alloc(n); a.status = d_status.p; }
+        if (view->timer) { d_timer.alloc(n); a.timer = d_timer.p; }
+        if (view->current_bldg) { d_cur.alloc(n); a.current_bldg = d_cur.p; }
+        if (view->on_pt) { d_on_pt.alloc(n); a.on_pt = d_on_pt.p; }
+        if (view->vax_eligible) { d_elig.alloc(n); a.vax_eligible = d_elig.p; }
+        CK(export_state(a, s->stream));
+        if (view->status) CK(cudaMemcpyAsync(view->status, d_status.p, n, cudaMemcpyDeviceToHost, s->stream));
+        if (view->timer) CK(cudaMemcpyAsync(view->timer, d_timer.p, n * 2, cudaMemcpyDeviceToHost, s->stream));
+        if (view->current_bldg) CK(cudaMemcpyAsync(view->current_bldg, d_cur.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+        if (view->on_pt) CK(cudaMemcpyAsync(view->on_pt, d_on_pt.p, n, cudaMemcpyDeviceToHost, s->stream));
+        if (view->vax_eligible) CK(cudaMemcpyAsync(view->vax_eligible, d_elig.p, n, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
         return ESIM_OK;
     });
 }
@@ -925,6 +977,13 @@ static int exchange_copy(EsimSim* s, int which, uint32_t* host, bool to_host) {
 }
 int esim_exchange_get(EsimSim* s, int which, uint32_t* out) { return exchange_copy(s, which, out, true); }
 int esim_exchange_put(EsimSim* s, int which, const uint32_t* in) { return exchange_copy(s, which, const_cast<uint32_t*>(in), false); }
+
+void* esim_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void esim_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 const char* esim_last_error(EsimSim* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
 

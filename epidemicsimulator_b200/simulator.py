@@ -34,6 +34,56 @@ def default_config(**overrides) -> _abi.EsimConfig:
     return cfg
 
 
+class _PinnedBlock:
+    """A cudaMallocHost allocation that lives as long as the numpy arrays viewing it."""
+
+    def __init__(self, nbytes: int):
+        self._lib = cuda_lib()
+        self.ptr = self._lib.esim_alloc_pinned(nbytes)
+        if not self.ptr:
+            raise MemoryError("esim_alloc_pinned(%d) failed" % nbytes)
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            self._lib.esim_free_pinned(self.ptr)
+        except Exception:
+            pass
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray subclass that keeps its cudaMallocHost block alive."""
+    _block = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._block = getattr(obj, "_block", None)
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """A page-locked numpy array (host <-> device copies from it run asynchronously at full link speed)."""
+    dt = np.dtype(dtype)
+    block = _PinnedBlock(max(n * dt.itemsize, 1))
+    buf = (C.c_uint8 * block.nbytes).from_address(block.ptr)
+    arr = np.frombuffer(buf, dtype=dt, count=n).view(_PinnedArray)
+    arr._block = block
+    return arr
+
+
+def pin_population(pop: Population) -> Population:
+    """Copy of `pop` whose arrays live in page-locked host memory."""
+    out = pop.copy()
+    for name in ("home_bldg", "work_bldg", "room", "age", "occupation", "flags", "status", "timer", "bldg_area", "bldg_type",
+                 "room_bldg", "global_id"):
+        a = getattr(out, name)
+        if a is None:
+            continue
+        b = pinned_empty(a.shape[0], a.dtype)
+        b[:] = a
+        setattr(out, name, b)
+    return out
+
+
 class DiseaseModel:
     """sim/src/disease.rs:97-129"""
 
@@ -177,10 +227,17 @@ class Simulator:
         n = self._check(self._lib.esim_read_stats(self._h, first, count, buf.ctypes.data_as(C.POINTER(_abi.EsimStepStats))))
         return buf[:n].astype(np.int64)
 
-    def state(self) -> Dict[str, np.ndarray]:
+    @staticmethod
+    def state_buffers(n: int, pinned: bool = False) -> Dict[str, np.ndarray]:
+        """Output buffers for state(); page-locked ones make the device -> host copies asynchronous and fast."""
+        mk = pinned_empty if pinned else (lambda k, dt: np.zeros(k, dt))
+        return dict(status=mk(n, np.uint8), timer=mk(n, np.uint16), current_bldg=mk(n, np.uint32),
+                    on_pt=mk(n, np.uint8), vax_eligible=mk(n, np.uint8))
+
+    def state(self, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         n = self.pop.n_citizens
-        out = dict(status=np.zeros(n, np.uint8), timer=np.zeros(n, np.uint16), current_bldg=np.zeros(n, np.uint32),
-                   on_pt=np.zeros(n, np.uint8), vax_eligible=np.zeros(n, np.uint8))
+        if out is None:
+            out = self.state_buffers(n)
         v = _abi.EsimStateView()
         v.status = out["status"].ctypes.data_as(_abi.u8p)
         v.timer = out["timer"].ctypes.data_as(_abi.u16p)

@@ -19,6 +19,7 @@
 #ifndef ESIM_H
 #define ESIM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -254,6 +255,11 @@ int esim_shard_step_end(EsimSim* sim, EsimStepStats* out);   /* tail; same retur
 int esim_exchange_words(EsimSim* sim, int which);            /* length of the vector in uint32 words */
 int esim_exchange_get(EsimSim* sim, int which, uint32_t* out);
 int esim_exchange_put(EsimSim* sim, int which, const uint32_t* in);
+
+/* Page-locked host memory (cudaMallocHost): population arrays and read-out buffers placed here are copied
+ * asynchronously at full PCIe / C2C speed; any other host memory works too, only slower. */
+void* esim_alloc_pinned(size_t bytes);
+void  esim_free_pinned(void* p);
 
 const char* esim_last_error(EsimSim* sim /* NULL = creation errors */);
 

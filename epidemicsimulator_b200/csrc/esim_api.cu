@@ -348,7 +348,7 @@ int esim_create(const EsimConfig* cfg, EsimSim** out) {
     if (!cfg || !out) return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     if (cfg->max_time_step == 0 || cfg->max_time_step > MAX_STEPS)
-        return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "max_time_step must be in [1, 64510]");
+        return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "max_time_step must be in [1, 31742]");
     if (cfg->exposed_time + cfg->infected_time + 2 >= EXPOSURE_BIAS)
         return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "exposed_time + infected_time must be below 1022");
     if (cfg->bus_capacity == 0) return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "bus_capacity must be positive");
@@ -682,7 +682,7 @@ void download_state(EsimSim* s, HostState& h, bool cells) {
 }
 inline bool host_eligible(uint32_t w, const Ctrl& c) {
     if (!c.vax_some) return false;
-    const uint32_t e = w & CS_E_MASK;
+    const uint32_t e = w & CS_EXPOSURE;
     if (e == 0) return true;
     return (int)e - (int)EXPOSURE_BIAS > (int)c.vax_start_step && !(w & CS_VIA_PT);
 }
@@ -806,7 +806,7 @@ int esim_dump_statistics(EsimSim* s, const char* directory, const char* const* a
             const uint32_t B = s->v.n_bldg;
             std::vector<std::map<uint32_t, uint32_t>> per_area(s->n_areas);
             for (uint32_t i = 0; i < s->v.n; ++i) {
-                const uint32_t w = h.cstate[i], e = w & CS_E_MASK;
+                const uint32_t w = h.cstate[i], e = w & CS_EXPOSURE;
                 if (e <= EXPOSURE_BIAS || (w & CS_VIA_PT)) continue;
                 const uint32_t x = e - EXPOSURE_BIAS;
                 if (x == 0 || x > T) continue;

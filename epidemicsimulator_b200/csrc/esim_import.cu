@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_import(ImportRaw r, ImportOut o, uint32
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= o.n_pad) return;
     if (i >= r.n) {
-        o.cstate[i] = CS_ABSENT; o.home_cell[i] = 0; o.work_cell[i] = 0; o.gid[i] = 0; o.is_rider[i] = 0; o.route_key[i] = 0;
+        o.cstate[i] = CS_PADDING; o.home_cell[i] = 0; o.work_cell[i] = 0; o.gid[i] = 0; o.is_rider[i] = 0; o.route_key[i] = 0;
         return;
     }
     const uint32_t h = r.home[i], w = r.work[i], m = r.room[i];
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) k_import(ImportRaw r, ImportOut o, uint32
         if (f & ESIM_FLAG_MASK_COMPLIANT) word |= CS_COMPLIANT;
         const uint32_t ah = r.bldg_area[h], aw = r.bldg_area[w];
         if (ah == aw) word |= CS_SAME_AREA;
+        if (w != h) word |= CS_HAS_WORK;
         const uint32_t st = r.status ? r.status[i] : (uint32_t)ESIM_STATUS_SUSCEPTIBLE;
         const uint32_t tm = r.timer ? r.timer[i] : 0u;
         // the hour of exposure that reproduces (status, timer) at time step 0, see esim_internal.h
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) k_export_state(ExportArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     uint32_t w = a.cstate[i];
-    const uint32_t e = w & CS_E_MASK;
+    const uint32_t e = w & CS_EXPOSURE;
     bool elig = false;
     if (a.vax_some) elig = e == 0 || ((int)e - (int)EXPOSURE_BIAS > (int)a.vax_start_step && !(w & CS_VIA_PT));
     if (a.vax_all_pending && elig) w |= CS_VACCINATED;

@@ -12,26 +12,32 @@ namespace esim {
 // infected citizen every hour (disease.rs:47-71).  Both timers are pure functions of the hour of exposure, so the
 // state word stores that hour once and no citizen is rewritten while it progresses E -> I -> R:
 //
-//   bits  0..15  E = 0 (never exposed) or (time_step of the exposure + EXPOSURE_BIAS)
-//   bit   16     vaccinated (DiseaseStatus::Vaccinated overrides whatever E encodes, simulator.rs:551)
-//   bit   17     exposed on public transport (removed from citizens_eligible_for_vaccine, simulator.rs:447-449)
-//   bit   18     uses_public_transport       (static, citizen.rs:132)
-//   bit   19     is_mask_compliant           (static, citizen.rs:131)
-//   bit   20     household and workplace stand in the same output area (static; the simulator.rs:324 filter)
-//   bit   31     padding slot: not a citizen
+//   bits  0..14  E = 0 (never exposed) or (time_step of the exposure + EXPOSURE_BIAS)
+//   bit   15     vaccinated (DiseaseStatus::Vaccinated overrides whatever E encodes, simulator.rs:551)
+//   bit   16     exposed on public transport (removed from citizens_eligible_for_vaccine, simulator.rs:447-449)
+//   bit   17     uses_public_transport       (static, citizen.rs:132)
+//   bit   18     is_mask_compliant           (static, citizen.rs:131)
+//   bit   19     household and workplace stand in the same output area (static; the simulator.rs:324 filter)
+//   bit   20     workplace_code != household_code (static)
+//   padding slots hold CS_PADDING (counted as vaccinated by k_update and subtracted again by the tail)
 //
 // With d = time_step - (E - EXPOSURE_BIAS):  d <= exposed_time                     -> Exposed(d)
 //                                            d <= exposed_time + 1 + infected_time -> Infected(d - exposed_time - 1)
 //                                            otherwise                             -> Recovered
-constexpr uint32_t CS_E_MASK      = 0xFFFFu;
-constexpr uint32_t CS_VACCINATED  = 1u << 16;
-constexpr uint32_t CS_VIA_PT      = 1u << 17;
-constexpr uint32_t CS_USES_PT     = 1u << 18;
-constexpr uint32_t CS_COMPLIANT   = 1u << 19;
-constexpr uint32_t CS_SAME_AREA   = 1u << 20;
-constexpr uint32_t CS_ABSENT      = 1u << 31;
+// The low 16 bits order the five states for a given hour, so a tally is four unsigned comparisons:
+//   0 = Susceptible < [1, I_lo) Recovered < [I_lo, E_lo) Infected < [E_lo, 0x8000) Exposed < [0x8000, 0xFFFF] Vaccinated
+//   with E_lo = t + BIAS - exposed_time and I_lo = E_lo - 1 - infected_time.
+constexpr uint32_t CS_LOW16       = 0xFFFFu;
+constexpr uint32_t CS_EXPOSURE    = 0x7FFFu;
+constexpr uint32_t CS_VACCINATED  = 1u << 15;
+constexpr uint32_t CS_VIA_PT      = 1u << 16;
+constexpr uint32_t CS_USES_PT     = 1u << 17;
+constexpr uint32_t CS_COMPLIANT   = 1u << 18;
+constexpr uint32_t CS_SAME_AREA   = 1u << 19;
+constexpr uint32_t CS_HAS_WORK    = 1u << 20;
+constexpr uint32_t CS_PADDING     = 0xFFFFu;
 constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 2
-constexpr uint32_t MAX_STEPS      = 0xFFFFu - EXPOSURE_BIAS - 1;
+constexpr uint32_t MAX_STEPS      = CS_EXPOSURE - EXPOSURE_BIAS - 1;
 #define ESIM_VAX_SHARD_DRAWS 8192u   // vaccination candidate draws a sharded run examines per step
 constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer, see k_vax_prepare
 

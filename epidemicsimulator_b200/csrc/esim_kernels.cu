@@ -24,7 +24,7 @@ constexpr int ST_S = ESIM_STATUS_SUSCEPTIBLE, ST_E = ESIM_STATUS_EXPOSED, ST_I =
 // DiseaseStatus::execute_time_step (disease.rs:47-71) in closed form, see esim_internal.h
 __device__ __forceinline__ int status_at(uint32_t w, uint32_t t, uint32_t te, uint32_t ti) {
     if (w & CS_VACCINATED) return ST_V;
-    const uint32_t e = w & CS_E_MASK;
+    const uint32_t e = w & CS_EXPOSURE;
     if (e == 0) return ST_S;
     const int d = (int)t - ((int)e - (int)EXPOSURE_BIAS);
     if (d <= (int)te) return ST_E;
@@ -36,8 +36,7 @@ __device__ __forceinline__ int status_at(uint32_t w, uint32_t t, uint32_t te, ui
 // (simulator.rs:487-513), minus citizens exposed on public transport afterwards (simulator.rs:447-449); citizens
 // exposed in buildings or already vaccinated stay in the set (the removal at simulator.rs:346-348 is dead code).
 __device__ __forceinline__ bool vax_eligible(uint32_t w, uint32_t vax_start_step) {
-    if (w & CS_ABSENT) return false;
-    const uint32_t e = w & CS_E_MASK;
+    const uint32_t e = w & CS_EXPOSURE;
     if (e == 0) return true;
     const int s = (int)e - (int)EXPOSURE_BIAS;
     return s > (int)vax_start_step && !(w & CS_VIA_PT);
@@ -46,14 +45,26 @@ __device__ __forceinline__ bool vax_eligible(uint32_t w, uint32_t vax_start_step
 __device__ __forceinline__ uint32_t warp_sum(uint32_t x) { return __reduce_add_sync(0xffffffffu, x); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-constexpr uint32_t NOT_SUSCEPTIBLE = CS_E_MASK | CS_VACCINATED | CS_ABSENT;
+// k_update counts cumulatively (#code != 0, #code >= i_lo, #code >= e_lo, #code >= 0x8000) over all n_pad slots, the padding
+// slots counting as vaccinated: turn that into S, E, I, R, V of the n real citizens.
+__device__ __forceinline__ void classes_from_cumulative(const uint32_t* cum, uint32_t n_pad, uint32_t n, uint32_t* out5) {
+    out5[0] = n_pad - cum[0];            // susceptible
+    out5[1] = cum[2] - cum[3];           // exposed
+    out5[2] = cum[1] - cum[2];           // infected
+    out5[3] = cum[0] - cum[1];           // recovered
+    out5[4] = cum[3] - (n_pad - n);      // vaccinated
+}
+
+// susceptible <=> never exposed and not vaccinated <=> the low 16 bits are zero (padding slots hold 0xFFFF)
+__device__ __forceinline__ bool is_susceptible(uint32_t w) { return (w & CS_LOW16) == 0u; }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
-// k_update: persistent grid (one wave), every thread keeps four 128-bit loads of state words in flight.  It also zeroes
-// the count buffer of the next step (a coalesced stream of 128-bit stores).  The S/E/I/R/V tallies leave the kernel as one
-// partial sum per block (no atomics): the tail adds them up.
+// k_update: persistent grid (one wave), every thread keeps four 128-bit loads of state words in flight.  The five-way
+// tally is four unsigned comparisons per citizen (see esim_internal.h); the rare infected citizens are handled in a second
+// pass over the thread's registers so that the common path has no divergent branch.  It also zeroes the count buffer of
+// the next step.  The tallies leave the kernel as one partial sum per block (no atomics): the tail adds them up.
 constexpr int UPDATE_THREADS = 256;
 constexpr int UPDATE_UNROLL = 4;
 
@@ -62,57 +73,81 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
-    const uint4 absent4 = make_uint4(CS_ABSENT, CS_ABSENT, CS_ABSENT, CS_ABSENT);
+    const uint4 none4 = make_uint4(0u, 0u, 0u, 0u);   // quads past the end: an all-zero word adds nothing to the cumulative counts
     if (c->finished) return;
-    const uint32_t t = c->t, at_work = c->at_work, pt_active = c->pt_mode != ESIM_PT_NONE;
+    const uint32_t t = c->t, at_work = c->at_work;
     const uint32_t vax_all = c->vax_all_pending, vax_start = c->vax_start_step;
-    const uint32_t te = v.mp.exposed_time, ti = v.mp.infected_time;
+    // riders only count on their bus (simulator.rs:181-198): while public transport runs, a rider is never "present"
+    const uint32_t rider_mask = c->pt_mode != ESIM_PT_NONE ? CS_USES_PT : 0u;
+    const uint32_t e_lo = t + EXPOSURE_BIAS - v.mp.exposed_time;          // first exposure code that is still Exposed
+    const uint32_t i_lo = e_lo - 1u - v.mp.infected_time;                 // first exposure code that is still Infected
     const uint32_t* __restrict__ pos = at_work ? v.work_cell : v.home_cell;
     uint32_t* __restrict__ cnt = v.cnt[t & 1u];
     uint4* __restrict__ cnt_next = reinterpret_cast<uint4*>(v.cnt[(t + 1u) & 1u]);
 
     for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_next[z] = make_uint4(0u, 0u, 0u, 0u);
 
-    uint32_t n_s = 0, n_e = 0, n_i = 0, n_r = 0, n_v = 0;
+    uint32_t c_exp = 0, c_inf = 0, c_ei = 0, c_vax = 0;   // #(code != 0), #(code >= i_lo), #(code >= e_lo), #(code >= 0x8000)
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += UPDATE_UNROLL * T) {
         uint4 cur[UPDATE_UNROLL];
 #pragma unroll
-        for (int u = 0; u < UPDATE_UNROLL; ++u) { const uint32_t q = q0 + u * T; cur[u] = q < n_quads ? cs4[q] : absent4; }
+        for (int u = 0; u < UPDATE_UNROLL; ++u) { const uint32_t q = q0 + u * T; cur[u] = q < n_quads ? cs4[q] : none4; }
+        if (vax_all) {
+            // choose_multiple took the whole eligible set at the end of the previous step (simulator.rs:525-552)
+#pragma unroll
+            for (int u = 0; u < UPDATE_UNROLL; ++u) {
+                uint32_t* w = reinterpret_cast<uint32_t*>(&cur[u]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t i = ((q0 + u * T) << 2) + (uint32_t)k;
+                    if (i < v.n && !(w[k] & CS_VACCINATED) && vax_eligible(w[k], vax_start)) { w[k] |= CS_VACCINATED; v.cstate[i] = w[k]; }
+                }
+            }
+        }
+        uint32_t any_present_infected = 0;
 #pragma unroll
         for (int u = 0; u < UPDATE_UNROLL; ++u) {
-            uint32_t w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+            const uint32_t w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (w[k] & CS_ABSENT) continue;
-                const uint32_t i = ((q0 + u * T) << 2) + (uint32_t)k;
-                if (vax_all && !(w[k] & CS_VACCINATED) && vax_eligible(w[k], vax_start)) {
-                    w[k] |= CS_VACCINATED;  // choose_multiple took the whole eligible set (simulator.rs:525-552)
-                    v.cstate[i] = w[k];
-                }
-                const int st = status_at(w[k], t, te, ti);
-                // StatisticEntry::add_citizen (statistics.rs:256-272)
-                n_s += st == ST_S; n_e += st == ST_E; n_i += st == ST_I; n_r += st == ST_R; n_v += st == ST_V;
-                // a rider only counts on its bus; otherwise an infected citizen marks its current building (simulator.rs:181-198)
-                if (st == ST_I && !(pt_active && (w[k] & CS_USES_PT))) {
-                    const uint32_t cell = pos[i];
-                    atomicAdd(&cnt[cell], 1u);
-                    if (cell >= v.n_bldg) atomicAdd(&cnt[v.room_parent[cell - v.n_bldg]], 1u);
+                const uint32_t code = w[k] & CS_LOW16;
+                // StatisticEntry::add_citizen (statistics.rs:256-272) as cumulative counts
+                c_exp += code != 0u;
+                c_inf += code >= i_lo;
+                c_ei += code >= e_lo;
+                c_vax += code >> 15;
+                any_present_infected |= (code >= i_lo) & (code < e_lo) & ((w[k] & rider_mask) == 0u);
+            }
+        }
+        if (any_present_infected) {
+            // an infected citizen marks its current building, and its room inside a school (simulator.rs:187-198)
+#pragma unroll
+            for (int u = 0; u < UPDATE_UNROLL; ++u) {
+                const uint32_t w[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t code = w[k] & CS_LOW16;
+                    if (code >= i_lo && code < e_lo && (w[k] & rider_mask) == 0u) {
+                        const uint32_t cell = pos[((q0 + u * T) << 2) + (uint32_t)k];
+                        atomicAdd(&cnt[cell], 1u);
+                        if (cell >= v.n_bldg) atomicAdd(&cnt[v.room_parent[cell - v.n_bldg]], 1u);
+                    }
                 }
             }
         }
     }
-    // block reduction of the five counters -> tally_partial[block]
-    __shared__ uint32_t s_cnt[5];
-    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+    // block reduction -> tally_partial[block] = {susceptible-complement, ...}: the tail turns the cumulative counts into S,E,I,R,V
+    __shared__ uint32_t s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t cnt5[5] = {warp_sum(n_s), warp_sum(n_e), warp_sum(n_i), warp_sum(n_r), warp_sum(n_v)};
+    const uint32_t r4[4] = {warp_sum(c_exp), warp_sum(c_inf), warp_sum(c_ei), warp_sum(c_vax)};
     if (lane_id() == 0) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
-            if (cnt5[k]) atomicAdd(&s_cnt[k], cnt5[k]);
+        for (int k = 0; k < 4; ++k)
+            if (r4[k]) atomicAdd(&s_cnt[k], r4[k]);
     }
     __syncthreads();
-    if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 5 ? s_cnt[threadIdx.x] : 0u;
+    if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -134,23 +169,28 @@ __device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long 
     return false;
 }
 
+// AT_WORK is uniform over the launch.  The simulator.rs:324 filter ("the citizen must currently stand in the building's
+// output area") becomes two bit tests per citizen:
+//   at home:  household trial always,                   workplace trial iff HAS_WORK and SAME_AREA
+//   at work:  household trial iff SAME_AREA,            workplace trial iff HAS_WORK
+template <bool AT_WORK>
 __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, const uint4 w4,
-                                                const uint4 h4, const uint4 k4, uint32_t t, uint32_t at_work, uint32_t mask_everywhere) {
+                                                const uint4 h4, const uint4 k4, uint32_t t, uint32_t mask_everywhere) {
     const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
     const uint32_t hc[4] = {h4.x, h4.y, h4.z, h4.w};
     const uint32_t wc[4] = {k4.x, k4.y, k4.z, k4.w};
     const uint32_t n_bldg = v.n_bldg;
+    constexpr uint32_t HOME_TEST = AT_WORK ? (CS_LOW16 | CS_SAME_AREA) : CS_LOW16;
+    constexpr uint32_t HOME_WANT = AT_WORK ? CS_SAME_AREA : 0u;
+    constexpr uint32_t WORK_TEST = AT_WORK ? (CS_LOW16 | CS_HAS_WORK) : (CS_LOW16 | CS_HAS_WORK | CS_SAME_AREA);
+    constexpr uint32_t WORK_WANT = AT_WORK ? CS_HAS_WORK : (CS_HAS_WORK | CS_SAME_AREA);
     // gather the counts of all sources first: the household (building.rs:202-204) and the workplace / own room
-    // (building.rs:278-280, 494-522), each only if the simulator.rs:324 filter lets the citizen be exposed there
+    // (building.rs:278-280, 494-522)
     uint32_t n_h[4], n_w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const bool sus = !(w[k] & NOT_SUSCEPTIBLE);
-        const bool same_area = (w[k] & CS_SAME_AREA) != 0;
-        const bool home_ok = sus && (!at_work || same_area);
-        const bool work_ok = sus && wc[k] != hc[k] && (at_work || same_area);
-        n_h[k] = home_ok ? __ldg(&cnt[hc[k]]) : 0u;
-        n_w[k] = work_ok ? __ldg(&cnt[wc[k]]) : 0u;
+        n_h[k] = (w[k] & HOME_TEST) == HOME_WANT ? __ldg(&cnt[hc[k]]) : 0u;
+        n_w[k] = (w[k] & WORK_TEST) == WORK_WANT ? __ldg(&cnt[wc[k]]) : 0u;
     }
     if (!(n_h[0] | n_h[1] | n_h[2] | n_h[3] | n_w[0] | n_w[1] | n_w[2] | n_w[3])) return 0u;
     uint32_t n_exposed = 0;
@@ -180,28 +220,28 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
 }
 
 __device__ __forceinline__ bool any_susceptible(const uint4 w) {
-    return !(w.x & NOT_SUSCEPTIBLE) || !(w.y & NOT_SUSCEPTIBLE) || !(w.z & NOT_SUSCEPTIBLE) || !(w.w & NOT_SUSCEPTIBLE);
+    return is_susceptible(w.x) || is_susceptible(w.y) || is_susceptible(w.z) || is_susceptible(w.w);
 }
 
 // EAGER: request the household / workplace ids together with the state words (one memory round trip less per quad);
 // used while more than a quarter of the shard is susceptible, when nearly every quad needs them anyway.
-template <bool EAGER>
+template <bool EAGER, bool AT_WORK>
 __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* __restrict__ c) {
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
     const uint4* __restrict__ hc4 = reinterpret_cast<const uint4*>(v.home_cell);
     const uint4* __restrict__ wc4 = reinterpret_cast<const uint4*>(v.work_cell);
-    const uint32_t t = c->t, at_work = c->at_work;
+    const uint32_t t = c->t;
     const uint32_t mask_everywhere = c->mask_kind == ESIM_MASK_EVERYWHERE;
     const uint32_t* __restrict__ cnt = v.cnt[t & 1u];
-    const uint4 absent4 = make_uint4(CS_ABSENT, CS_ABSENT, CS_ABSENT, CS_ABSENT);
+    const uint4 pad4 = make_uint4(CS_PADDING, CS_PADDING, CS_PADDING, CS_PADDING);
     uint32_t n_exposed = 0;
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
         const uint32_t q1 = q0 + T;
         const bool have1 = q1 < n_quads;
         const uint4 wa = cs4[q0];
-        const uint4 wb = have1 ? cs4[q1] : absent4;
+        const uint4 wb = have1 ? cs4[q1] : pad4;
         uint4 ha, ka, hb, kb;
         if (EAGER) {
             ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0);
@@ -212,8 +252,8 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
             if (sa) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
             if (sb) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
         }
-        if (sa) n_exposed += expose_quad(v, cnt, q0, wa, ha, ka, t, at_work, mask_everywhere);
-        if (sb) n_exposed += expose_quad(v, cnt, q1, wb, hb, kb, t, at_work, mask_everywhere);
+        if (sa) n_exposed += expose_quad<AT_WORK>(v, cnt, q0, wa, ha, ka, t, mask_everywhere);
+        if (sb) n_exposed += expose_quad<AT_WORK>(v, cnt, q1, wb, hb, kb, t, mask_everywhere);
     }
     return n_exposed;
 }
@@ -221,9 +261,9 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
 __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished) return;
-    // tally_partial of this step's k_update is complete: block 0's partial is enough to pick the load strategy
-    const bool eager = c->eager_expose != 0;
-    const uint32_t n_exposed = eager ? expose_stream<true>(v, c) : expose_stream<false>(v, c);
+    const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
+    const uint32_t n_exposed = eager ? (at_work ? expose_stream<true, true>(v, c) : expose_stream<true, false>(v, c))
+                                     : (at_work ? expose_stream<false, true>(v, c) : expose_stream<false, false>(v, c));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
 }
@@ -274,7 +314,7 @@ __device__ __noinline__ uint32_t pt_route_slow(const DevView& v, uint32_t off, u
         if (v.record_buses) { v.rec_bus[i] = bus; v.rec_businf[i] = n_b; }
         if (n_b == 0) continue;
         const uint32_t w = __ldcg(&v.cstate[i]);
-        if (w & NOT_SUSCEPTIBLE) continue;
+        if (!is_susceptible(w)) continue;
         const uint32_t mc = (mask_everywhere && !(w & CS_COMPLIANT)) ? 256u : 0u;
         const unsigned long long thr = __ldg(&v.thr[mc + (n_b & 255u)]);
         if (thr == 0) continue;
@@ -306,7 +346,7 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
         }
 #pragma unroll
         for (int s = 0; s < PT_PER_LANE; ++s) {
-            w[s] = idx[s] != 0xFFFFFFFFu ? __ldcg(&v.cstate[idx[s]]) : CS_ABSENT;
+            w[s] = idx[s] != 0xFFFFFFFFu ? __ldcg(&v.cstate[idx[s]]) : CS_PADDING;
             gid[s] = idx[s] != 0xFFFFFFFFu ? __ldg(&v.global_id[idx[s]]) : 0u;
         }
         uint32_t key[PT_PER_LANE], u_lo[PT_PER_LANE], u_hi[PT_PER_LANE];
@@ -345,7 +385,7 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
             if (j >= n) continue;
             const uint32_t n_b = ws->buscnt[bus[s]];
             if (v.record_buses) { v.rec_bus[idx[s]] = bus[s]; v.rec_businf[idx[s]] = n_b; }
-            if (n_b == 0 || (w[s] & NOT_SUSCEPTIBLE)) continue;
+            if (n_b == 0 || !is_susceptible(w[s])) continue;
             const uint32_t mc = (mask_everywhere && !(w[s] & CS_COMPLIANT)) ? 256u : 0u;
             const unsigned long long thr = __ldg(&v.thr[mc + (n_b & 255u)]);
             const uint64_t m52 = (((uint64_t)u_hi[s] << 32) | (uint64_t)u_lo[s]) >> 12;
@@ -454,6 +494,12 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         if (lane < 8 && part) atomicAdd(&sm.tally[lane], part);
     }
     __syncthreads();
+    if (!sharded && tid == 0) {
+        uint32_t cls[5];
+        classes_from_cumulative(sm.tally, v.n_pad, v.n, cls);
+        for (int k = 0; k < 5; ++k) sm.tally[k] = cls[k];
+    }
+    __syncthreads();
     const uint32_t t = sm.c.t;
     if (tid == 0) {
         Ctrl* c = &sm.c;
@@ -542,12 +588,14 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                 for (uint32_t h = tid; h < HT_SIZE; h += TAIL_THREADS) { bat_keys[h] = HT_EMPTY; bat_minj[h] = 0xFFFFFFFFu; }
                 __syncthreads();
                 uint32_t cand[2], slot[2], wv[2];
+                bool owned[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const uint32_t j = base + 2 * tid + q;
                     cand[q] = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
                     const uint32_t local = cand[q] - v.mp.shard_lo;
-                    wv[q] = local < v.n ? __ldcg(&v.cstate[local]) : CS_ABSENT;   // issued before the hash traffic
+                    owned[q] = local < v.n;
+                    wv[q] = owned[q] ? __ldcg(&v.cstate[local]) : 0u;   // issued before the hash traffic
                     slot[q] = ht_insert(bat_keys, cand[q]);
                     atomicMin(&bat_minj[slot[q]], j);
                 }
@@ -556,7 +604,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const uint32_t j = base + 2 * tid + q;
-                    const bool ok = bat_minj[slot[q]] == j && !ht_contains(acc_keys, cand[q]) && vax_eligible(wv[q], vax_start);
+                    const bool ok = owned[q] && bat_minj[slot[q]] == j && !ht_contains(acc_keys, cand[q]) && vax_eligible(wv[q], vax_start);
                     flag[q] = ok ? 1u : 0u;
                 }
                 // exclusive scan of the flags in draw order
@@ -674,6 +722,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
     const uint32_t vax_start = c->vax_some ? c->vax_start_step : t;
     constexpr int PER = VAX_SHARD_DRAWS / TAIL_THREADS;
     uint32_t wv[PER], slot[PER];
+    bool owned[PER];
     if (may_vaccinate) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
@@ -681,8 +730,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
             const uint32_t cand = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
             v.vax_cand[j] = cand;
             const uint32_t local = cand - v.mp.shard_lo;
-            wv[q] = CS_ABSENT; slot[q] = 0;
-            if (local < v.n) {
+            wv[q] = 0u; slot[q] = 0; owned[q] = local < v.n;
+            if (owned[q]) {
                 wv[q] = __ldcg(&v.cstate[local]);
                 uint32_t h = (cand * 2654435761u) >> 18 & (VP_HT - 1);
                 while (true) {
@@ -700,11 +749,15 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             const uint32_t j = tid * PER + q;
-            if (!(wv[q] & CS_ABSENT) && minj[slot[q]] == j && vax_eligible(wv[q], vax_start)) atomicOr(&mask[j >> 5], 1u << (j & 31u));
+            if (owned[q] && minj[slot[q]] == j && vax_eligible(wv[q], vax_start)) atomicOr(&mask[j >> 5], 1u << (j & 31u));
         }
     }
     __syncthreads();
-    if (tid < 5) v.exch[tid] = s_tally[tid];
+    if (tid == 0) {
+        uint32_t cls[5];
+        classes_from_cumulative(s_tally, v.n_pad, v.n, cls);
+        for (int k = 0; k < 5; ++k) v.exch[k] = cls[k];
+    }
     if (tid == 5) v.exch[5] = c->new_exp_bldg;
     if (tid == 6) v.exch[6] = c->new_exp_pt;
     if (tid == 7) v.exch[7] = 0;

@@ -148,6 +148,9 @@ struct EsimSim {
     // index = parity of the first time step of the graph (the count buffers alternate, and NCCL needs fixed pointers)
     cudaGraph_t graph1[2] = {nullptr, nullptr}, graph_day[2] = {nullptr, nullptr};
     cudaGraphExec_t exec1[2] = {nullptr, nullptr}, exec_day[2] = {nullptr, nullptr};
+    // single shard, no lockdown: day graphs without the idle public-transport launches, one per hour-of-day alignment
+    cudaGraph_t graph_spec[24] = {};
+    cudaGraphExec_t exec_spec[24] = {};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     EsimTimings timings{};
     std::vector<float> step_total_ms;   // per recorded step, 0 when not measured
@@ -156,6 +159,11 @@ struct EsimSim {
     std::string err;
 
     void destroy_graphs() {
+        for (int h = 0; h < 24; ++h) {
+            if (exec_spec[h]) cudaGraphExecDestroy(exec_spec[h]);
+            if (graph_spec[h]) cudaGraphDestroy(graph_spec[h]);
+            exec_spec[h] = nullptr; graph_spec[h] = nullptr;
+        }
         if (exec1[1] == exec1[0]) exec1[1] = nullptr;          // one graph serves both parities on a single shard
         if (exec_day[1] == exec_day[0]) exec_day[1] = nullptr;
         for (int p = 0; p < 2; ++p) {
@@ -259,18 +267,40 @@ void allreduce_tail(EsimSim* s) {
     NCCLCK(nccl_api()->AllReduce(s->exch.p, s->exch.p, EXCH_WORDS, NCCL_UINT32, NCCL_SUM, s->comm, s->stream));
 }
 
-// one time step whose number has the given parity
-void enqueue_step(EsimSim* s, uint32_t parity) {
-    const DevView& v = s->v;
+// one time step whose number has the given parity; `with_pt` / `next_has_pt`: see the specialised day graphs below
+void enqueue_step(EsimSim* s, uint32_t parity, bool with_pt = true, bool next_has_pt = true) {
+    DevView v = s->v;
+    v.next_has_pt = next_has_pt ? 1u : 0u;
     launch_update(v, s->stream);
     if (s->world > 1 && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
     launch_expose(v, s->stream);
-    launch_pt(v, s->stream);
+    if (with_pt) launch_pt(v, s->stream);
     if (s->world > 1) {
         launch_vax_prepare(v, s->stream);
         allreduce_tail(s);
     }
     launch_tail(v, s->stream);
+}
+
+// While no lockdown is in force everybody who uses public transport rides at hours 8 and 16 only (citizen.rs:179-195), so a
+// day graph that starts at hour-of-day h0 needs the public-transport kernel in two of its 24 slots.  If a lockdown freezes the
+// riders on their buses the tail raises Ctrl::abort_graph, the rest of the replay is a no-op, and esim_run continues with the
+// generic graphs (a public-transport kernel in every slot) until the lockdown is over.
+inline bool hour_has_pt(uint32_t t) { const uint32_t h = t % 24u; return h == 8u || h == 16u; }
+
+cudaGraphExec_t spec_day_graph(EsimSim* s, uint32_t first_step) {
+    const uint32_t h0 = first_step % 24u;
+    if (!s->exec_spec[h0]) {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        for (uint32_t i = 0; i < (uint32_t)GRAPH_DAY; ++i)
+            enqueue_step(s, (first_step + i) & 1u, hour_has_pt(first_step + i), hour_has_pt(first_step + i + 1));
+        CK(cudaStreamEndCapture(s->stream, &g));
+        cudaGraphExec_t e = nullptr;
+        CK(cudaGraphInstantiate(&e, g, 0));
+        s->graph_spec[h0] = g; s->exec_spec[h0] = e;
+    }
+    return s->exec_spec[h0];
 }
 
 void capture_graphs(EsimSim* s) {
@@ -527,6 +557,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         DevView& v = s->v;
         v.n = N; v.n_pad = n_pad; v.n_bldg = B; v.n_rooms = R; v.n_cells = B + R;
         v.n_routes = n_routes; v.n_riders = n_riders; v.record_buses = rec ? 1u : 0u;
+        v.next_has_pt = 1;   // every launch sequence has a public-transport kernel unless a specialised graph says otherwise
         v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
         v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt0.p; v.cnt[1] = s->cnt1.p; v.thr = s->thr.p;
         v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
@@ -625,12 +656,17 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
             throw ApiError{ESIM_ERR_COMM, "sharded handle: attach a communicator (esim_comm_init) or drive the esim_shard_step_* phases"};
         while (budget > 0 && !s->finished) {
             uint32_t queued = 0;
+            const uint32_t before_chunk = s->steps_done;
             const uint32_t parity = (s->steps_done + 1u) & 1u;   // GRAPH_DAY is even: the parity is the same for every day
-            if (s->exec_day[parity])
+            if (s->exec_day[parity]) {
+                // h_ctrl is current here: no lockdown => the schedule of the coming hours is known
+                const bool spec = s->world == 1 && !s->h_ctrl->lockdown_some && GRAPH_DAY == 24;
+                cudaGraphExec_t day = spec ? spec_day_graph(s, s->steps_done + 1u) : s->exec_day[parity];
                 for (uint32_t d = 0; d < CHUNK_DAYS && budget - queued >= (uint32_t)GRAPH_DAY; ++d) {
-                    CK(cudaGraphLaunch(s->exec_day[parity], s->stream));
+                    CK(cudaGraphLaunch(day, s->stream));
                     queued += GRAPH_DAY;
                 }
+            }
             if (queued == 0) {
                 const uint32_t n = std::min<uint32_t>(budget, GRAPH_DAY);
                 for (uint32_t k = 0; k < n; ++k) {
@@ -642,7 +678,14 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
             fetch_ctrl(s);
             const int rc = after_steps(s);
             if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
-            budget -= queued;
+            const uint32_t executed = s->steps_done - before_chunk;
+            if (s->h_ctrl->abort_graph) {
+                // the specialised graph stopped early (lockdown froze public transport): clear the flag, go on with the generic one
+                s->h_ctrl->abort_graph = 0;
+                CK(cudaMemsetAsync(&s->ctrl.p->abort_graph, 0, sizeof(uint32_t), s->stream));
+            }
+            budget -= std::min(budget, executed);
+            if (executed == 0 && !s->finished) throw ApiError{ESIM_ERR_SIMULATION, "no progress"};
         }
         if (steps_done) *steps_done = s->steps_done - start;
         return s->finished ? 0 : 1;

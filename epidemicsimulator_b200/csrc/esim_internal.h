@@ -58,7 +58,7 @@ struct Ctrl {
     uint32_t new_exp_bldg;   // successful building exposures of step t
     uint32_t new_exp_pt;     // successful public-transport exposures of step t
     uint32_t vaccinated_now;
-    uint32_t blocks_done;    // spare
+    uint32_t abort_graph;    // the schedule left the assumptions of the specialised graph being replayed: the rest of it is a no-op
     uint32_t eager_expose;   // more than a quarter of the citizens are susceptible: k_expose loads cell ids eagerly
     uint32_t pad[7];
 };
@@ -77,6 +77,7 @@ struct DevView {
     uint32_t n_bldg, n_rooms, n_cells;
     uint32_t n_routes, n_riders;
     uint32_t record_buses;
+    uint32_t next_has_pt;  // tail only: the graph slot of the next hour contains a public-transport kernel
     uint32_t* cstate;      // [n_pad]
     const uint32_t* home_cell;   // [n_pad] building id
     const uint32_t* work_cell;   // [n_pad] building id, or n_bldg + room id for school members

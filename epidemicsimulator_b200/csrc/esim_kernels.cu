@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
     const uint4 none4 = make_uint4(0u, 0u, 0u, 0u);   // quads past the end: an all-zero word adds nothing to the cumulative counts
-    if (c->finished) return;
+    if (c->finished | c->abort_graph) return;
     const uint32_t t = c->t, at_work = c->at_work;
     const uint32_t vax_all = c->vax_all_pending, vax_start = c->vax_start_step;
     // riders only count on their bus (simulator.rs:181-198): while public transport runs, a rider is never "present"
@@ -260,7 +260,7 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
 
 __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
     const Ctrl* __restrict__ c = v.ctrl;
-    if (c->finished) return;
+    if (c->finished | c->abort_graph) return;
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
     const uint32_t n_exposed = eager ? (at_work ? expose_stream<true, true>(v, c) : expose_stream<true, false>(v, c))
                                      : (at_work ? expose_stream<false, true>(v, c) : expose_stream<false, false>(v, c));
@@ -679,7 +679,9 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         c->tally[0] = c->tally[1] = c->tally[2] = c->tally[3] = c->tally[4] = 0;
         c->new_exp_bldg = 0; c->new_exp_pt = 0;
         c->vaccinated_now = sm.accepted;
-        c->blocks_done = 0;
+        // a specialised day graph has no public-transport kernel in most slots: if the next hour needs one after all (lockdown
+        // froze the riders on their buses), the rest of that graph must not run
+        if (!v.next_has_pt && c->pt_mode != ESIM_PT_NONE && v.n_routes) c->abort_graph = 1;
         // k_expose requests the cell ids together with the state words while most citizens are susceptible
         c->eager_expose = (uint64_t)s.susceptible * 4u > (uint64_t)(s.susceptible + s.exposed + s.infected + s.recovered + s.vaccinated) ? 1u : 0u;
     }
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
     uint32_t* mask = dyn_smem + 2 * VP_HT;     // [VAX_SHARD_DRAWS / 32]
     __shared__ uint32_t s_tally[8];
     const Ctrl* __restrict__ c = v.ctrl;
-    if (c->finished) return;
+    if (c->finished | c->abort_graph) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t t = c->t;
     if (tid < 8) s_tally[tid] = 0;
@@ -771,14 +773,14 @@ constexpr int PT_THREADS = 128;  // 4 routes per block: small blocks start (and,
 __global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
     __shared__ PtWarpSmem ws[PT_THREADS / 32];
     const Ctrl* __restrict__ c = v.ctrl;
-    if (c->finished || c->pt_mode == ESIM_PT_NONE) return;
+    if (c->finished | c->abort_graph || c->pt_mode == ESIM_PT_NONE) return;
     pt_phase(v, &ws[threadIdx.x >> 5], c->t, c->mask_kind == ESIM_MASK_EVERYWHERE);
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
-    if (v.ctrl->finished) return;
+    if (v.ctrl->finished | v.ctrl->abort_graph) return;
     tail_phase(v, dyn_smem, sm);
 }
 

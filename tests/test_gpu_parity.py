@@ -234,3 +234,20 @@ def test_timed_steps_equal_graph_steps():
     t = a.timings()
     assert t["steps"] == 100 and t["total"] > 0 and abs(t["generate_exposures"] + t["apply_exposures"] + t["apply_interventions"] - t["total"]) < 1e-6
     a.close(); b.close(); c.close()
+
+
+@pytest.mark.parametrize("onset", [8, 16, 11, 20])
+def test_device_resident_run_across_lockdown_changes(onset):
+    # esim_run replays day graphs specialised for "no lockdown"; a lockdown that freezes riders on their buses (onset 8, 16)
+    # or everybody at work / at home must make it fall back to the generic graph without losing or repeating a step
+    pop = _pop_infected_at(onset, cross_area_fraction=0.3)
+    cfg = dict(exposure_chance=0.01, seed=40 + onset)
+    sim = _sim(pop, **cfg)
+    orc = Oracle(pop, default_config(**cfg))
+    n = sim.run(700)
+    assert n == orc.run(700)
+    st, so = sim.statistics(), orc.stats()
+    assert np.array_equal(st, so), np.nonzero((st != so).any(1))[0][:3]
+    assert (so[:, 8] != _abi.NONE_U32).any() and (so[-1, 8] == _abi.NONE_U32)   # a lockdown started and ended
+    _compare_state(sim, orc, n)
+    sim.close(); orc.close()

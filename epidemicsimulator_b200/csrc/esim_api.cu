@@ -414,6 +414,7 @@ int esim_create(const EsimConfig* cfg, EsimSim** out) {
         s->h_stat = reinterpret_cast<EsimStepStats*>(s->mailbox + 256);
         for (auto& e : s->ev) CK(cudaEventCreate(&e));
         CK((cudaError_t)configure_kernels());
+        if (const char* e = getenv("ESIM_NO_PDL")) set_pdl(e[0] != '1');
         return ESIM_OK;
     });
     if (rc < 0) { g_create_error = s->err; delete s; return rc; }

@@ -112,6 +112,7 @@ void launch_tail(const DevView& v, cudaStream_t s);
 void launch_vax_prepare(const DevView& v, cudaStream_t s);  // sharded runs only
 int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as int
 int  sm_count();
+void set_pdl(bool on);   // programmatic dependent launch of the step kernels (default on)
 uint32_t update_blocks(uint32_t n_pad);
 
 }  // namespace esim

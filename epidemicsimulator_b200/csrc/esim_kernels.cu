@@ -42,6 +42,13 @@ __device__ __forceinline__ bool vax_eligible(uint32_t w, uint32_t vax_start_step
     return s > (int)vax_start_step && !(w & CS_VIA_PT);
 }
 
+// Programmatic dependent launch: every step kernel lets its successor's blocks be scheduled right away (they fill the SMs as
+// this kernel's blocks retire) and then waits until its predecessor has completed and flushed its writes.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t warp_sum(uint32_t x) { return __reduce_add_sync(0xffffffffu, x); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
@@ -69,6 +76,7 @@ constexpr int UPDATE_THREADS = 256;
 constexpr int UPDATE_UNROLL = 4;
 
 __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
+    pdl_prologue();
     const Ctrl* __restrict__ c = v.ctrl;
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
@@ -259,6 +267,7 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
 }
 
 __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
+    pdl_prologue();
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
@@ -698,6 +707,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
 //   occurrence of its citizen.  Duplicates of a citizen are owned by the same shard, so de-duplication is local.
 constexpr uint32_t VP_HT = 2 * VAX_SHARD_DRAWS;  // hash slots (power of two)
 __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
+    pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
     uint32_t* keys = dyn_smem;                 // [VP_HT]
     uint32_t* minj = dyn_smem + VP_HT;         // [VP_HT]
@@ -771,6 +781,7 @@ constexpr size_t HT_BYTES = 3 * HT_SIZE * sizeof(uint32_t);
 constexpr int PT_THREADS = 128;  // 4 routes per block: small blocks start (and, on idle hours, retire) quickly
 
 __global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
+    pdl_prologue();
     __shared__ PtWarpSmem ws[PT_THREADS / 32];
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph || c->pt_mode == ESIM_PT_NONE) return;
@@ -778,6 +789,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
+    pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
     if (v.ctrl->finished | v.ctrl->abort_graph) return;
@@ -809,26 +821,41 @@ static inline uint32_t blocks_for(uint64_t items, uint32_t per_block, uint32_t c
     return (uint32_t)(b < cap ? b : cap);
 }
 
+// all step kernels are launched with the programmatic-stream-serialization attribute (see pdl_prologue)
+static bool g_use_pdl = true;
+void set_pdl(bool on) { g_use_pdl = on; }
+
+template <class K>
+static void launch_step_kernel(K kernel, uint32_t grid, uint32_t block, size_t smem, cudaStream_t s, const DevView& v) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, v);
+}
+
 uint32_t update_blocks(uint32_t n_pad) {
     // one resident wave: 6 blocks of 256 threads per SM
     return blocks_for(n_pad >> 2, UPDATE_THREADS, (uint32_t)sm_count() * 6u);
 }
 void launch_update(const DevView& v, cudaStream_t s) {
-    k_update<<<v.n_update_blocks, UPDATE_THREADS, 0, s>>>(v);
+    launch_step_kernel(k_update, v.n_update_blocks, UPDATE_THREADS, 0, s, v);
 }
 void launch_expose(const DevView& v, cudaStream_t s) {
-    k_expose<<<blocks_for(v.n_pad >> 2, EXPOSE_THREADS, (uint32_t)sm_count() * 4u), EXPOSE_THREADS, 0, s>>>(v);
+    launch_step_kernel(k_expose, blocks_for(v.n_pad >> 2, EXPOSE_THREADS, (uint32_t)sm_count() * 4u), EXPOSE_THREADS, 0, s, v);
 }
 void launch_pt(const DevView& v, cudaStream_t s) {
     if (v.n_routes == 0) return;
     // one warp per route, grid-stride; at most 8 resident blocks per SM
-    k_pt<<<blocks_for(v.n_routes, PT_THREADS / 32, (uint32_t)sm_count() * 8u), PT_THREADS, 0, s>>>(v);
+    launch_step_kernel(k_pt, blocks_for(v.n_routes, PT_THREADS / 32, (uint32_t)sm_count() * 8u), PT_THREADS, 0, s, v);
 }
 void launch_tail(const DevView& v, cudaStream_t s) {
-    k_tail<<<1, TAIL_THREADS, HT_BYTES, s>>>(v);
+    launch_step_kernel(k_tail, 1, TAIL_THREADS, HT_BYTES, s, v);
 }
 void launch_vax_prepare(const DevView& v, cudaStream_t s) {
-    k_vax_prepare<<<1, TAIL_THREADS, VP_SMEM, s>>>(v);
+    launch_step_kernel(k_vax_prepare, 1, TAIL_THREADS, VP_SMEM, s, v);
 }
 
 }  // namespace esim

@@ -132,6 +132,9 @@ struct EsimSim {
     DevBuf<unsigned long long> thr;
     DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
     DevBuf<uint32_t> exch, vax_cand;    // sharded runs
+    DevBuf<unsigned int> barrier;       // grid barrier of the persistent kernel
+    DevBuf<unsigned long long> pk_prof; // ESIM_TRACE: cycles per phase
+    bool use_persistent = false;
     uint32_t world = 1, rank = 0, n_shared_bldgs = 0, n_shared_rooms = 0;
     void* comm = nullptr;               // ncclComm_t
     DevBuf<Ctrl> ctrl;
@@ -178,7 +181,7 @@ struct EsimSim {
         if (device >= 0) cudaSetDevice(device);
         destroy_graphs();
         if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
-        exch.release(); vax_cand.release();
+        exch.release(); vax_cand.release(); barrier.release(); pk_prof.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt0.release(); cnt1.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
@@ -527,7 +530,11 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
         if (rec) { s->rec_bus.alloc(N); s->rec_businf.alloc(N); }
         const uint32_t n_update_blocks = update_blocks(n_pad);
-        s->tally_partial.alloc((size_t)n_update_blocks * 8);
+        const int pk_grid = persistent_grid();
+        s->use_persistent = pk_grid > 0 && p->n_shards <= 1 && (s->cfg.flags & ESIM_CFG_PERSISTENT) && !(s->cfg.flags & ESIM_CFG_NO_GRAPH);
+        s->tally_partial.alloc((size_t)std::max<uint32_t>(n_update_blocks, (uint32_t)std::max(pk_grid, 1)) * 8);
+        s->barrier.alloc(4);
+        if (getenv("ESIM_TRACE")) { s->pk_prof.alloc(8); CK(cudaMemsetAsync(s->pk_prof.p, 0, s->pk_prof.bytes(), s->stream)); }
         s->world = p->n_shards > 1 ? p->n_shards : 1;
         s->n_shared_bldgs = p->n_shared_bldgs; s->n_shared_rooms = p->n_shared_rooms;
         s->exch.alloc(EXCH_WORDS); s->vax_cand.alloc(ESIM_VAX_SHARD_DRAWS);
@@ -658,6 +665,27 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
         while (budget > 0 && !s->finished) {
             uint32_t queued = 0;
             const uint32_t before_chunk = s->steps_done;
+            if (s->use_persistent) {
+                // one cooperative launch runs the whole chunk; grid barriers separate the phases of a step
+                const uint32_t n = std::min<uint32_t>(budget, 4096u);
+                CK(cudaMemsetAsync(s->barrier.p, 0, s->barrier.bytes(), s->stream));
+                CK((cudaError_t)launch_persistent(s->v, n, s->barrier.p, s->pk_prof.p, s->stream));
+                fetch_ctrl(s);
+                if (s->pk_prof.p) {
+                    unsigned long long h[8];
+                    CK(cudaMemcpy(h, s->pk_prof.p, sizeof(h), cudaMemcpyDeviceToHost));
+                    static const char* nm[8] = {"ctrl", "update", "barrier1", "expose", "pt", "barrier2", "tail", "barrier3"};
+                    const double steps_run = std::max<double>(1.0, s->steps_done - before_chunk);
+                    for (int k = 0; k < 8; ++k) fprintf(stderr, "[esim] persistent %-9s %8.0f cycles/step\n", nm[k], h[k] / steps_run);
+                    CK(cudaMemset(s->pk_prof.p, 0, sizeof(h)));
+                }
+                const int prc = after_steps(s);
+                if (prc < 0) throw ApiError{prc, "device-side error flag raised"};
+                const uint32_t done_now = s->steps_done - before_chunk;
+                if (done_now == 0 && !s->finished) throw ApiError{ESIM_ERR_SIMULATION, "no progress"};
+                budget -= std::min(budget, done_now);
+                continue;
+            }
             const uint32_t parity = (s->steps_done + 1u) & 1u;   // GRAPH_DAY is even: the parity is the same for every day
             if (s->exec_day[parity]) {
                 // h_ctrl is current here: no lockdown => the schedule of the coming hours is known

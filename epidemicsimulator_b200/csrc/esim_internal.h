@@ -114,5 +114,7 @@ int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as
 int  sm_count();
 void set_pdl(bool on);   // programmatic dependent launch of the step kernels (default on)
 uint32_t update_blocks(uint32_t n_pad);
+int  persistent_grid();   // co-resident blocks of k_persistent (0 = unavailable)
+int  launch_persistent(const DevView& v, uint32_t n_steps, unsigned int* barrier_counter, unsigned long long* prof, cudaStream_t s);
 
 }  // namespace esim

@@ -75,14 +75,12 @@ __device__ __forceinline__ bool is_susceptible(uint32_t w) { return (w & CS_LOW1
 constexpr int UPDATE_THREADS = 256;
 constexpr int UPDATE_UNROLL = 4;
 
-__global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
-    pdl_prologue();
-    const Ctrl* __restrict__ c = v.ctrl;
+// `s_cnt` = 4 words of shared memory; the block's partial tallies go to tally_partial[blockIdx.x * 8 ..]
+__device__ __forceinline__ void update_phase(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt) {
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
     const uint4 none4 = make_uint4(0u, 0u, 0u, 0u);   // quads past the end: an all-zero word adds nothing to the cumulative counts
-    if (c->finished | c->abort_graph) return;
     const uint32_t t = c->t, at_work = c->at_work;
     const uint32_t vax_all = c->vax_all_pending, vax_start = c->vax_start_step;
     // riders only count on their bus (simulator.rs:181-198): while public transport runs, a rider is never "present"
@@ -99,7 +97,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += UPDATE_UNROLL * T) {
         uint4 cur[UPDATE_UNROLL];
 #pragma unroll
-        for (int u = 0; u < UPDATE_UNROLL; ++u) { const uint32_t q = q0 + u * T; cur[u] = q < n_quads ? cs4[q] : none4; }
+        for (int u = 0; u < UPDATE_UNROLL; ++u) { const uint32_t q = q0 + u * T; cur[u] = q < n_quads ? __ldcg(cs4 + q) : none4; }
         if (vax_all) {
             // choose_multiple took the whole eligible set at the end of the previous step (simulator.rs:525-552)
 #pragma unroll
@@ -144,8 +142,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
             }
         }
     }
-    // block reduction -> tally_partial[block] = {susceptible-complement, ...}: the tail turns the cumulative counts into S,E,I,R,V
-    __shared__ uint32_t s_cnt[4];
+    // block reduction -> tally_partial[block]: the tail turns the cumulative counts into S,E,I,R,V
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t r4[4] = {warp_sum(c_exp), warp_sum(c_inf), warp_sum(c_ei), warp_sum(c_vax)};
@@ -156,6 +153,14 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     }
     __syncthreads();
     if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
+}
+
+__global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
+    pdl_prologue();
+    __shared__ uint32_t s_cnt[4];
+    const Ctrl* __restrict__ c = v.ctrl;
+    if (c->finished | c->abort_graph) return;
+    update_phase(v, c, s_cnt);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -197,8 +202,8 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
     uint32_t n_h[4], n_w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        n_h[k] = (w[k] & HOME_TEST) == HOME_WANT ? __ldg(&cnt[hc[k]]) : 0u;
-        n_w[k] = (w[k] & WORK_TEST) == WORK_WANT ? __ldg(&cnt[wc[k]]) : 0u;
+        n_h[k] = (w[k] & HOME_TEST) == HOME_WANT ? __ldcg(&cnt[hc[k]]) : 0u;   // .cg: written by other SMs in this launch
+        n_w[k] = (w[k] & WORK_TEST) == WORK_WANT ? __ldcg(&cnt[wc[k]]) : 0u;
     }
     if (!(n_h[0] | n_h[1] | n_h[2] | n_h[3] | n_w[0] | n_w[1] | n_w[2] | n_w[3])) return 0u;
     uint32_t n_exposed = 0;
@@ -213,7 +218,7 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
         if (n_h[k]) thr_h = __ldg(&v.thr[mc + (n_h[k] & 255u)]);  // `exposure_total as u8` (citizen.rs:239)
         if (n_w[k]) {
             // a room member gets one trial per infected member of its own room, each with n = infected in the school
-            const uint32_t n_total = wc[k] >= n_bldg ? __ldg(&cnt[__ldg(&v.room_parent[wc[k] - n_bldg])]) : n_w[k];
+            const uint32_t n_total = wc[k] >= n_bldg ? __ldcg(&cnt[__ldg(&v.room_parent[wc[k] - n_bldg])]) : n_w[k];
             thr_w = __ldg(&v.thr[mc + (n_total & 255u)]);
             k_w = thr_w ? (wc[k] >= n_bldg ? n_w[k] : 1u) : 0u;
         }
@@ -248,8 +253,8 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
         const uint32_t q1 = q0 + T;
         const bool have1 = q1 < n_quads;
-        const uint4 wa = cs4[q0];
-        const uint4 wb = have1 ? cs4[q1] : pad4;
+        const uint4 wa = __ldcg(cs4 + q0);
+        const uint4 wb = have1 ? __ldcg(cs4 + q1) : pad4;
         uint4 ha, ka, hb, kb;
         if (EAGER) {
             ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0);
@@ -412,7 +417,7 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
 // ---------------------------------------------------------------------------------------------------------
 // Tail: one block of 1024 threads.  Thread 0 runs the scalar state machines; the whole block draws the vaccination picks.
 constexpr int TAIL_THREADS = 1024;
-constexpr uint32_t VAX_BATCH = 2 * TAIL_THREADS;
+constexpr uint32_t VAX_BATCH = 2048;   // candidate draws examined per round of the rejection loop
 constexpr uint32_t HT_SIZE = 8192;  // power of two
 constexpr uint32_t HT_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t MAX_VAX_PER_STEP = 4000;  // accepted-pick table stays below half of HT_SIZE
@@ -479,7 +484,9 @@ struct TailSmem {
 
 // `ht` = 3 * HT_SIZE words of shared memory.  Must be called by all TAIL_THREADS threads of one block, after every
 // other writer of the control block and of the citizens' state words of this step has finished.
-__device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailSmem& sm) {
+template <int NT>
+__device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailSmem& sm, uint32_t n_partial_blocks) {
+    constexpr int PER = VAX_BATCH / NT;   // draws per thread and round
     uint32_t* acc_keys = ht;                  // citizens chosen in this step
     uint32_t* bat_keys = ht + HT_SIZE;        // candidates of the current batch
     uint32_t* bat_minj = ht + 2 * HT_SIZE;    // first draw index of each candidate
@@ -496,8 +503,8 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         if (tid == 6) sm.c.new_exp_pt = __ldcg(&v.exch[6]);
     } else {   // S/E/I/R/V = sum of k_update's per-block partials (8 words per block, 5 used)
         uint32_t part = 0;
-        for (uint32_t z = tid; z < v.n_update_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
-        // threads tid, tid+8, ... hold the same counter: TAIL_THREADS is a multiple of 8
+        for (uint32_t z = tid; z < n_partial_blocks * 8u; z += NT) part += __ldcg(&v.tally_partial[z]);
+        // threads tid, tid+8, ... hold the same counter: NT is a multiple of 8
         part += __shfl_xor_sync(0xffffffffu, part, 8);
         part += __shfl_xor_sync(0xffffffffu, part, 16);
         if (lane < 8 && part) atomicAdd(&sm.tally[lane], part);
@@ -557,7 +564,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
             if (lane == 31) sm.scan[wid] = incl;
             __syncthreads();
             if (wid == 0) {
-                const uint32_t x = sm.scan[lane];
+                const uint32_t x = lane < NT / 32 ? sm.scan[lane] : 0u;
                 uint32_t inc2 = x;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -591,16 +598,16 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                 sm.accepted = K;
             }
         } else {
-            for (uint32_t h = tid; h < HT_SIZE; h += TAIL_THREADS) acc_keys[h] = HT_EMPTY;
+            for (uint32_t h = tid; h < HT_SIZE; h += NT) acc_keys[h] = HT_EMPTY;
             uint32_t base = 0;
             for (uint32_t guard = 0; guard < (1u << 20); ++guard) {
-                for (uint32_t h = tid; h < HT_SIZE; h += TAIL_THREADS) { bat_keys[h] = HT_EMPTY; bat_minj[h] = 0xFFFFFFFFu; }
+                for (uint32_t h = tid; h < HT_SIZE; h += NT) { bat_keys[h] = HT_EMPTY; bat_minj[h] = 0xFFFFFFFFu; }
                 __syncthreads();
-                uint32_t cand[2], slot[2], wv[2];
-                bool owned[2];
+                uint32_t cand[PER], slot[PER], wv[PER];
+                bool owned[PER];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const uint32_t j = base + 2 * tid + q;
+                for (int q = 0; q < PER; ++q) {
+                    const uint32_t j = base + PER * tid + q;
                     cand[q] = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
                     const uint32_t local = cand[q] - v.mp.shard_lo;
                     owned[q] = local < v.n;
@@ -609,15 +616,16 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                     atomicMin(&bat_minj[slot[q]], j);
                 }
                 __syncthreads();
-                uint32_t flag[2];
+                uint32_t flag[PER];
+                uint32_t mine = 0;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const uint32_t j = base + 2 * tid + q;
+                for (int q = 0; q < PER; ++q) {
+                    const uint32_t j = base + PER * tid + q;
                     const bool ok = owned[q] && bat_minj[slot[q]] == j && !ht_contains(acc_keys, cand[q]) && vax_eligible(wv[q], vax_start);
                     flag[q] = ok ? 1u : 0u;
+                    mine += flag[q];
                 }
                 // exclusive scan of the flags in draw order
-                const uint32_t mine = flag[0] + flag[1];
                 uint32_t incl = mine;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -627,7 +635,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                 if (lane == 31) sm.scan[wid] = incl;
                 __syncthreads();
                 if (wid == 0) {
-                    const uint32_t x = sm.scan[lane];
+                    const uint32_t x = lane < NT / 32 ? sm.scan[lane] : 0u;
                     uint32_t inc2 = x;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -641,7 +649,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                 const uint32_t accepted_before = sm.accepted;
                 uint32_t rank = accepted_before + sm.scan[wid] + (incl - mine);
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < PER; ++q) {
                     if (flag[q]) {
                         if (rank < K) {
                             atomicOr(&v.cstate[cand[q] - v.mp.shard_lo], CS_VACCINATED);
@@ -793,7 +801,103 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
     if (v.ctrl->finished | v.ctrl->abort_graph) return;
-    tail_phase(v, dyn_smem, sm);
+    tail_phase<TAIL_THREADS>(v, dyn_smem, sm, v.n_update_blocks);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_persistent: the whole step loop in ONE cooperative launch (single shard).  All blocks are co-resident; the phases of a
+// step are separated by grid-wide barriers instead of kernel boundaries, which removes the launch / drain latency that
+// dominates a step once the population fits in L2.  Mutable data (state words, counts, control block) is always read with
+// ld.global.cg so that no SM sees a stale L1 line from an earlier phase.
+constexpr int PK_THREADS = 512;
+
+// out-of-line copies of the rare, register-hungry phases keep the streaming loops of k_persistent free of spills
+__device__ __noinline__ void pk_pt_phase(const DevView* v, PtWarpSmem* ws, uint32_t t, uint32_t mask_everywhere) {
+    pt_phase(*v, ws, t, mask_everywhere);
+}
+__device__ __noinline__ void pk_tail_phase(const DevView* v, uint32_t* ht, TailSmem* sm, uint32_t n_partial_blocks) {
+    tail_phase<PK_THREADS>(*v, ht, *sm, n_partial_blocks);
+}
+__device__ __noinline__ void pk_update_phase(const DevView* v, const Ctrl* c, uint32_t* s_cnt) { update_phase(*v, c, s_cnt); }
+__device__ __noinline__ uint32_t pk_expose_phase(const DevView* v, const Ctrl* c) {
+    const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
+    return eager ? (at_work ? expose_stream<true, true>(*v, c) : expose_stream<true, false>(*v, c))
+                 : (at_work ? expose_stream<false, true>(*v, c) : expose_stream<false, false>(*v, c));
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& generation) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        generation += 1;
+        const unsigned int target = generation * gridDim.x;
+        __threadfence();                       // publish this block's writes
+        atomicAdd(counter, 1u);
+        while (true) {
+            unsigned int seen;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if (seen >= target) break;
+            __nanosleep(20);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1) k_persistent(const __grid_constant__ DevView v, const uint32_t n_steps, unsigned int* barrier_counter,
+                                                               unsigned long long* prof /* nullable: cycles per phase of block 0 */) {
+    extern __shared__ uint32_t dyn_smem[];      // HT_BYTES: vaccination hash tables (tail) / public-transport staging
+    __shared__ TailSmem sm;
+    __shared__ uint32_t s_cnt[4];
+    __shared__ Ctrl s_ctrl;                     // this block's copy of the control block for the current step
+    unsigned int generation = 0;
+    const bool profile = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t0 = profile ? clock64() : 0;
+#define PK_MARK(slot) do { if (profile) { const long long t1 = clock64(); prof[slot] += (unsigned long long)(t1 - t0); t0 = t1; } } while (0)
+    for (uint32_t step = 0; step < n_steps; ++step) {
+        if (threadIdx.x < sizeof(Ctrl) / 4)
+            reinterpret_cast<uint32_t*>(&s_ctrl)[threadIdx.x] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + threadIdx.x);
+        __syncthreads();
+        if (s_ctrl.finished) break;             // uniform over the grid: every block reads the same control block
+        PK_MARK(0);
+        pk_update_phase(&v, &s_ctrl, s_cnt);
+        PK_MARK(1);
+        grid_barrier(barrier_counter, generation);
+        PK_MARK(2);
+        {
+            const uint32_t s = warp_sum(pk_expose_phase(&v, &s_ctrl));
+            if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+        }
+        PK_MARK(3);
+        if (s_ctrl.pt_mode != ESIM_PT_NONE && v.n_routes) {
+            grid_barrier(barrier_counter, generation);   // every building trial of the step precedes the bus trials
+            pk_pt_phase(&v, reinterpret_cast<PtWarpSmem*>(dyn_smem) + (threadIdx.x >> 5), s_ctrl.t, s_ctrl.mask_kind == ESIM_MASK_EVERYWHERE);
+            PK_MARK(4);
+        }
+        grid_barrier(barrier_counter, generation);
+        PK_MARK(5);
+        if (blockIdx.x == 0) pk_tail_phase(&v, dyn_smem, &sm, gridDim.x);
+        PK_MARK(6);
+        grid_barrier(barrier_counter, generation);
+        PK_MARK(7);
+    }
+#undef PK_MARK
+}
+
+int persistent_grid() {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PK_THREADS, HT_BYTES) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm * sm_count();
+}
+
+int launch_persistent(const DevView& v, uint32_t n_steps, unsigned int* barrier_counter, unsigned long long* prof, cudaStream_t s) {
+    const int grid = persistent_grid();
+    if (grid <= 0) return (int)cudaErrorLaunchOutOfResources;
+    DevView vv = v;
+    uint32_t steps = n_steps;
+    void* args[] = {(void*)&vv, (void*)&steps, (void*)&barrier_counter, (void*)&prof};
+    return (int)cudaLaunchCooperativeKernel((const void*)k_persistent, dim3((unsigned)grid), dim3(PK_THREADS), args, HT_BYTES, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -812,6 +916,7 @@ int sm_count() {
 int configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vax_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     return (int)e;
 }
 

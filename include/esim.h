@@ -71,6 +71,8 @@ extern "C" {
 /* config flag bits */
 #define ESIM_CFG_RECORD_BUSES 0x1u /* keep per-rider (bus, infected-on-bus) of the last PT step for parity reads */
 #define ESIM_CFG_NO_GRAPH     0x2u /* launch kernels directly instead of replaying the captured CUDA graph   */
+#define ESIM_CFG_PERSISTENT   0x8u /* experimental: esim_run launches one cooperative kernel with grid-wide barriers between the
+                                      phases instead of replaying CUDA graphs (single shard; currently slower) */
 #define ESIM_CFG_FLUSH_L2     0x4u /* esim_step_timed overwrites a 256 MiB scratch buffer before every step, so
                                       that each timed step starts with a cold L2 (benchmark hygiene only)       */
 

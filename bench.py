@@ -229,7 +229,10 @@ def main():
     def make_sim(flags=0):
         sim = Simulator.from_population(pop, default_config(flags=flags, **cfg_kwargs))
         if world > 1:
-            sim.attach_comm(dist)
+            if os.environ.get("ESIM_COMM", "p2p") == "nccl":
+                sim.attach_comm(dist)      # NCCL all-reduces inside the captured graphs
+            else:
+                sim.connect_peers(dist)    # in-kernel exchange over NVLink peer mappings
         return sim
 
     # ---- warm-up on a throw-away handle (module load, graph capture, clocks) --------------------------------------

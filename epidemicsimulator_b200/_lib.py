@@ -67,6 +67,8 @@ def cuda_lib() -> C.CDLL:
     lib.esim_inject_rng.argtypes = [vp, C.c_uint64]
     lib.esim_dump_statistics.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p)]
     lib.esim_get_timings.argtypes = [vp, C.POINTER(_abi.EsimTimings)]
+    lib.esim_peer_info.argtypes = [vp, _abi.u8p]
+    lib.esim_peer_connect.argtypes = [vp, C.c_uint32, C.c_uint32, _abi.u8p]
     lib.esim_comm_unique_id.argtypes = [_abi.u8p]
     lib.esim_comm_init.argtypes = [vp, _abi.u8p, C.c_uint32, C.c_uint32]
     lib.esim_shard_step_begin.argtypes = [vp]

@@ -52,14 +52,17 @@ struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t stream = nullptr;
-    void alloc(size_t count) {
+    bool plain = false;   // cudaMalloc instead of the pool: required for memory that is exported through CUDA IPC
+    void alloc(size_t count, bool plain_malloc = false) {
         release();
         n = count;
         stream = g_pool_stream;
-        if (count) CK(cudaMallocAsync(&p, count * sizeof(T), stream));
+        plain = plain_malloc;
+        if (!count) return;
+        if (plain) CK(cudaMalloc(&p, count * sizeof(T))); else CK(cudaMallocAsync(&p, count * sizeof(T), stream));
     }
     void release() {
-        if (p) cudaFreeAsync(p, stream);
+        if (p) { if (plain) cudaFree(p); else cudaFreeAsync(p, stream); }
         p = nullptr; n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }
@@ -132,6 +135,9 @@ struct EsimSim {
     DevBuf<unsigned long long> thr;
     DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
     DevBuf<uint32_t> exch, vax_cand;    // sharded runs
+    DevBuf<uint32_t> peer_mail;         // peer-to-peer exchange (sharded runs): this shard's mailbox in HBM
+    DevBuf<PeerView> peer_view;         // pointer tables of the mapped peers
+    std::vector<void*> peer_mappings;   // cudaIpcOpenMemHandle results
     DevBuf<unsigned int> barrier;       // grid barrier of the persistent kernel
     DevBuf<unsigned long long> pk_prof; // ESIM_TRACE: cycles per phase
     bool use_persistent = false;
@@ -181,7 +187,8 @@ struct EsimSim {
         if (device >= 0) cudaSetDevice(device);
         destroy_graphs();
         if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
-        exch.release(); vax_cand.release(); barrier.release(); pk_prof.release();
+        for (void* m : peer_mappings) cudaIpcCloseMemHandle(m);
+        exch.release(); vax_cand.release(); barrier.release(); pk_prof.release(); peer_mail.release(); peer_view.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt0.release(); cnt1.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
@@ -275,12 +282,13 @@ void enqueue_step(EsimSim* s, uint32_t parity, bool with_pt = true, bool next_ha
     DevView v = s->v;
     v.next_has_pt = next_has_pt ? 1u : 0u;
     launch_update(v, s->stream);
-    if (s->world > 1 && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
+    const bool nccl = s->world > 1 && !s->v.p2p;
+    if (nccl && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
     launch_expose(v, s->stream);
     if (with_pt) launch_pt(v, s->stream);
     if (s->world > 1) {
         launch_vax_prepare(v, s->stream);
-        allreduce_tail(s);
+        if (nccl) allreduce_tail(s);
     }
     launch_tail(v, s->stream);
 }
@@ -524,7 +532,9 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         unsigned long long thr[512];
         build_thresholds(s->cfg, thr);
 
-        s->cnt0.alloc((size_t)B + R + 4); s->cnt1.alloc((size_t)B + R + 4);
+        const bool sharded_pop = p->n_shards > 1;
+        s->cnt0.alloc((size_t)B + R + 4, sharded_pop); s->cnt1.alloc((size_t)B + R + 4, sharded_pop);
+        if (sharded_pop) { s->peer_mail.alloc(MAIL_WORDS, true); CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st)); }
         s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
         s->pt_buscnt.alloc(std::max<uint32_t>(n_riders, 1));
         const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
@@ -571,6 +581,8 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
         v.pt_buscnt = s->pt_buscnt.p; v.rec_bus = s->rec_bus.p; v.rec_businf = s->rec_businf.p;
         v.world = s->world; v.exch = s->exch.p; v.vax_cand = s->vax_cand.p;
+        v.p2p = 0; v.rank = 0; v.peer = nullptr;
+        v.n_shared_b = s->n_shared_bldgs; v.n_shared_r = s->n_shared_rooms;
         v.tally_partial = s->tally_partial.p; v.n_update_blocks = n_update_blocks;
         v.ctrl = s->ctrl.p; v.stats = s->stats.p; v.max_steps = s->cfg.max_time_step;
         v.mp.exposed_time = te; v.mp.infected_time = ti; v.mp.vaccination_rate = s->cfg.vaccination_rate;
@@ -600,20 +612,20 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
             throw ApiError{ESIM_ERR_SIMULATION, "max_time_step reached"};
         const uint32_t before = s->steps_done;
         const uint32_t parity = (before + 1u) & 1u;
-        if (s->world > 1 && !s->comm)
-            throw ApiError{ESIM_ERR_COMM, "sharded handle: attach a communicator (esim_comm_init) or drive the esim_shard_step_* phases"};
+        if (s->world > 1 && !s->comm && !s->v.p2p)
+            throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
         if (timed) {
             const DevView& v = s->v;
             if (s->l2_scratch.p) CK(cudaMemsetAsync(s->l2_scratch.p, (int)(s->steps_done & 0xFF), s->l2_scratch.bytes(), s->stream));
             CK(cudaEventRecord(s->ev[0], s->stream));
             launch_update(v, s->stream);
-            if (s->world > 1 && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
+            if (s->world > 1 && !v.p2p && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
             CK(cudaEventRecord(s->ev[1], s->stream));
             launch_expose(v, s->stream);
             CK(cudaEventRecord(s->ev[2], s->stream));
             launch_pt(v, s->stream);
             CK(cudaEventRecord(s->ev[3], s->stream));
-            if (s->world > 1) { launch_vax_prepare(v, s->stream); allreduce_tail(s); }
+            if (s->world > 1) { launch_vax_prepare(v, s->stream); if (!v.p2p) allreduce_tail(s); }
             launch_tail(v, s->stream);
             CK(cudaEventRecord(s->ev[4], s->stream));
         } else if (s->exec1[parity]) {
@@ -660,8 +672,8 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
         uint32_t budget = std::min<uint32_t>(max_steps, s->cfg.max_time_step - std::min(s->cfg.max_time_step, start));
         // the loop is device-resident: the host only looks at the control block every few simulated days
         constexpr uint32_t CHUNK_DAYS = 8;
-        if (s->world > 1 && !s->comm)
-            throw ApiError{ESIM_ERR_COMM, "sharded handle: attach a communicator (esim_comm_init) or drive the esim_shard_step_* phases"};
+        if (s->world > 1 && !s->comm && !s->v.p2p)
+            throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
         while (budget > 0 && !s->finished) {
             uint32_t queued = 0;
             const uint32_t before_chunk = s->steps_done;
@@ -689,7 +701,7 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
             const uint32_t parity = (s->steps_done + 1u) & 1u;   // GRAPH_DAY is even: the parity is the same for every day
             if (s->exec_day[parity]) {
                 // h_ctrl is current here: no lockdown => the schedule of the coming hours is known
-                const bool spec = s->world == 1 && !s->h_ctrl->lockdown_some && GRAPH_DAY == 24;
+                const bool spec = (s->world == 1 || s->v.p2p) && !s->h_ctrl->lockdown_some && GRAPH_DAY == 24;
                 cudaGraphExec_t day = spec ? spec_day_graph(s, s->steps_done + 1u) : s->exec_day[parity];
                 for (uint32_t d = 0; d < CHUNK_DAYS && budget - queued >= (uint32_t)GRAPH_DAY; ++d) {
                     CK(cudaGraphLaunch(day, s->stream));
@@ -950,6 +962,69 @@ int esim_dump_statistics(EsimSim* s, const char* directory, const char* const* a
 }
 
 // ---- sharded runs ----------------------------------------------------------------------------------------
+namespace {
+struct PeerInfo {   // what a rank publishes; padded to ESIM_PEER_INFO_BYTES
+    cudaIpcMemHandle_t cnt0, cnt1, mail;
+    uint32_t n_bldg, n_rooms, n_shared_b, n_shared_r, world, device;
+};
+static_assert(sizeof(PeerInfo) <= ESIM_PEER_INFO_BYTES, "peer info does not fit");
+}  // namespace
+
+int esim_peer_info(EsimSim* s, uint8_t info[ESIM_PEER_INFO_BYTES]) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (!info) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null info"};
+        if (s->world < 2 || !s->peer_mail.p) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "not a sharded handle"};
+        PeerInfo pi;
+        std::memset(&pi, 0, sizeof(pi));
+        CK(cudaIpcGetMemHandle(&pi.cnt0, s->cnt0.p));
+        CK(cudaIpcGetMemHandle(&pi.cnt1, s->cnt1.p));
+        CK(cudaIpcGetMemHandle(&pi.mail, s->peer_mail.p));
+        pi.n_bldg = s->v.n_bldg; pi.n_rooms = s->v.n_rooms; pi.n_shared_b = s->n_shared_bldgs; pi.n_shared_r = s->n_shared_rooms;
+        pi.world = s->world; pi.device = (uint32_t)s->device;
+        std::memset(info, 0, ESIM_PEER_INFO_BYTES);
+        std::memcpy(info, &pi, sizeof(pi));
+        return ESIM_OK;
+    });
+}
+
+int esim_peer_connect(EsimSim* s, uint32_t rank, uint32_t world, const uint8_t* all_infos) {
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (!all_infos || world != s->world || rank >= world || world > MAX_WORLD)
+            throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "rank / world do not match the imported shard (at most 8 shards)"};
+        if (s->v.p2p || s->comm) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "peers already connected"};
+        if (s->steps_done) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "connect the peers before the first step"};
+        PeerView pv;
+        std::memset(&pv, 0, sizeof(pv));
+        s->v.rank = rank; s->rank = rank;
+        for (uint32_t p = 0; p < world; ++p) {
+            PeerInfo pi;
+            std::memcpy(&pi, all_infos + (size_t)p * ESIM_PEER_INFO_BYTES, sizeof(pi));
+            if (pi.world != world || pi.n_shared_b != s->n_shared_bldgs || pi.n_shared_r != s->n_shared_rooms)
+                throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "peer describes a different sharding"};
+            pv.n_bldg[p] = pi.n_bldg;
+            if (p == rank) {
+                pv.cnt[0][p] = s->cnt0.p; pv.cnt[1][p] = s->cnt1.p; pv.mail[p] = s->peer_mail.p;
+                continue;
+            }
+            void *m0 = nullptr, *m1 = nullptr, *mm = nullptr;
+            CK(cudaIpcOpenMemHandle(&m0, pi.cnt0, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(m0);
+            CK(cudaIpcOpenMemHandle(&m1, pi.cnt1, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(m1);
+            CK(cudaIpcOpenMemHandle(&mm, pi.mail, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(mm);
+            pv.cnt[0][p] = (uint32_t*)m0; pv.cnt[1][p] = (uint32_t*)m1; pv.mail[p] = (uint32_t*)mm;
+        }
+        s->peer_view.alloc(1);
+        CK(cudaMemcpyAsync(s->peer_view.p, &pv, sizeof(pv), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        s->v.peer = s->peer_view.p;
+        s->v.p2p = 1;
+        if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(s);
+        CK(cudaStreamSynchronize(s->stream));
+        return ESIM_OK;
+    });
+}
+
 int esim_comm_unique_id(uint8_t id[128]) {
     return guarded(nullptr, [&]() -> int {
         NcclApi* n = nccl_api();

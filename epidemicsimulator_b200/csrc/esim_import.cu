@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "esim_import.h"
 #include "esim_internal.h"
@@ -126,16 +127,16 @@ cudaError_t import_convert(const ImportRaw& raw, const ImportOut& out, uint32_t*
 
 size_t route_build_temp_bytes(uint32_t n_citizens) {
     size_t a = 0, b = 0, c = 0;
-    cub::DeviceSelect::Flagged(nullptr, a, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_citizens);
+    cub::DeviceSelect::Flagged(nullptr, a, thrust::counting_iterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_citizens);
     cub::DeviceRadixSort::SortPairs(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_citizens);
-    cub::DeviceSelect::Flagged(nullptr, c, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_citizens);
+    cub::DeviceSelect::Flagged(nullptr, c, thrust::counting_iterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_citizens);
     size_t m = a > b ? a : b;
     return (m > c ? m : c) + 256;
 }
 
 // step 1: compact the riders (ascending citizen index); *d_count receives their number
 cudaError_t route_select_riders(const ImportOut& out, uint32_t n_pad, uint32_t* rider_idx, uint32_t* d_count, void* temp, size_t temp_bytes, cudaStream_t s) {
-    return cub::DeviceSelect::Flagged(temp, temp_bytes, cub::CountingInputIterator<uint32_t>(0), out.is_rider, rider_idx, d_count, (int)n_pad, s);
+    return cub::DeviceSelect::Flagged(temp, temp_bytes, thrust::counting_iterator<uint32_t>(0), out.is_rider, rider_idx, d_count, (int)n_pad, s);
 }
 
 // step 2: stable sort by route key, then mark and compact the first rider of every route
@@ -147,7 +148,7 @@ cudaError_t route_sort_and_heads(const ImportOut& out, const uint32_t* rider_idx
     cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, rider_idx, riders_sorted, (int)n_riders, 0, 64, s);
     if (e != cudaSuccess) return e;
     k_route_heads<<<(n_riders + 255) / 256, 256, 0, s>>>(keys_out, head, n_riders);
-    return cub::DeviceSelect::Flagged(temp, temp_bytes, cub::CountingInputIterator<uint32_t>(0), head, route_off, d_count, (int)n_riders, s);
+    return cub::DeviceSelect::Flagged(temp, temp_bytes, thrust::counting_iterator<uint32_t>(0), head, route_off, d_count, (int)n_riders, s);
 }
 
 cudaError_t export_state(const ExportArgs& a, cudaStream_t s) {

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define ESIM_VAX_SHARD_DRAWS 4096u   // vaccination candidate draws a sharded run examines per step
+
 #include "esim.h"
 
 namespace esim {
@@ -38,8 +40,23 @@ constexpr uint32_t CS_HAS_WORK    = 1u << 20;
 constexpr uint32_t CS_PADDING     = 0xFFFFu;
 constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 2
 constexpr uint32_t MAX_STEPS      = CS_EXPOSURE - EXPOSURE_BIAS - 1;
-#define ESIM_VAX_SHARD_DRAWS 8192u   // vaccination candidate draws a sharded run examines per step
 constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer, see k_vax_prepare
+
+// ---- peer-to-peer exchange of a sharded run (one process per GPU, NVLink peer mappings) --------------------------------
+// Every shard owns a mailbox in its own HBM that its peers write into:
+//   flag_a[r]  time step for which peer r has finished pushing its infected counts into this shard's count buffer
+//   flag_b[r]  time step for which peer r's tail vector has arrived
+//   vec_b[t & 1][r][EXCH_WORDS]  peer r's tail vector of step t (double-buffered: a peer can be at most one step ahead)
+constexpr uint32_t MAX_WORLD      = 8;
+constexpr uint32_t MAIL_FLAG_A    = 0;
+constexpr uint32_t MAIL_FLAG_B    = MAX_WORLD;
+constexpr uint32_t MAIL_VEC_B     = 32;
+constexpr uint32_t MAIL_WORDS     = MAIL_VEC_B + 2 * MAX_WORLD * (8 + ESIM_VAX_SHARD_DRAWS / 32);
+struct PeerView {                       // lives in device memory: kernel parameters stay small
+    uint32_t n_bldg[MAX_WORLD];         // peers' n_bldg (their room cells start there)
+    uint32_t* cnt[2][MAX_WORLD];        // peers' count buffers
+    uint32_t* mail[MAX_WORLD];          // peers' mailboxes ([rank] = own)
+};
 
 // device-resident control block: the scalar part of Simulator / InterventionStatus / StatisticsRecorder
 struct Ctrl {
@@ -59,8 +76,9 @@ struct Ctrl {
     uint32_t new_exp_pt;     // successful public-transport exposures of step t
     uint32_t vaccinated_now;
     uint32_t abort_graph;    // the schedule left the assumptions of the specialised graph being replayed: the rest of it is a no-op
+    uint32_t blocks_done;    // last-block-done counter of k_update in peer-to-peer mode
     uint32_t eager_expose;   // more than a quarter of the citizens are susceptible: k_expose loads cell ids eagerly
-    uint32_t pad[7];
+    uint32_t pad[6];
 };
 
 struct ModelParams {
@@ -94,6 +112,10 @@ struct DevView {
     uint32_t* pt_buscnt;   // [n_riders] scratch: infected riders per bus (route_off[r] + bus)
     uint32_t* rec_bus;     // [n] optional record: bus index per citizen
     uint32_t* rec_businf;  // [n] optional record: infected on that bus
+    uint32_t p2p;                // 1 = peers are mapped: the kernels exchange over NVLink themselves
+    uint32_t rank;
+    uint32_t n_shared_b, n_shared_r;   // the first cells of the building / room ranges exist on every shard
+    const PeerView* peer;        // device memory, valid when p2p
     uint32_t world;              // number of shards (1 = the whole population is here)
     uint32_t* exch;              // [EXCH_WORDS] second exchange buffer of a sharded step
     uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] candidate citizen of every draw of this step

@@ -10,6 +10,7 @@
 // All are HBM/L2-bandwidth or latency bound integer kernels: no tensor-core work exists on this path.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "esim_internal.h"
 #include "esim_rng.h"
@@ -52,6 +53,47 @@ __device__ __forceinline__ void pdl_prologue() {
 __device__ __forceinline__ uint32_t warp_sum(uint32_t x) { return __reduce_add_sync(0xffffffffu, x); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// ---- peer-to-peer helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t x) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(x) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t x;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+    return x;
+}
+// An infected citizen standing in a cell that other shards reference adds itself to their count buffers as well
+// (system-scope reductions over NVLink); after the flag exchange every shard holds the global count of its shared cells.
+__device__ __forceinline__ bool push_to_peers(const DevView& v, uint32_t parity, uint32_t cell) {
+    const PeerView& pv = *v.peer;
+    if (cell < v.n_shared_b) {
+        for (uint32_t p = 0; p < v.world; ++p)
+            if (p != v.rank) atomicAdd_system(pv.cnt[parity][p] + cell, 1u);
+        return true;
+    }
+    if (cell >= v.n_bldg && cell - v.n_bldg < v.n_shared_r) {
+        const uint32_t r = cell - v.n_bldg;
+        for (uint32_t p = 0; p < v.world; ++p)
+            if (p != v.rank) atomicAdd_system(pv.cnt[parity][p] + pv.n_bldg[p] + r, 1u);
+        return true;
+    }
+    return false;
+}
+// thread 0 of the block waits until every peer's flag has reached `t`; bounded, so that a lost peer raises an error
+// instead of hanging the GPU
+__device__ __forceinline__ void wait_for_peers(const DevView& v, uint32_t flag_base, uint32_t t) {
+    if (threadIdx.x == 0) {
+        const uint32_t* mail = v.peer->mail[v.rank];
+        for (uint32_t p = 0; p < v.world; ++p) {
+            if (p == v.rank) continue;
+            uint32_t spins = 0;
+            while (ld_acquire_sys(mail + flag_base + p) < t) {
+                if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_COMM); break; }
+                __nanosleep(64);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // k_update counts cumulatively (#code != 0, #code >= i_lo, #code >= e_lo, #code >= 0x8000) over all n_pad slots, the padding
 // slots counting as vaccinated: turn that into S, E, I, R, V of the n real citizens.
 __device__ __forceinline__ void classes_from_cumulative(const uint32_t* cum, uint32_t n_pad, uint32_t n, uint32_t* out5) {
@@ -76,7 +118,9 @@ constexpr int UPDATE_THREADS = 256;
 constexpr int UPDATE_UNROLL = 4;
 
 // `s_cnt` = 4 words of shared memory; the block's partial tallies go to tally_partial[blockIdx.x * 8 ..]
-__device__ __forceinline__ void update_phase(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt) {
+// returns true if this thread added to a peer's count buffer
+__device__ __forceinline__ bool update_phase(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt) {
+    bool pushed = false;
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
@@ -136,7 +180,12 @@ __device__ __forceinline__ void update_phase(const DevView& v, const Ctrl* __res
                     if (code >= i_lo && code < e_lo && (w[k] & rider_mask) == 0u) {
                         const uint32_t cell = pos[((q0 + u * T) << 2) + (uint32_t)k];
                         atomicAdd(&cnt[cell], 1u);
-                        if (cell >= v.n_bldg) atomicAdd(&cnt[v.room_parent[cell - v.n_bldg]], 1u);
+                        if (v.p2p) pushed |= push_to_peers(v, t & 1u, cell);
+                        if (cell >= v.n_bldg) {
+                            const uint32_t school = v.room_parent[cell - v.n_bldg];
+                            atomicAdd(&cnt[school], 1u);
+                            if (v.p2p) pushed |= push_to_peers(v, t & 1u, school);
+                        }
                     }
                 }
             }
@@ -153,6 +202,7 @@ __device__ __forceinline__ void update_phase(const DevView& v, const Ctrl* __res
     }
     __syncthreads();
     if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
+    return pushed;
 }
 
 __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
@@ -160,7 +210,23 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     __shared__ uint32_t s_cnt[4];
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
-    update_phase(v, c, s_cnt);
+    const uint32_t t = c->t;
+    const bool pushed = update_phase(v, c, s_cnt);
+    if (v.p2p && (v.n_shared_b | v.n_shared_r)) {
+        // The last block to finish tells every peer that this shard's counts of step t are complete.  One thread fences for
+        // its block after the barrier (the pattern of a cooperative grid sync); the fence is system-wide only if the block
+        // really wrote to a peer.
+        const int any_pushed = __syncthreads_or(pushed);
+        if (threadIdx.x == 0) {
+            if (any_pushed) __threadfence_system(); else __threadfence();
+            if (atomicAdd(&v.ctrl->blocks_done, 1u) == gridDim.x - 1u) {
+                v.ctrl->blocks_done = 0;
+                __threadfence_system();
+                for (uint32_t p = 0; p < v.world; ++p)
+                    if (p != v.rank) st_release_sys(v.peer->mail[p] + MAIL_FLAG_A + v.rank, t);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -186,7 +252,9 @@ __device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long 
 // output area") becomes two bit tests per citizen:
 //   at home:  household trial always,                   workplace trial iff HAS_WORK and SAME_AREA
 //   at work:  household trial iff SAME_AREA,            workplace trial iff HAS_WORK
-template <bool AT_WORK>
+// CG: read the counts with ld.global.cg (needed inside the persistent kernel, where another SM wrote them during the same
+// launch); the graph kernels use the L1-cached read-only path: neighbours in a quad share their household.
+template <bool AT_WORK, bool CG>
 __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, const uint4 w4,
                                                 const uint4 h4, const uint4 k4, uint32_t t, uint32_t mask_everywhere) {
     const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -202,8 +270,8 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
     uint32_t n_h[4], n_w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        n_h[k] = (w[k] & HOME_TEST) == HOME_WANT ? __ldcg(&cnt[hc[k]]) : 0u;   // .cg: written by other SMs in this launch
-        n_w[k] = (w[k] & WORK_TEST) == WORK_WANT ? __ldcg(&cnt[wc[k]]) : 0u;
+        n_h[k] = (w[k] & HOME_TEST) == HOME_WANT ? (CG ? __ldcg(&cnt[hc[k]]) : __ldg(&cnt[hc[k]])) : 0u;
+        n_w[k] = (w[k] & WORK_TEST) == WORK_WANT ? (CG ? __ldcg(&cnt[wc[k]]) : __ldg(&cnt[wc[k]])) : 0u;
     }
     if (!(n_h[0] | n_h[1] | n_h[2] | n_h[3] | n_w[0] | n_w[1] | n_w[2] | n_w[3])) return 0u;
     uint32_t n_exposed = 0;
@@ -218,7 +286,8 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
         if (n_h[k]) thr_h = __ldg(&v.thr[mc + (n_h[k] & 255u)]);  // `exposure_total as u8` (citizen.rs:239)
         if (n_w[k]) {
             // a room member gets one trial per infected member of its own room, each with n = infected in the school
-            const uint32_t n_total = wc[k] >= n_bldg ? __ldcg(&cnt[__ldg(&v.room_parent[wc[k] - n_bldg])]) : n_w[k];
+            const uint32_t school = wc[k] >= n_bldg ? __ldg(&v.room_parent[wc[k] - n_bldg]) : 0u;
+            const uint32_t n_total = wc[k] >= n_bldg ? (CG ? __ldcg(&cnt[school]) : __ldg(&cnt[school])) : n_w[k];
             thr_w = __ldg(&v.thr[mc + (n_total & 255u)]);
             k_w = thr_w ? (wc[k] >= n_bldg ? n_w[k] : 1u) : 0u;
         }
@@ -238,7 +307,7 @@ __device__ __forceinline__ bool any_susceptible(const uint4 w) {
 
 // EAGER: request the household / workplace ids together with the state words (one memory round trip less per quad);
 // used while more than a quarter of the shard is susceptible, when nearly every quad needs them anyway.
-template <bool EAGER, bool AT_WORK>
+template <bool EAGER, bool AT_WORK, bool CG>
 __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* __restrict__ c) {
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
@@ -253,8 +322,8 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
         const uint32_t q1 = q0 + T;
         const bool have1 = q1 < n_quads;
-        const uint4 wa = __ldcg(cs4 + q0);
-        const uint4 wb = have1 ? __ldcg(cs4 + q1) : pad4;
+        const uint4 wa = CG ? __ldcg(cs4 + q0) : cs4[q0];
+        const uint4 wb = have1 ? (CG ? __ldcg(cs4 + q1) : cs4[q1]) : pad4;
         uint4 ha, ka, hb, kb;
         if (EAGER) {
             ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0);
@@ -265,8 +334,8 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
             if (sa) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
             if (sb) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
         }
-        if (sa) n_exposed += expose_quad<AT_WORK>(v, cnt, q0, wa, ha, ka, t, mask_everywhere);
-        if (sb) n_exposed += expose_quad<AT_WORK>(v, cnt, q1, wb, hb, kb, t, mask_everywhere);
+        if (sa) n_exposed += expose_quad<AT_WORK, CG>(v, cnt, q0, wa, ha, ka, t, mask_everywhere);
+        if (sb) n_exposed += expose_quad<AT_WORK, CG>(v, cnt, q1, wb, hb, kb, t, mask_everywhere);
     }
     return n_exposed;
 }
@@ -275,9 +344,10 @@ __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
     pdl_prologue();
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
+    if (v.p2p && (v.n_shared_b | v.n_shared_r)) wait_for_peers(v, MAIL_FLAG_A, c->t);   // peers' pushes have landed
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
-    const uint32_t n_exposed = eager ? (at_work ? expose_stream<true, true>(v, c) : expose_stream<true, false>(v, c))
-                                     : (at_work ? expose_stream<false, true>(v, c) : expose_stream<false, false>(v, c));
+    const uint32_t n_exposed = eager ? (at_work ? expose_stream<true, true, false>(v, c) : expose_stream<true, false, false>(v, c))
+                                     : (at_work ? expose_stream<false, true, false>(v, c) : expose_stream<false, false, false>(v, c));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
 }
@@ -496,6 +566,17 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
     if (tid < 8) sm.tally[tid] = 0;
     __syncthreads();
     const bool sharded = v.world > 1;
+    if (sharded && v.p2p) {
+        // sum the tail vectors of all shards (fixed order) into the exchange buffer the code below reads
+        wait_for_peers(v, MAIL_FLAG_B, sm.c.t);
+        const uint32_t* mail = v.peer->mail[v.rank] + MAIL_VEC_B + (sm.c.t & 1u) * MAX_WORLD * EXCH_WORDS;
+        for (uint32_t h = tid; h < EXCH_WORDS; h += NT) {
+            uint32_t sum = 0;
+            for (uint32_t p = 0; p < v.world; ++p) sum += __ldcg(mail + p * EXCH_WORDS + h);
+            v.exch[h] = sum;
+        }
+        __syncthreads();
+    }
     if (sharded) {
         // k_vax_prepare + the all-reduce left the global tallies and exposure counts in the exchange buffer
         if (tid < 5) sm.tally[tid] = __ldcg(&v.exch[tid]);
@@ -575,15 +656,19 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                 if (lane == 31) sm.batch_total = inc2;
             }
             __syncthreads();
-            if (tid < VAX_SHARD_DRAWS / 32) {
-                uint32_t bits = __ldcg(&mask[tid]);
-                uint32_t rank = sm.scan[wid] + (incl - pc);   // set bits before this word
-                while (bits && rank < K) {
-                    const uint32_t b = __ffs(bits) - 1u;
-                    bits &= bits - 1u;
-                    const uint32_t local = __ldcg(&v.vax_cand[tid * 32u + b]) - v.mp.shard_lo;
+            // scan[] now holds, per warp, the number of set bits before the warp's first word; word-level prefixes are
+            // recomputed per draw: every thread looks at VAX_SHARD_DRAWS / NT independent draws (all loads in flight)
+            {
+                __shared__ uint32_t s_word_prefix[VAX_SHARD_DRAWS / 32];
+                if (tid < VAX_SHARD_DRAWS / 32) s_word_prefix[tid] = sm.scan[wid] + (incl - pc);
+                __syncthreads();
+                for (uint32_t j = tid; j < VAX_SHARD_DRAWS; j += NT) {
+                    const uint32_t word = __ldcg(&mask[j >> 5]);
+                    if (!((word >> (j & 31u)) & 1u)) continue;
+                    const uint32_t rank = s_word_prefix[j >> 5] + __popc(word & ((1u << (j & 31u)) - 1u));
+                    if (rank >= K) continue;
+                    const uint32_t local = __ldcg(&v.vax_cand[j]) - v.mp.shard_lo;
                     if (local < v.n) atomicOr(&v.cstate[local], CS_VACCINATED);
-                    ++rank;
                 }
             }
             if (tid == 0) {
@@ -713,7 +798,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
 //   exch[0..4] S,E,I,R,V of this shard   exch[5..6] building / public-transport exposures of this shard
 //   exch[8 + j/32] bit j%32: draw j of the vaccination candidate stream is owned by this shard, eligible, and the first
 //   occurrence of its citizen.  Duplicates of a citizen are owned by the same shard, so de-duplication is local.
-constexpr uint32_t VP_HT = 2 * VAX_SHARD_DRAWS;  // hash slots (power of two)
+constexpr uint32_t VP_HT = VAX_SHARD_DRAWS;  // hash slots (power of two): a shard owns about 1/world of the draws
 __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
     pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
@@ -744,16 +829,23 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
     uint32_t wv[PER], slot[PER];
     bool owned[PER];
     if (may_vaccinate) {
+        uint32_t cands[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {   // all candidate draws and state-word gathers of the thread in flight together
+            const uint32_t j = tid * PER + q;
+            cands[q] = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
+            v.vax_cand[j] = cands[q];
+            const uint32_t local = cands[q] - v.mp.shard_lo;
+            owned[q] = local < v.n;
+            wv[q] = owned[q] ? __ldcg(&v.cstate[local]) : 0u;
+        }
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             const uint32_t j = tid * PER + q;
-            const uint32_t cand = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
-            v.vax_cand[j] = cand;
-            const uint32_t local = cand - v.mp.shard_lo;
-            wv[q] = 0u; slot[q] = 0; owned[q] = local < v.n;
+            const uint32_t cand = cands[q];
+            slot[q] = 0;
             if (owned[q]) {
-                wv[q] = __ldcg(&v.cstate[local]);
-                uint32_t h = (cand * 2654435761u) >> 18 & (VP_HT - 1);
+                uint32_t h = (cand * 2654435761u) >> 20 & (VP_HT - 1);
                 while (true) {
                     const uint32_t prev = atomicCAS(&keys[h], HT_EMPTY, cand);
                     if (prev == HT_EMPTY || prev == cand) break;
@@ -782,6 +874,16 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
     if (tid == 6) v.exch[6] = c->new_exp_pt;
     if (tid == 7) v.exch[7] = 0;
     for (uint32_t h = tid; h < VAX_SHARD_DRAWS / 32; h += TAIL_THREADS) v.exch[8 + h] = mask[h];
+    if (v.p2p) {
+        // hand the vector to every shard (including this one) and raise the arrival flag
+        __syncthreads();
+        const uint32_t slot = MAIL_VEC_B + ((t & 1u) * MAX_WORLD + v.rank) * EXCH_WORDS;
+        for (uint32_t p = 0; p < v.world; ++p)
+            for (uint32_t h = tid; h < EXCH_WORDS; h += TAIL_THREADS) v.peer->mail[p][slot + h] = v.exch[h];
+        __threadfence_system();
+        __syncthreads();
+        if (tid < v.world && tid != v.rank) st_release_sys(v.peer->mail[tid] + MAIL_FLAG_B + v.rank, t);
+    }
 }
 constexpr size_t VP_SMEM = (2 * VP_HT + VAX_SHARD_DRAWS / 32) * sizeof(uint32_t);
 
@@ -818,11 +920,11 @@ __device__ __noinline__ void pk_pt_phase(const DevView* v, PtWarpSmem* ws, uint3
 __device__ __noinline__ void pk_tail_phase(const DevView* v, uint32_t* ht, TailSmem* sm, uint32_t n_partial_blocks) {
     tail_phase<PK_THREADS>(*v, ht, *sm, n_partial_blocks);
 }
-__device__ __noinline__ void pk_update_phase(const DevView* v, const Ctrl* c, uint32_t* s_cnt) { update_phase(*v, c, s_cnt); }
+__device__ __noinline__ void pk_update_phase(const DevView* v, const Ctrl* c, uint32_t* s_cnt) { (void)update_phase(*v, c, s_cnt); }
 __device__ __noinline__ uint32_t pk_expose_phase(const DevView* v, const Ctrl* c) {
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
-    return eager ? (at_work ? expose_stream<true, true>(*v, c) : expose_stream<true, false>(*v, c))
-                 : (at_work ? expose_stream<false, true>(*v, c) : expose_stream<false, false>(*v, c));
+    return eager ? (at_work ? expose_stream<true, true, true>(*v, c) : expose_stream<true, false, true>(*v, c))
+                 : (at_work ? expose_stream<false, true, true>(*v, c) : expose_stream<false, false, true>(*v, c));
 }
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& generation) {
@@ -917,6 +1019,15 @@ int configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vax_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
+    // One shared-memory carve-out for every step kernel: switching the L1 / shared split between consecutive kernels costs
+    // microseconds, which is what a step is made of.  ESIM_CARVEOUT (percent) overrides the default for experiments.
+    int carve = -1;
+    if (const char* env = getenv("ESIM_CARVEOUT")) carve = atoi(env);
+    if (carve >= 0) {
+        const void* all[] = {(const void*)k_update, (const void*)k_expose, (const void*)k_pt, (const void*)k_tail, (const void*)k_vax_prepare};
+        for (const void* f : all)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
     return (int)e;
 }
 

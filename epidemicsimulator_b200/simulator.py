@@ -190,6 +190,24 @@ class Simulator:
         ident = (C.c_uint8 * 128)(*t.cpu().tolist())
         self._check(self._lib.esim_comm_init(self._h, ident, rank, world))
 
+    PEER_INFO_BYTES = 256
+
+    def connect_peers(self, dist) -> None:
+        """Map the count buffers and mailboxes of the other ranks (CUDA IPC over NVLink); afterwards step() / run() exchange
+        inside the kernels, without a collective library.  `dist` is an initialised torch.distributed process group."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        info = (C.c_uint8 * self.PEER_INFO_BYTES)()
+        self._check(self._lib.esim_peer_info(self._h, info))
+        dev = torch.device("cuda", self.cfg.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        mine = torch.tensor(list(info), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        flat = bytes(torch.cat(gathered).cpu().tolist())
+        buf = (C.c_uint8 * len(flat)).from_buffer_copy(flat)
+        self._check(self._lib.esim_peer_connect(self._h, rank, world, buf))
+        dist.barrier()   # nobody steps before every rank has mapped every peer
+
     def shard_step_begin(self) -> None:
         self._check(self._lib.esim_shard_step_begin(self._h))
 

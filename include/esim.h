@@ -249,6 +249,14 @@ int esim_get_timings(EsimSim* sim, EsimTimings* out);
  */
 #define ESIM_EXCH_COUNTS 0
 #define ESIM_EXCH_TAIL   1
+/* Peer-to-peer exchange (preferred on an NVLink box): every rank publishes ESIM_PEER_INFO_BYTES describing its count
+ * buffers and mailbox (CUDA IPC handles), the application all-gathers them (rank order), and esim_peer_connect maps the
+ * peers.  The update kernel then adds infected counts of shared cells straight into the peers' buffers and the tail
+ * vectors travel through the mailboxes: no collective library, no extra kernel launches. */
+#define ESIM_PEER_INFO_BYTES 256
+int esim_peer_info(EsimSim* sim, uint8_t info[ESIM_PEER_INFO_BYTES]);
+int esim_peer_connect(EsimSim* sim, uint32_t rank, uint32_t world, const uint8_t* all_infos /* world * ESIM_PEER_INFO_BYTES */);
+
 int esim_comm_unique_id(uint8_t id[128]);                    /* ncclGetUniqueId, call on rank 0 and broadcast */
 int esim_comm_init(EsimSim* sim, const uint8_t id[128], uint32_t rank, uint32_t world);
 int esim_shard_step_begin(EsimSim* sim);                     /* update kernel; ESIM_EXCH_COUNTS holds this shard's part */

@@ -6,7 +6,7 @@
 //     begin()   disease progression, schedule, tally, infected occupants per building / room
 //                 -> exchange 0: counts of the shared buildings, then of the shared rooms
 //     middle()  building trials (every susceptible citizen pulls the counts of its <= 3 sources), public transport
-//                 -> exchange 1: [S,E,I,R,V, building exposures, PT exposures, 0, accept mask of 8192 vaccination draws]
+//                 -> exchange 1: [S,E,I,R,V, building exposures, PT exposures, 0, accept mask of 4096 vaccination draws]
 //     end()     statistics, InterventionStatus::update_status, vaccination picks, next hour's schedule
 //
 // It serves two purposes on hosts without a GPU: (1) with one shard it must reproduce the push oracle bit for bit, which
@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr uint32_t SHARD_DRAWS = 8192;            // vaccination candidate draws examined per step by a sharded run
+constexpr uint32_t SHARD_DRAWS = 4096;            // vaccination candidate draws examined per step by a sharded run
 constexpr uint32_t EXCH1_WORDS = 8 + SHARD_DRAWS / 32;
 
 void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t out[4]) {
@@ -223,7 +223,7 @@ struct PullShard {
                         if (c >= lo && c < lo + n) { status[c - lo] = V; timer[c - lo] = 0; }
                         ++accepted;
                     }
-                if (accepted < K) error = "vaccination needs more than 8192 candidate draws";
+                if (accepted < K) error = "vaccination needs more than 4096 candidate draws";
             }
         }
         s.lockdown_hours = lockdown_some ? lockdown : ESIM_NONE_U32;

@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--areas", type=int, default=120)
 ap.add_argument("--cross", type=float, default=0.5)
 ap.add_argument("--steps", type=int, default=600)
+ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -30,7 +31,10 @@ pop = synthetic_population(args.areas, areas_per_school=10, cross_area_fraction=
 shard = shard_population(pop, rank, world)
 cfg = dict(exposure_chance=0.02, vaccination_rate=120, seed=99, device=local)
 sim = Simulator.from_population(shard, default_config(**cfg))
-sim.attach_comm(dist)
+if args.comm == "p2p":
+    sim.connect_peers(dist)
+else:
+    sim.attach_comm(dist)
 # a few single steps (one-step graphs of both parities), then the bulk run (day graphs)
 for _ in range(5):
     sim.step()
@@ -56,8 +60,8 @@ if rank == 0:
         if not np.array_equal(state[k], mine[k]):
             ok = False
             print("MISMATCH per-citizen", k)
-    print("sharded_check world=%d citizens=%d steps=%d shared_bldgs=%d shared_rooms=%d: %s" % (
-        world, pop.n_citizens, n, shard.n_shared_bldgs, shard.n_shared_rooms, "OK" if ok else "FAILED"))
+    print("sharded_check comm=%s world=%d citizens=%d steps=%d shared_bldgs=%d shared_rooms=%d: %s" % (
+        args.comm, world, pop.n_citizens, n, shard.n_shared_bldgs, shard.n_shared_rooms, "OK" if ok else "FAILED"))
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 sim.close()

@@ -286,10 +286,10 @@ void enqueue_step(EsimSim* s, uint32_t parity, bool with_pt = true, bool next_ha
     if (nccl && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
     launch_expose(v, s->stream);
     if (with_pt) launch_pt(v, s->stream);
-    if (s->world > 1) {
+    if (nccl) {
         launch_vax_prepare(v, s->stream);
-        if (nccl) allreduce_tail(s);
-    }
+        allreduce_tail(s);
+    }   // peer-to-peer shards: the tail kernel prepares and exchanges the vector itself
     launch_tail(v, s->stream);
 }
 
@@ -625,7 +625,7 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
             CK(cudaEventRecord(s->ev[2], s->stream));
             launch_pt(v, s->stream);
             CK(cudaEventRecord(s->ev[3], s->stream));
-            if (s->world > 1) { launch_vax_prepare(v, s->stream); if (!v.p2p) allreduce_tail(s); }
+            if (s->world > 1 && !v.p2p) { launch_vax_prepare(v, s->stream); allreduce_tail(s); }
             launch_tail(v, s->stream);
             CK(cudaEventRecord(s->ev[4], s->stream));
         } else if (s->exec1[parity]) {

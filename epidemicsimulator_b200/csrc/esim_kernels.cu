@@ -799,15 +799,13 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
 //   exch[8 + j/32] bit j%32: draw j of the vaccination candidate stream is owned by this shard, eligible, and the first
 //   occurrence of its citizen.  Duplicates of a citizen are owned by the same shard, so de-duplication is local.
 constexpr uint32_t VP_HT = VAX_SHARD_DRAWS;  // hash slots (power of two): a shard owns about 1/world of the draws
-__global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
-    pdl_prologue();
-    extern __shared__ uint32_t dyn_smem[];
+// `dyn_smem`: at least VP_SMEM bytes; must be called by all TAIL_THREADS threads of one block
+__device__ __forceinline__ void vax_prepare_phase(const DevView& v, uint32_t* dyn_smem) {
     uint32_t* keys = dyn_smem;                 // [VP_HT]
     uint32_t* minj = dyn_smem + VP_HT;         // [VP_HT]
     uint32_t* mask = dyn_smem + 2 * VP_HT;     // [VAX_SHARD_DRAWS / 32]
     __shared__ uint32_t s_tally[8];
     const Ctrl* __restrict__ c = v.ctrl;
-    if (c->finished | c->abort_graph) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t t = c->t;
     if (tid < 8) s_tally[tid] = 0;
@@ -884,6 +882,14 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
         __syncthreads();
         if (tid < v.world && tid != v.rank) st_release_sys(v.peer->mail[tid] + MAIL_FLAG_B + v.rank, t);
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
+    pdl_prologue();
+    extern __shared__ uint32_t dyn_smem[];
+    if (v.ctrl->finished | v.ctrl->abort_graph) return;
+    vax_prepare_phase(v, dyn_smem);
 }
 constexpr size_t VP_SMEM = (2 * VP_HT + VAX_SHARD_DRAWS / 32) * sizeof(uint32_t);
 
@@ -903,6 +909,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
     if (v.ctrl->finished | v.ctrl->abort_graph) return;
+    if (v.p2p) vax_prepare_phase(v, dyn_smem);   // peer-to-peer shards: prepare, send, wait and finish in one launch
     tail_phase<TAIL_THREADS>(v, dyn_smem, sm, v.n_update_blocks);
 }
 

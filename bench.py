@@ -127,14 +127,15 @@ def hbm_peak():
 
 def algorithmic_bytes(stats, n_citizens, n_cells):
     """Per-step algorithmic bytes of the two streaming kernels for the layout in DESIGN.md section 3.
-    k_update: 4 B state word per citizen + 8 B (position id + count update) per infected citizen + the zeroing of the counts.
-    k_expose: 4 B state word per citizen + per susceptible citizen 8 B (household + workplace ids) + 8 B (two count gathers)."""
+    k_update: 4 B state word per citizen + 8 B (position id + count update) per infected citizen + 4 B per cell (zeroing).
+    k_expose: 4 B state word per citizen + 8 B (household + workplace ids) per susceptible citizen + 4 B per cell (every
+              infected count is needed from HBM once; citizens sharing a household / workplace share the fetch)."""
     from epidemicsimulator_b200 import _abi
     f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
     s_before = stats[:, f["susceptible"]] + stats[:, f["exposures_building"]] + stats[:, f["exposures_pt"]]
     infected = stats[:, f["infected"]]
     upd = 4.0 * n_citizens + 8.0 * infected + 4.0 * n_cells
-    exp = 4.0 * n_citizens + 16.0 * s_before
+    exp = 4.0 * n_citizens + 8.0 * s_before + 4.0 * n_cells
     return upd, exp
 
 

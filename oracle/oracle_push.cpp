@@ -25,6 +25,14 @@
 //     shuffle (SliceRandom::shuffle, simulator.rs:362) = ascending order of (shuffle key, citizen index)
 //     choose_multiple (simulator.rs:525-527) = the first K distinct eligible citizens of the candidate stream
 //
+//
+// A second randomness mode (oracle_set_rng_mode(o, 1)) consumes a *sequential* generator the way the reference consumes
+// rand 0.8: one generator per worker thread for the building trials (thread_rng(), simulator.rs:342), Fisher-Yates
+// `shuffle` from the top (simulator.rs:362), the reservoir of `choose_multiple` (simulator.rs:525-527).  It is not
+// reproducible across thread counts, like the reference; tests/test_distribution.py uses it to show that the
+// counter-based stream above yields the same epidemic *in distribution* (north star: daily S/E/I/R inside the
+// seed-to-seed 95 % band over 20 seeds).
+//
 // Build: see oracle/Makefile (g++ -O3 -fopenmp -shared).
 #include <algorithm>
 #include <cmath>
@@ -36,6 +44,8 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+
+#include <omp.h>
 
 #include "esim.h"  // struct layouts of the boundary only (EsimConfig, EsimPopulationSoA, EsimStepStats, EsimStateView)
 
@@ -93,6 +103,39 @@ struct Stream {
         block(draw, step, 0, 2, o);
         const uint64_t x = ((uint64_t)o[1] << 32) | o[0];
         return (uint32_t)(((unsigned __int128)x * n) >> 64);
+    }
+};
+
+// Sequential generator for rng mode 1: xoshiro256++ (Blackman, Vigna) seeded through SplitMix64.  The reference's
+// ChaCha12 `thread_rng()` is OS-seeded, so only the way the stream is *consumed* matters here.
+struct SeqRng {
+    uint64_t s[4];
+    void seed(uint64_t x) {
+        for (int k = 0; k < 4; ++k) {
+            x += 0x9E3779B97F4A7C15ull;
+            uint64_t z = x;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            s[k] = z ^ (z >> 31);
+        }
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() {
+        const uint64_t result = rotl(s[0] + s[3], 23) + s[0];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t; s[3] = rotl(s[3], 45);
+        return result;
+    }
+    double uniform() { const uint64_t x = next(); return Stream::to_unit((uint32_t)x, (uint32_t)(x >> 32)); }
+    // rand 0.8 `gen_index(rng, ubound)` = rng.gen_range(0..ubound): widening multiply with rejection (unbiased)
+    size_t gen_index(size_t ubound) {
+        const uint64_t range = (uint64_t)ubound;
+        const uint64_t zone = ~(uint64_t)0 - ((~(uint64_t)0 - range + 1) % range);
+        while (true) {
+            const unsigned __int128 m = (unsigned __int128)next() * range;
+            if ((uint64_t)m <= zone) return (size_t)(m >> 64);
+        }
     }
 };
 
@@ -331,6 +374,15 @@ struct Oracle {
     DiseaseModel disease_model;
     uint32_t bus_capacity = 20;
     Stream rng{0};
+    int rng_mode = 0;                    // 0 = counter-based stream shared with the CUDA kernels, 1 = sequential (see header)
+    SeqRng seq_rng;                      // Simulator::rng (simulator.rs:101)
+    std::vector<SeqRng> thread_rngs;     // thread_rng() of every worker
+    void set_rng_mode(int mode) {
+        rng_mode = mode;
+        seq_rng.seed(rng.seed * 0x2545F4914F6CDD1Dull + 1);
+        thread_rngs.resize((size_t)omp_get_max_threads());
+        for (size_t k = 0; k < thread_rngs.size(); ++k) thread_rngs[k].seed(rng.seed * 0x9E3779B97F4A7C15ull + 1000003ull * (k + 1));
+    }
     // StatisticsRecorder (statistics.rs:97-110)
     uint32_t current_time_step = 0;
     std::vector<StatisticEntry> global_stats;
@@ -466,7 +518,8 @@ struct Oracle {
                     Citizen& citizen = area.citizens[lookup_ref.second];
                     if (!citizen.is_susceptible()) continue;
                     const uint32_t slot = building.id.type == ESIM_BLDG_HOUSEHOLD ? 0u : next_work_slot(citizen_id);
-                    const double sample = rng.building_trial(citizen_id, current_time_step, slot);
+                    const double sample = rng_mode == 0 ? rng.building_trial(citizen_id, current_time_step, slot)
+                                                        : thread_rngs[(size_t)omp_get_thread_num()].uniform();
                     if (citizen.expose(exposure_count, disease_model, mask_status, sample))
                         exposure_statistics[area_index].push_back(building_id);
                 }
@@ -481,11 +534,16 @@ struct Oracle {
         for (auto& route : exposures.public_transport_pre_generated) {
             std::vector<Rider>& citizens = route.second;
             // citizens.shuffle(&mut self.rng)
-            std::vector<std::pair<std::pair<uint32_t, uint32_t>, Rider>> keyed;
-            keyed.reserve(citizens.size());
-            for (const Rider& r : citizens) keyed.push_back({{rng.pt_shuffle_key(r.citizen, current_time_step), r.citizen}, r});
-            std::sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-            for (size_t i = 0; i < keyed.size(); ++i) citizens[i] = keyed[i].second;
+            if (rng_mode == 0) {
+                std::vector<std::pair<std::pair<uint32_t, uint32_t>, Rider>> keyed;
+                keyed.reserve(citizens.size());
+                for (const Rider& r : citizens) keyed.push_back({{rng.pt_shuffle_key(r.citizen, current_time_step), r.citizen}, r});
+                std::sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+                for (size_t i = 0; i < keyed.size(); ++i) citizens[i] = keyed[i].second;
+            } else {
+                // SliceRandom::shuffle (rand 0.8): for i in (1..len).rev() { swap(i, gen_index(rng, i + 1)) }
+                for (size_t i = citizens.size(); i-- > 1;) std::swap(citizens[i], citizens[seq_rng.gen_index(i + 1)]);
+            }
             std::vector<uint32_t> bus;  // PublicTransport::citizens
             size_t bus_exposure_count = 0;
             uint32_t bus_number = 0;
@@ -512,7 +570,7 @@ struct Oracle {
         for (uint32_t citizen_id : citizens) {
             const auto& ref = citizen_output_area_lookup[citizen_id];
             Citizen& citizen = output_areas[ref.first].citizens[ref.second];
-            const double sample = rng.pt_trial(citizen_id, current_time_step);
+            const double sample = rng_mode == 0 ? rng.pt_trial(citizen_id, current_time_step) : seq_rng.uniform();
             if (citizen.is_susceptible() & citizen.expose(exposure_count, disease_model, interventions.mask_status, sample)) {
                 if (!add_exposure_pt()) error = "Cannot expose citizen as no citizens are susceptible!";
                 if (eligible_some && citizens_eligible_for_vaccine[citizen_id]) {
@@ -542,11 +600,24 @@ struct Oracle {
             std::vector<uint32_t> chosen;
             std::vector<uint8_t>& member = citizens_eligible_for_vaccine;
             std::unordered_map<uint32_t, bool> taken;
-            for (uint32_t draw = 0; chosen.size() < amount; ++draw) {
-                const uint32_t c = rng.vax_candidate(draw, current_time_step, n_citizens);
-                if (!member[c] || taken.count(c)) continue;
-                taken[c] = true;
-                chosen.push_back(c);
+            if (rng_mode == 0) {
+                for (uint32_t draw = 0; chosen.size() < amount; ++draw) {
+                    const uint32_t c = rng.vax_candidate(draw, current_time_step, n_citizens);
+                    if (!member[c] || taken.count(c)) continue;
+                    taken[c] = true;
+                    chosen.push_back(c);
+                }
+            } else {
+                // IteratorRandom::choose_multiple (rand 0.8): fill the reservoir with the first `amount` items, then item
+                // number amount + i replaces slot gen_index(rng, i + 1 + amount) if that is inside the reservoir
+                size_t seen = 0;
+                for (uint32_t c = 0; c < n_citizens; ++c) {
+                    if (!member[c]) continue;
+                    if (chosen.size() < amount) { chosen.push_back(c); continue; }
+                    const size_t k = seq_rng.gen_index(seen + 1 + amount);
+                    if (k < amount) chosen[k] = c;
+                    ++seen;
+                }
             }
             for (uint32_t citizen_id : chosen) {
                 const auto& ref = citizen_output_area_lookup[citizen_id];
@@ -678,6 +749,13 @@ int oracle_create(const EsimConfig* cfg, const EsimPopulationSoA* pop, Oracle** 
 }
 
 void oracle_destroy(Oracle* o) { delete o; }
+
+// 0 = counter-based stream (bit-exact partner of the CUDA kernels), 1 = sequential rand-0.8-style consumption
+int oracle_set_rng_mode(Oracle* o, int mode) {
+    if (!o || mode < 0 || mode > 1) return ESIM_ERR_INVALID_ARGUMENT;
+    o->set_rng_mode(mode);
+    return ESIM_OK;
+}
 
 int oracle_step(Oracle* o, EsimStepStats* out) {
     if (!o) return ESIM_ERR_INVALID_ARGUMENT;

@@ -39,6 +39,7 @@ def lib() -> C.CDLL:
         L.oracle_create.argtypes = [C.POINTER(_abi.EsimConfig), C.POINTER(_abi.EsimPopulationSoA), C.POINTER(vp)]
         L.oracle_destroy.argtypes = [vp]
         L.oracle_destroy.restype = None
+        L.oracle_set_rng_mode.argtypes = [vp, C.c_int]
         L.oracle_step.argtypes = [vp, C.POINTER(_abi.EsimStepStats)]
         L.oracle_run.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
         L.oracle_read_stats.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(_abi.EsimStepStats)]
@@ -104,7 +105,11 @@ def default_config(**overrides) -> _abi.EsimConfig:
 
 
 class Oracle:
-    def __init__(self, pop, cfg: _abi.EsimConfig | None = None, **overrides):
+    """rng_mode 0 = the counter-based stream shared with the CUDA kernels (bit-exact partner); 1 = a sequential generator
+    consumed the way the reference consumes rand 0.8 (thread_rng per worker, Fisher-Yates shuffle, reservoir
+    choose_multiple): equal to mode 0 only in distribution."""
+
+    def __init__(self, pop, cfg: _abi.EsimConfig | None = None, rng_mode: int = 0, **overrides):
         self._L = lib()
         self.cfg = cfg if cfg is not None else default_config(**overrides)
         self.pop = pop
@@ -113,6 +118,10 @@ class Oracle:
         rc = self._L.oracle_create(C.byref(self.cfg), C.byref(soa), C.byref(self._h))
         if rc < 0:
             raise _abi.SimError(rc, "oracle_create")
+        if rng_mode:
+            rc = self._L.oracle_set_rng_mode(self._h, rng_mode)
+            if rc < 0:
+                raise _abi.SimError(rc, "oracle_set_rng_mode")
 
     def close(self):
         if self._h:

@@ -130,7 +130,7 @@ struct EsimSim {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevView v{};
-    DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt0, cnt1, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
+    DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt0, cnt1, cnt2, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
         rec_bus, rec_businf;
     DevBuf<unsigned long long> thr;
     DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
@@ -141,6 +141,7 @@ struct EsimSim {
     DevBuf<unsigned int> barrier;       // grid barrier of the persistent kernel
     DevBuf<unsigned long long> pk_prof; // ESIM_TRACE: cycles per phase
     bool use_persistent = false;
+    bool fused = false;                 // single shard: one-pass step (k_step + k_tail_fused), three count buffers
     uint32_t world = 1, rank = 0, n_shared_bldgs = 0, n_shared_rooms = 0;
     void* comm = nullptr;               // ncclComm_t
     DevBuf<Ctrl> ctrl;
@@ -190,7 +191,7 @@ struct EsimSim {
         for (void* m : peer_mappings) cudaIpcCloseMemHandle(m);
         exch.release(); vax_cand.release(); barrier.release(); pk_prof.release(); peer_mail.release(); peer_view.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt0.release(); cnt1.release(); tally_partial.release();
+        cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt0.release(); cnt1.release(); cnt2.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
         if (stream) cudaStreamSynchronize(stream);
@@ -281,6 +282,12 @@ void allreduce_tail(EsimSim* s) {
 void enqueue_step(EsimSim* s, uint32_t parity, bool with_pt = true, bool next_has_pt = true) {
     DevView v = s->v;
     v.next_has_pt = next_has_pt ? 1u : 0u;
+    if (s->fused) {
+        launch_step_fused(v, s->stream);
+        if (with_pt) launch_pt(v, s->stream);
+        launch_tail_fused(v, s->stream);
+        return;
+    }
     launch_update(v, s->stream);
     const bool nccl = s->world > 1 && !s->v.p2p;
     if (nccl && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
@@ -534,6 +541,8 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
 
         const bool sharded_pop = p->n_shards > 1;
         s->cnt0.alloc((size_t)B + R + 4, sharded_pop); s->cnt1.alloc((size_t)B + R + 4, sharded_pop);
+        s->fused = p->n_shards <= 1 && !(s->cfg.flags & (ESIM_CFG_UNFUSED | ESIM_CFG_PERSISTENT)) && !getenv("ESIM_UNFUSED");
+        if (s->fused) s->cnt2.alloc((size_t)B + R + 4);
         if (sharded_pop) { s->peer_mail.alloc(MAIL_WORDS, true); CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st)); }
         s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
         s->pt_buscnt.alloc(std::max<uint32_t>(n_riders, 1));
@@ -542,7 +551,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         const uint32_t n_update_blocks = update_blocks(n_pad);
         const int pk_grid = persistent_grid();
         s->use_persistent = pk_grid > 0 && p->n_shards <= 1 && (s->cfg.flags & ESIM_CFG_PERSISTENT) && !(s->cfg.flags & ESIM_CFG_NO_GRAPH);
-        s->tally_partial.alloc((size_t)std::max<uint32_t>(n_update_blocks, (uint32_t)std::max(pk_grid, 1)) * 8);
+        s->tally_partial.alloc((size_t)std::max<uint32_t>(std::max(n_update_blocks, step_blocks(n_pad)), (uint32_t)std::max(pk_grid, 1)) * 8);
         s->barrier.alloc(4);
         if (getenv("ESIM_TRACE")) { s->pk_prof.alloc(8); CK(cudaMemsetAsync(s->pk_prof.p, 0, s->pk_prof.bytes(), s->stream)); }
         s->world = p->n_shards > 1 ? p->n_shards : 1;
@@ -555,6 +564,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         CK(cudaMemsetAsync(s->cnt0.p, 0, s->cnt0.bytes(), st));
         CK(cudaMemsetAsync(s->tally_partial.p, 0, s->tally_partial.bytes(), st));
         CK(cudaMemsetAsync(s->cnt1.p, 0, s->cnt1.bytes(), st));
+        if (s->fused) CK(cudaMemsetAsync(s->cnt2.p, 0, s->cnt2.bytes(), st));
         if (rec) {
             CK(cudaMemsetAsync(s->rec_bus.p, 0xFF, s->rec_bus.bytes(), st));
             CK(cudaMemsetAsync(s->rec_businf.p, 0, s->rec_businf.bytes(), st));
@@ -577,7 +587,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.n_routes = n_routes; v.n_riders = n_riders; v.record_buses = rec ? 1u : 0u;
         v.next_has_pt = 1;   // every launch sequence has a public-transport kernel unless a specialised graph says otherwise
         v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
-        v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt0.p; v.cnt[1] = s->cnt1.p; v.thr = s->thr.p;
+        v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt0.p; v.cnt[1] = s->cnt1.p; v.cnt[2] = s->cnt2.p; v.fused = s->fused ? 1u : 0u; v.thr = s->thr.p;
         v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
         v.pt_buscnt = s->pt_buscnt.p; v.rec_bus = s->rec_bus.p; v.rec_businf = s->rec_businf.p;
         v.world = s->world; v.exch = s->exch.p; v.vax_cand = s->vax_cand.p;
@@ -593,8 +603,10 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.mp.n_global_citizens = n_global; v.mp.shard_lo = shard_lo;
 
         s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->gid.bytes() +
-                          s->room_parent.bytes() + s->cnt0.bytes() * 2 + s->route_off.bytes() + s->riders.bytes() * 4 +
+                          s->room_parent.bytes() + s->cnt0.bytes() * (s->fused ? 3 : 2) + s->route_off.bytes() + s->riders.bytes() * 4 +
                           s->rec_bus.bytes() * 2 + s->stats.bytes();
+        // fused pipeline: count step 1 and lay out the first schedule (k_update + k_boot_fused), once
+        if (s->fused) { launch_boot_fused(v, st); CK(cudaGetLastError()); }
         if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH) && s->world == 1) capture_graphs(s);  // sharded: captured by esim_comm_init
         tr.mark("graph capture", st);
         CK(cudaStreamSynchronize(st));
@@ -618,15 +630,16 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
             const DevView& v = s->v;
             if (s->l2_scratch.p) CK(cudaMemsetAsync(s->l2_scratch.p, (int)(s->steps_done & 0xFF), s->l2_scratch.bytes(), s->stream));
             CK(cudaEventRecord(s->ev[0], s->stream));
-            launch_update(v, s->stream);
+            if (!s->fused) launch_update(v, s->stream);
             if (s->world > 1 && !v.p2p && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
             CK(cudaEventRecord(s->ev[1], s->stream));
-            launch_expose(v, s->stream);
+            if (s->fused) launch_step_fused(v, s->stream); else launch_expose(v, s->stream);
             CK(cudaEventRecord(s->ev[2], s->stream));
-            launch_pt(v, s->stream);
+            // the host has just read the control block: it knows whether anybody rides in this step
+            if (s->h_ctrl->pt_mode != ESIM_PT_NONE) launch_pt(v, s->stream);
             CK(cudaEventRecord(s->ev[3], s->stream));
             if (s->world > 1 && !v.p2p) { launch_vax_prepare(v, s->stream); allreduce_tail(s); }
-            launch_tail(v, s->stream);
+            if (s->fused) launch_tail_fused(v, s->stream); else launch_tail(v, s->stream);
             CK(cudaEventRecord(s->ev[4], s->stream));
         } else if (s->exec1[parity]) {
             CK(cudaGraphLaunch(s->exec1[parity], s->stream));
@@ -788,7 +801,8 @@ int esim_read_state(EsimSim* s, EsimStateView* view) {
             CK(cudaStreamSynchronize(s->stream));
             a.at_work = last.at_work; a.pt_mode = last.pt_mode;
         }
-        a.vax_some = c.vax_some; a.vax_start_step = c.vax_start_step; a.vax_all_pending = c.vax_all_pending;
+        // fused pipeline: the state machine is one step ahead; the eligible set exists once the tail has taken the snapshot
+        a.vax_some = c.vax_some && !(s->fused && c.vax_event); a.vax_start_step = c.vax_start_step; a.vax_all_pending = c.vax_all_pending;
         a.exposed_time = s->cfg.exposed_time; a.infected_time = s->cfg.infected_time;
         a.cstate = s->cstate.p; a.home_cell = s->home_cell.p; a.work_cell = s->work_cell.p; a.room_parent = s->room_parent.p;
         const size_t n = s->v.n;
@@ -816,7 +830,7 @@ int esim_read_state(EsimSim* s, EsimStateView* view) {
 int esim_read_building_counts(EsimSim* s, uint32_t* bldg, uint32_t* room) {
     return guarded(s, [&]() -> int {
         require_ready(s);
-        const uint32_t* cnt = s->v.cnt[s->steps_done & 1u];  // step t accumulates into cnt[t & 1]
+        const uint32_t* cnt = s->v.cnt[cnt_slot(s->v.fused, s->steps_done)];  // step t accumulates into cnt[t & 1] (fused: t % 3)
         if (bldg) CK(cudaMemcpyAsync(bldg, cnt, (size_t)s->v.n_bldg * 4, cudaMemcpyDeviceToHost, s->stream));
         if (room && s->v.n_rooms)
             CK(cudaMemcpyAsync(room, cnt + s->v.n_bldg, (size_t)s->v.n_rooms * 4, cudaMemcpyDeviceToHost, s->stream));

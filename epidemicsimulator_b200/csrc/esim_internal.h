@@ -42,6 +42,9 @@ constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 
 constexpr uint32_t MAX_STEPS      = CS_EXPOSURE - EXPOSURE_BIAS - 1;
 constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer, see k_vax_prepare
 
+// index of the count buffer that holds the infected occupants of step t
+__host__ __device__ inline uint32_t cnt_slot(uint32_t fused, uint32_t t) { return fused ? t % 3u : t & 1u; }
+
 // ---- peer-to-peer exchange of a sharded run (one process per GPU, NVLink peer mappings) --------------------------------
 // Every shard owns a mailbox in its own HBM that its peers write into:
 //   flag_a[r]  time step for which peer r has finished pushing its infected counts into this shard's count buffer
@@ -78,7 +81,13 @@ struct Ctrl {
     uint32_t abort_graph;    // the schedule left the assumptions of the specialised graph being replayed: the rest of it is a no-op
     uint32_t blocks_done;    // last-block-done counter of k_update in peer-to-peer mode
     uint32_t eager_expose;   // more than a quarter of the citizens are susceptible: k_expose loads cell ids eagerly
-    uint32_t pad[6];
+    uint32_t mask_cur;       // MaskStatus the exposures of step t are evaluated with (= mask_kind except in the fused pipeline,
+                             // whose intervention state machine runs one step ahead)
+    // fused pipeline only (see k_step): the schedule of step t + 1 and the pending Vaccination event
+    uint32_t next_at_work, next_pt_mode;
+    uint32_t vax_event;      // update_status raised the Vaccination event for step t: the tail of step t takes the snapshot
+    uint32_t vax_all_done;   // the whole eligible set has been vaccinated once: choosing all of it again changes nothing
+    uint32_t pad[1];
 };
 
 struct ModelParams {
@@ -101,8 +110,10 @@ struct DevView {
     const uint32_t* work_cell;   // [n_pad] building id, or n_bldg + room id for school members
     const uint32_t* global_id;   // [n_pad]
     const uint32_t* room_parent; // [n_rooms] school building of a room
-    uint32_t* cnt[2];      // [n_cells] x 2: infected occupants present per building / room.  Step t accumulates into
-                           // cnt[t & 1] while k_update zeroes cnt[(t + 1) & 1] for the next step.
+    uint32_t* cnt[3];      // [n_cells] x 2 (x 3 fused): infected occupants present per building / room.  Step t accumulates into
+                           // cnt[t & 1] while k_update zeroes cnt[(t + 1) & 1] for the next step.  Fused pipeline: k_step of
+                           // step t reads cnt[t % 3], accumulates step t + 1 into cnt[(t + 1) % 3] and zeroes cnt[(t + 2) % 3].
+    uint32_t fused;        // 1 = fused pipeline (three count buffers)
     const unsigned long long* thr;  // [2][256] integer trial thresholds
     // public transport
     const uint32_t* route_off;   // [n_routes + 1]
@@ -132,6 +143,11 @@ void launch_expose(const DevView& v, cudaStream_t s);
 void launch_pt(const DevView& v, cudaStream_t s);
 void launch_tail(const DevView& v, cudaStream_t s);
 void launch_vax_prepare(const DevView& v, cudaStream_t s);  // sharded runs only
+// fused pipeline (single shard): k_step = apply_exposures of step t + generate_exposures of step t + 1 in one pass
+void launch_step_fused(const DevView& v, cudaStream_t s);
+void launch_tail_fused(const DevView& v, cudaStream_t s);
+void launch_boot_fused(const DevView& v, cudaStream_t s);   // after import: k_update of step 1 + the first schedule
+uint32_t step_blocks(uint32_t n_pad);
 int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as int
 int  sm_count();
 void set_pdl(bool on);   // programmatic dependent launch of the step kernels (default on)

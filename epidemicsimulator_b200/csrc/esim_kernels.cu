@@ -132,8 +132,8 @@ __device__ __forceinline__ bool update_phase(const DevView& v, const Ctrl* __res
     const uint32_t e_lo = t + EXPOSURE_BIAS - v.mp.exposed_time;          // first exposure code that is still Exposed
     const uint32_t i_lo = e_lo - 1u - v.mp.infected_time;                 // first exposure code that is still Infected
     const uint32_t* __restrict__ pos = at_work ? v.work_cell : v.home_cell;
-    uint32_t* __restrict__ cnt = v.cnt[t & 1u];
-    uint4* __restrict__ cnt_next = reinterpret_cast<uint4*>(v.cnt[(t + 1u) & 1u]);
+    uint32_t* __restrict__ cnt = v.cnt[cnt_slot(v.fused, t)];
+    uint4* __restrict__ cnt_next = reinterpret_cast<uint4*>(v.cnt[cnt_slot(v.fused, t + 1u)]);
 
     for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_next[z] = make_uint4(0u, 0u, 0u, 0u);
 
@@ -255,9 +255,8 @@ __device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long 
 // CG: read the counts with ld.global.cg (needed inside the persistent kernel, where another SM wrote them during the same
 // launch); the graph kernels use the L1-cached read-only path: neighbours in a quad share their household.
 template <bool AT_WORK, bool CG>
-__device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, const uint4 w4,
+__device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, uint32_t (&w)[4],
                                                 const uint4 h4, const uint4 k4, uint32_t t, uint32_t mask_everywhere) {
-    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
     const uint32_t hc[4] = {h4.x, h4.y, h4.z, h4.w};
     const uint32_t wc[4] = {k4.x, k4.y, k4.z, k4.w};
     const uint32_t n_bldg = v.n_bldg;
@@ -294,7 +293,8 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
         if (thr_h == 0 && k_w == 0) continue;
         const uint32_t i = (q << 2) + (uint32_t)k;
         if (run_trials(thr_h, thr_w, k_w, __ldg(&v.global_id[i]), t, v.mp.seed_lo, v.mp.seed_hi)) {
-            v.cstate[i] = w[k] | (t + EXPOSURE_BIAS);  // DiseaseStatus::Exposed(0) (citizen.rs:244)
+            w[k] |= t + EXPOSURE_BIAS;                 // DiseaseStatus::Exposed(0) (citizen.rs:244)
+            v.cstate[i] = w[k];
             ++n_exposed;
         }
     }
@@ -315,8 +315,8 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
     const uint4* __restrict__ hc4 = reinterpret_cast<const uint4*>(v.home_cell);
     const uint4* __restrict__ wc4 = reinterpret_cast<const uint4*>(v.work_cell);
     const uint32_t t = c->t;
-    const uint32_t mask_everywhere = c->mask_kind == ESIM_MASK_EVERYWHERE;
-    const uint32_t* __restrict__ cnt = v.cnt[t & 1u];
+    const uint32_t mask_everywhere = c->mask_cur == ESIM_MASK_EVERYWHERE;
+    const uint32_t* __restrict__ cnt = v.cnt[cnt_slot(v.fused, t)];
     const uint4 pad4 = make_uint4(CS_PADDING, CS_PADDING, CS_PADDING, CS_PADDING);
     uint32_t n_exposed = 0;
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
@@ -334,8 +334,8 @@ __device__ __forceinline__ uint32_t expose_stream(const DevView& v, const Ctrl* 
             if (sa) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
             if (sb) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
         }
-        if (sa) n_exposed += expose_quad<AT_WORK, CG>(v, cnt, q0, wa, ha, ka, t, mask_everywhere);
-        if (sb) n_exposed += expose_quad<AT_WORK, CG>(v, cnt, q1, wb, hb, kb, t, mask_everywhere);
+        if (sa) { uint32_t w[4] = {wa.x, wa.y, wa.z, wa.w}; n_exposed += expose_quad<AT_WORK, CG>(v, cnt, q0, w, ha, ka, t, mask_everywhere); }
+        if (sb) { uint32_t w[4] = {wb.x, wb.y, wb.z, wb.w}; n_exposed += expose_quad<AT_WORK, CG>(v, cnt, q1, w, hb, kb, t, mask_everywhere); }
     }
     return n_exposed;
 }
@@ -348,6 +348,115 @@ __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
     const uint32_t n_exposed = eager ? (at_work ? expose_stream<true, true, false>(v, c) : expose_stream<true, false, false>(v, c))
                                      : (at_work ? expose_stream<false, true, false>(v, c) : expose_stream<false, false, false>(v, c));
+    const uint32_t s = warp_sum(n_exposed);
+    if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_step (fused pipeline, single shard): ONE pass over the citizens per time step.  For every quad of citizens it runs
+// apply_exposures of step t (the body of k_expose) and then, on the updated state words still in registers,
+// generate_exposures of step t + 1 (the body of k_update): class tally and infected occupants of step t + 1.  The state word
+// of a citizen is read once per step instead of twice and a step is two launches (k_step, k_tail_fused) instead of three.
+// What step t + 1's counts cannot know yet - public-transport exposures and vaccinations of step t - is corrected by the
+// tail (see tail_phase<.., true>); the schedule of step t + 1 is known because update_status only needs the infected share,
+// which the previous tail already had.
+constexpr int STEP_THREADS = 256;
+
+template <bool EAGER, bool AT_WORK>
+__device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt) {
+    const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_quads = v.n_pad >> 2;
+    const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
+    const uint4* __restrict__ hc4 = reinterpret_cast<const uint4*>(v.home_cell);
+    const uint4* __restrict__ wc4 = reinterpret_cast<const uint4*>(v.work_cell);
+    const uint32_t t = c->t, t1 = t + 1u;
+    const uint32_t mask_everywhere = c->mask_cur == ESIM_MASK_EVERYWHERE;
+    const uint32_t* __restrict__ cnt = v.cnt[cnt_slot(1u, t)];
+    uint32_t* __restrict__ cnt_next = v.cnt[cnt_slot(1u, t1)];
+    uint4* __restrict__ cnt_zero = reinterpret_cast<uint4*>(v.cnt[cnt_slot(1u, t1 + 1u)]);
+    // step t + 1: riders only count on their bus (simulator.rs:181-198); thresholds of the order-preserving state code
+    const uint32_t rider_mask = c->next_pt_mode != ESIM_PT_NONE ? CS_USES_PT : 0u;
+    const uint32_t e_lo = t1 + EXPOSURE_BIAS - v.mp.exposed_time;
+    const uint32_t i_lo = e_lo - 1u - v.mp.infected_time;
+    const uint32_t* __restrict__ pos_next = c->next_at_work ? v.work_cell : v.home_cell;
+    const uint4 pad4 = make_uint4(CS_PADDING, CS_PADDING, CS_PADDING, CS_PADDING);
+
+    for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
+
+    uint32_t n_exposed = 0;
+    uint32_t c_exp = 0, c_inf = 0, c_ei = 0, c_vax = 0;   // #(code != 0), #(code >= i_lo), #(code >= e_lo), #(code >= 0x8000)
+    for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
+        const uint32_t q1 = q0 + T;
+        const bool have1 = q1 < n_quads;
+        const uint4 wa = cs4[q0];
+        const uint4 wb = have1 ? cs4[q1] : pad4;
+        uint4 ha, ka, hb, kb;
+        if (EAGER) {
+            ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0);
+            if (have1) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); } else { hb = kb = make_uint4(0u, 0u, 0u, 0u); }
+        }
+        uint32_t w[2][4] = {{wa.x, wa.y, wa.z, wa.w}, {wb.x, wb.y, wb.z, wb.w}};
+        const bool sa = any_susceptible(wa), sb = any_susceptible(wb);
+        if (!EAGER) {
+            if (sa) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
+            if (sb) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
+        }
+        // apply_exposures of step t
+        if (sa) n_exposed += expose_quad<AT_WORK, false>(v, cnt, q0, w[0], ha, ka, t, mask_everywhere);
+        if (sb) n_exposed += expose_quad<AT_WORK, false>(v, cnt, q1, w[1], hb, kb, t, mask_everywhere);
+        // generate_exposures of step t + 1 on the updated words
+        uint32_t any_present_infected = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !have1) break;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t code = w[u][k] & CS_LOW16;
+                c_exp += code != 0u;
+                c_inf += code >= i_lo;
+                c_ei += code >= e_lo;
+                c_vax += code >> 15;
+                any_present_infected |= (code >= i_lo) & (code < e_lo) & ((w[u][k] & rider_mask) == 0u);
+            }
+        }
+        if (any_present_infected) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !have1) break;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t code = w[u][k] & CS_LOW16;
+                    if (code >= i_lo && code < e_lo && (w[u][k] & rider_mask) == 0u) {
+                        const uint32_t cell = __ldg(&pos_next[((u ? q1 : q0) << 2) + (uint32_t)k]);
+                        atomicAdd(&cnt_next[cell], 1u);
+                        if (cell >= v.n_bldg) atomicAdd(&cnt_next[__ldg(&v.room_parent[cell - v.n_bldg])], 1u);
+                    }
+                }
+            }
+        }
+    }
+    // block reduction of the class counts -> tally_partial[block]
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t r4[4] = {warp_sum(c_exp), warp_sum(c_inf), warp_sum(c_ei), warp_sum(c_vax)};
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (r4[k]) atomicAdd(&s_cnt[k], r4[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
+    return n_exposed;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) {
+    pdl_prologue();
+    __shared__ uint32_t s_cnt[4];
+    const Ctrl* __restrict__ c = v.ctrl;
+    if (c->finished | c->abort_graph) return;
+    const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
+    const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true>(v, c, s_cnt) : step_stream<true, false>(v, c, s_cnt))
+                                     : (at_work ? step_stream<false, true>(v, c, s_cnt) : step_stream<false, false>(v, c, s_cnt));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
 }
@@ -549,12 +658,34 @@ struct TailSmem {
     EsimStepStats stats;
     uint32_t scan[TAIL_THREADS / 32];
     uint32_t tally[8];
+    uint32_t fix[8];             // fused: citizens vaccinated now, by the class k_step counted them in for the next step
     uint32_t k, accepted, batch_total;
 };
 
+// Fused pipeline: k_step has already counted citizen `local` for step t + 1 (class tally, infected occupants of its building)
+// when the tail of step t vaccinates it (simulator.rs:549-552): take it out of both again.
+__device__ __forceinline__ void vaccinate_counted(const DevView& v, TailSmem& sm, uint32_t local) {
+    const uint32_t old = atomicOr(&v.cstate[local], CS_VACCINATED);
+    if (old & CS_VACCINATED) return;    // already Vaccinated (chosen citizens stay in the eligible set): nothing changes
+    const uint32_t t1 = sm.c.t + 1u;
+    const int x = status_at(old, t1, v.mp.exposed_time, v.mp.infected_time);
+    atomicAdd(&sm.fix[x], 1u);
+    if (x == ST_I && !((old & CS_USES_PT) && sm.c.next_pt_mode != ESIM_PT_NONE)) {
+        uint32_t* cnt_next = v.cnt[cnt_slot(1u, t1)];
+        const uint32_t cell = sm.c.next_at_work ? v.work_cell[local] : v.home_cell[local];
+        atomicSub(&cnt_next[cell], 1u);
+        if (cell >= v.n_bldg) atomicSub(&cnt_next[v.room_parent[cell - v.n_bldg]], 1u);
+    }
+}
+
 // `ht` = 3 * HT_SIZE words of shared memory.  Must be called by all TAIL_THREADS threads of one block, after every
 // other writer of the control block and of the citizens' state words of this step has finished.
-template <int NT>
+// FUSED: the tail of step t in the fused pipeline.  k_step has left the (speculative) class counts of step t + 1 in
+// tally_partial; Ctrl::tally holds the final counts of step t, the intervention state machine is the one after
+// apply_interventions of step t, and at_work / pt_mode / mask_cur describe step t.  The tail records the statistics of step t,
+// draws the vaccination picks of step t, corrects the counts of step t + 1 for them, runs update_status of step t + 1 on the
+// corrected counts (it needs nothing else, statistics.rs:252-254) and derives the schedule of step t + 2 from it.
+template <int NT, bool FUSED = false>
 __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailSmem& sm, uint32_t n_partial_blocks) {
     constexpr int PER = VAX_BATCH / NT;   // draws per thread and round
     uint32_t* acc_keys = ht;                  // citizens chosen in this step
@@ -563,9 +694,9 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     // one coalesced read of the control block (L2: other blocks updated it with atomics)
     if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + tid);
-    if (tid < 8) sm.tally[tid] = 0;
+    if (tid < 8) { sm.tally[tid] = 0; sm.fix[tid] = 0; }
     __syncthreads();
-    const bool sharded = v.world > 1;
+    const bool sharded = !FUSED && v.world > 1;
     if (sharded && v.p2p) {
         // sum the tail vectors of all shards (fixed order) into the exchange buffer the code below reads
         wait_for_peers(v, MAIL_FLAG_B, sm.c.t);
@@ -603,22 +734,29 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         c->vax_all_pending = 0;  // consumed by this step's k_update
         // statistics.rs:275-287: every successful exposure moves one citizen from susceptible to exposed
         const uint32_t new_exp = c->new_exp_bldg + c->new_exp_pt;
+        const uint32_t* now = FUSED ? c->tally : sm.tally;   // S,E,I,R,V of step t before the exposure adjustment
         EsimStepStats s;
         s.time_step = t;
-        s.susceptible = sm.tally[0] - new_exp;
-        s.exposed = sm.tally[1] + new_exp;
-        s.infected = sm.tally[2];
-        s.recovered = sm.tally[3];
-        s.vaccinated = sm.tally[4];
+        s.susceptible = now[0] - new_exp;
+        s.exposed = now[1] + new_exp;
+        s.infected = now[2];
+        s.recovered = now[3];
+        s.vaccinated = now[4];
         s.exposures_building = c->new_exp_bldg;
         s.exposures_pt = c->new_exp_pt;
         const uint32_t total = s.susceptible + s.exposed + s.infected + s.recovered + s.vaccinated;
         const double p = (double)s.infected / (double)total;  // StatisticEntry::infected_percentage (statistics.rs:252-254)
         // citizens exposed on public transport leave the eligible set if it exists (simulator.rs:447-449)
-        if (c->vax_some) c->n_elig -= c->new_exp_pt;
-        if (update_interventions(c, v.mp, p)) {
-            c->vax_start_step = t;
-            c->n_elig = s.susceptible;  // everybody Susceptible right now (simulator.rs:487-513)
+        if (FUSED) {
+            // update_status of step t ran in the previous tail; the snapshot of its Vaccination event is taken now
+            if (c->vax_some && !c->vax_event) c->n_elig -= c->new_exp_pt;
+            if (c->vax_event) { c->vax_start_step = t; c->n_elig = s.susceptible; c->vax_event = 0; }
+        } else {
+            if (c->vax_some) c->n_elig -= c->new_exp_pt;
+            if (update_interventions(c, v.mp, p)) {
+                c->vax_start_step = t;
+                c->n_elig = s.susceptible;  // everybody Susceptible right now (simulator.rs:487-513)
+            }
         }
         sm.stats = s;
         sm.k = c->vax_some ? min(v.mp.vaccination_rate, c->n_elig) : 0u;
@@ -674,6 +812,20 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
             if (tid == 0) {
                 if (sm.batch_total < K) sm.c.error = (uint32_t)(-ESIM_ERR_SIMULATION);  // more than VAX_SHARD_DRAWS draws needed
                 sm.accepted = min(K, sm.batch_total);
+            }
+        } else if (FUSED && (K == sm.c.n_elig || K > MAX_VAX_PER_STEP)) {
+            // the whole eligible set is chosen.  The set only shrinks and Vaccinated is final, so this changes something the
+            // first time only: one pass of this block over the citizens (rare: the programme started with <= rate candidates)
+            if (!sm.c.vax_all_done) {
+                for (uint32_t i = tid; i < v.n; i += NT) {
+                    const uint32_t w = __ldcg(&v.cstate[i]);
+                    if (!(w & CS_VACCINATED) && vax_eligible(w, vax_start)) vaccinate_counted(v, sm, i);
+                }
+            }
+            if (tid == 0) {
+                if (K != sm.c.n_elig) sm.c.error = (uint32_t)(-ESIM_ERR_INVALID_ARGUMENT);
+                sm.c.vax_all_done = 1;
+                sm.accepted = K;
             }
         } else if (K == sm.c.n_elig || K > MAX_VAX_PER_STEP) {
             // the whole eligible set is chosen: k_update of the next step marks it while it streams the citizens
@@ -737,7 +889,8 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                 for (int q = 0; q < PER; ++q) {
                     if (flag[q]) {
                         if (rank < K) {
-                            atomicOr(&v.cstate[cand[q] - v.mp.shard_lo], CS_VACCINATED);
+                            if (FUSED) vaccinate_counted(v, sm, cand[q] - v.mp.shard_lo);
+                            else atomicOr(&v.cstate[cand[q] - v.mp.shard_lo], CS_VACCINATED);
                             ht_insert(acc_keys, cand[q]);
                         }
                         ++rank;
@@ -767,18 +920,40 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         sm.stats = s;
         // StatisticEntry::disease_exists (statistics.rs:289-291)
         if (!(s.exposed != 0 || s.infected != 0 || s.susceptible != 0)) c->finished = 1;
-        // schedule of the next hour (citizen.rs:176-205): frozen while lockdown is enabled
         const uint32_t nt = t + 1;
-        if (!c->lockdown_some) {
-            const uint32_t h = nt % 24u;
-            if (h == 8u) c->pt_mode = ESIM_PT_HOME_TO_WORK;
-            else if (h == 9u) { c->at_work = 1; c->pt_mode = ESIM_PT_NONE; }
-            else if (h == 16u) c->pt_mode = ESIM_PT_WORK_TO_HOME;
-            else if (h == 17u) { c->at_work = 0; c->pt_mode = ESIM_PT_NONE; }
-            else c->pt_mode = ESIM_PT_NONE;
+        c->mask_cur = c->mask_kind;   // the exposures of the next step see the status computed by step t (simulator.rs:262-268)
+        if (FUSED) {
+            // final class counts of step t + 1: k_step's counts, the public-transport exposures of step t (counted Susceptible,
+            // now Exposed) and the citizens vaccinated just now
+            uint32_t n1[5] = {sm.tally[0] - c->new_exp_pt, sm.tally[1] + c->new_exp_pt, sm.tally[2], sm.tally[3], sm.tally[4]};
+            for (int k = 0; k < 5; ++k) { n1[k] -= sm.fix[k]; n1[4] += sm.fix[k]; }
+            for (int k = 0; k < 5; ++k) c->tally[k] = n1[k];
+            // apply_interventions of step t + 1 only looks at the infected share of these counts (simulator.rs:456-458)
+            const double p1 = (double)n1[2] / (double)(n1[0] + n1[1] + n1[2] + n1[3] + n1[4]);
+            c->vax_event = update_interventions(c, v.mp, p1) ? 1u : 0u;
+            // the schedule of step t + 1 becomes current, the one of step t + 2 follows from the new lockdown status
+            c->at_work = c->next_at_work; c->pt_mode = c->next_pt_mode;
+            if (!c->lockdown_some) {
+                const uint32_t h = (nt + 1u) % 24u;
+                if (h == 8u) c->next_pt_mode = ESIM_PT_HOME_TO_WORK;
+                else if (h == 9u) { c->next_at_work = 1; c->next_pt_mode = ESIM_PT_NONE; }
+                else if (h == 16u) c->next_pt_mode = ESIM_PT_WORK_TO_HOME;
+                else if (h == 17u) { c->next_at_work = 0; c->next_pt_mode = ESIM_PT_NONE; }
+                else c->next_pt_mode = ESIM_PT_NONE;
+            }
+        } else {
+            // schedule of the next hour (citizen.rs:176-205): frozen while lockdown is enabled
+            if (!c->lockdown_some) {
+                const uint32_t h = nt % 24u;
+                if (h == 8u) c->pt_mode = ESIM_PT_HOME_TO_WORK;
+                else if (h == 9u) { c->at_work = 1; c->pt_mode = ESIM_PT_NONE; }
+                else if (h == 16u) c->pt_mode = ESIM_PT_WORK_TO_HOME;
+                else if (h == 17u) { c->at_work = 0; c->pt_mode = ESIM_PT_NONE; }
+                else c->pt_mode = ESIM_PT_NONE;
+            }
+            c->tally[0] = c->tally[1] = c->tally[2] = c->tally[3] = c->tally[4] = 0;
         }
         c->t = nt;
-        c->tally[0] = c->tally[1] = c->tally[2] = c->tally[3] = c->tally[4] = 0;
         c->new_exp_bldg = 0; c->new_exp_pt = 0;
         c->vaccinated_now = sm.accepted;
         // a specialised day graph has no public-transport kernel in most slots: if the next hour needs one after all (lockdown
@@ -901,7 +1076,43 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
     __shared__ PtWarpSmem ws[PT_THREADS / 32];
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph || c->pt_mode == ESIM_PT_NONE) return;
-    pt_phase(v, &ws[threadIdx.x >> 5], c->t, c->mask_kind == ESIM_MASK_EVERYWHERE);
+    pt_phase(v, &ws[threadIdx.x >> 5], c->t, c->mask_cur == ESIM_MASK_EVERYWHERE);
+}
+
+// fused pipeline: v.n_update_blocks is the grid of k_step here (set by the launcher)
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail_fused(const DevView v) {
+    pdl_prologue();
+    extern __shared__ uint32_t dyn_smem[];
+    __shared__ TailSmem sm;
+    if (v.ctrl->finished | v.ctrl->abort_graph) return;
+    tail_phase<TAIL_THREADS, true>(v, dyn_smem, sm, v.n_update_blocks);
+}
+
+// fused pipeline, once after the import: k_update has counted step 1; this turns its partial sums into Ctrl::tally, runs
+// update_status of step 1 and lays out the schedule of steps 1 and 2 (everybody starts at home, citizen.rs:156-160)
+__global__ void __launch_bounds__(TAIL_THREADS) k_boot_fused(const DevView v) {
+    __shared__ uint32_t s_tally[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    if (tid < 8) s_tally[tid] = 0;
+    __syncthreads();
+    uint32_t part = 0;
+    for (uint32_t z = tid; z < v.n_update_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    part += __shfl_xor_sync(0xffffffffu, part, 16);
+    if (lane < 8 && part) atomicAdd(&s_tally[lane], part);
+    __syncthreads();
+    if (tid == 0) {
+        Ctrl* c = v.ctrl;
+        uint32_t cls[5];
+        classes_from_cumulative(s_tally, v.n_pad, v.n, cls);
+        for (int k = 0; k < 5; ++k) c->tally[k] = cls[k];
+        c->mask_cur = c->mask_kind;
+        const double p1 = (double)cls[2] / (double)(cls[0] + cls[1] + cls[2] + cls[3] + cls[4]);
+        c->vax_event = update_interventions(c, v.mp, p1) ? 1u : 0u;
+        c->at_work = 0; c->pt_mode = ESIM_PT_NONE;            // hour 1
+        c->next_at_work = 0; c->next_pt_mode = ESIM_PT_NONE;  // hour 2, with or without lockdown
+        c->eager_expose = (uint64_t)cls[0] * 4u > (uint64_t)v.n ? 1u : 0u;
+    }
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
@@ -978,7 +1189,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_persistent(const __grid_const
         PK_MARK(3);
         if (s_ctrl.pt_mode != ESIM_PT_NONE && v.n_routes) {
             grid_barrier(barrier_counter, generation);   // every building trial of the step precedes the bus trials
-            pk_pt_phase(&v, reinterpret_cast<PtWarpSmem*>(dyn_smem) + (threadIdx.x >> 5), s_ctrl.t, s_ctrl.mask_kind == ESIM_MASK_EVERYWHERE);
+            pk_pt_phase(&v, reinterpret_cast<PtWarpSmem*>(dyn_smem) + (threadIdx.x >> 5), s_ctrl.t, s_ctrl.mask_cur == ESIM_MASK_EVERYWHERE);
             PK_MARK(4);
         }
         grid_barrier(barrier_counter, generation);
@@ -1025,13 +1236,15 @@ int sm_count() {
 int configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vax_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tail_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     // One shared-memory carve-out for every step kernel: switching the L1 / shared split between consecutive kernels costs
     // microseconds, which is what a step is made of.  ESIM_CARVEOUT (percent) overrides the default for experiments.
     int carve = -1;
     if (const char* env = getenv("ESIM_CARVEOUT")) carve = atoi(env);
     if (carve >= 0) {
-        const void* all[] = {(const void*)k_update, (const void*)k_expose, (const void*)k_pt, (const void*)k_tail, (const void*)k_vax_prepare};
+        const void* all[] = {(const void*)k_update, (const void*)k_expose, (const void*)k_pt, (const void*)k_tail, (const void*)k_vax_prepare,
+                             (const void*)k_step, (const void*)k_tail_fused};
         for (const void* f : all)
             if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
@@ -1076,6 +1289,22 @@ void launch_pt(const DevView& v, cudaStream_t s) {
 }
 void launch_tail(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_tail, 1, TAIL_THREADS, HT_BYTES, s, v);
+}
+uint32_t step_blocks(uint32_t n_pad) {
+    // one resident wave: 3 blocks of 256 threads per SM, two quads per thread and iteration
+    return blocks_for(n_pad >> 2, STEP_THREADS, (uint32_t)sm_count() * 3u);
+}
+void launch_step_fused(const DevView& v, cudaStream_t s) {
+    launch_step_kernel(k_step, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+}
+void launch_tail_fused(const DevView& v, cudaStream_t s) {
+    DevView vv = v;
+    vv.n_update_blocks = step_blocks(v.n_pad);   // the partial sums come from k_step
+    launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);
+}
+void launch_boot_fused(const DevView& v, cudaStream_t s) {
+    launch_update(v, s);
+    k_boot_fused<<<1, TAIL_THREADS, 0, s>>>(v);
 }
 void launch_vax_prepare(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_vax_prepare, 1, TAIL_THREADS, VP_SMEM, s, v);

@@ -73,6 +73,8 @@ extern "C" {
 #define ESIM_CFG_NO_GRAPH     0x2u /* launch kernels directly instead of replaying the captured CUDA graph   */
 #define ESIM_CFG_PERSISTENT   0x8u /* experimental: esim_run launches one cooperative kernel with grid-wide barriers between the
                                       phases instead of replaying CUDA graphs (single shard; currently slower) */
+#define ESIM_CFG_UNFUSED      0x10u /* single shard: use the three-kernel step (k_update, k_expose, k_tail) instead of the fused
+                                       one-pass step (k_step, k_tail_fused); results are identical (parity tests run both)   */
 #define ESIM_CFG_FLUSH_L2     0x4u /* esim_step_timed overwrites a 256 MiB scratch buffer before every step, so
                                       that each timed step starts with a cold L2 (benchmark hygiene only)       */
 
@@ -181,7 +183,7 @@ typedef struct EsimTimings {
     double apply_exposures;    /* "Apply Exposures"    */
     double apply_interventions;/* "Apply Interventions"*/
     double total;
-    double k_update;           /* per-kernel split of the above */
+    double k_update;           /* per-kernel split of the above (fused step: k_update = 0, k_expose = k_step) */
     double k_expose;
     double k_pt;
     double k_tail;

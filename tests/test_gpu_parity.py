@@ -13,6 +13,17 @@ from oracle.oracle_py import Oracle, default_config
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["fused", "unfused"])
+def pipeline(request, monkeypatch):
+    """Every test runs on both single-shard pipelines: the fused one-pass step (k_step + k_tail_fused, the default) and the
+    three-kernel step (k_update, k_expose, k_tail) that the sharded and persistent paths are built from."""
+    if request.param == "unfused":
+        monkeypatch.setenv("ESIM_UNFUSED", "1")
+    else:
+        monkeypatch.delenv("ESIM_UNFUSED", raising=False)
+    return request.param
+
+
 def _sim(pop, **cfg):
     from epidemicsimulator_b200.simulator import Simulator
     c = default_config(**cfg)

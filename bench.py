@@ -126,17 +126,30 @@ def hbm_peak():
 
 
 def algorithmic_bytes(stats, n_citizens, n_cells):
-    """Per-step algorithmic bytes of the two streaming kernels for the layout in DESIGN.md section 3.
+    """Per-step algorithmic bytes of the streaming kernels for the layout in DESIGN.md section 3.
     k_update: 4 B state word per citizen + 8 B (position id + count update) per infected citizen + 4 B per cell (zeroing).
     k_expose: 4 B state word per citizen + 8 B (household + workplace ids) per susceptible citizen + 4 B per cell (every
-              infected count is needed from HBM once; citizens sharing a household / workplace share the fetch)."""
+              infected count is needed from HBM once; citizens sharing a household / workplace share the fetch).
+    k_step  : the fused pass = both of the above with the state word read once:
+              4 B per citizen + 8 B per susceptible + 8 B per infected + 8 B per cell (count gathers + zeroing)."""
     from epidemicsimulator_b200 import _abi
     f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
     s_before = stats[:, f["susceptible"]] + stats[:, f["exposures_building"]] + stats[:, f["exposures_pt"]]
     infected = stats[:, f["infected"]]
     upd = 4.0 * n_citizens + 8.0 * infected + 4.0 * n_cells
     exp = 4.0 * n_citizens + 8.0 * s_before + 4.0 * n_cells
-    return upd, exp
+    fused = 4.0 * n_citizens + 8.0 * s_before + 8.0 * infected + 8.0 * n_cells
+    return upd, exp, fused
+
+
+def traffic_from_profile(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json, written by scripts/ncu_summary.py traffic); None if no capture of that kernel is committed."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return float(json.loads(p.read_text())[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def cpu_baseline(pop, cfg_kwargs, seconds, min_steps=8):
@@ -247,8 +260,9 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
 
-    # ---- device-resident number: CUDA events per step, cold L2 ---------------------------------------------------
+    # ---- device-resident number: CUDA events around every step, cold L2 -------------------------------------------
     sim = make_sim(_abi.CFG_FLUSH_L2)
+    fused = sim.fused
     barrier()
     steps_run = 0
     for _ in range(args.steps):
@@ -257,10 +271,19 @@ def main():
         if not alive:
             break
     barrier()
-    tm = sim.timings()
     stats = sim.statistics()
     n_cells = pop.n_buildings + pop.n_rooms
-    dev_seconds = tm["total"]
+    dev_seconds = sim.timings()["total"]
+    sim.close()
+
+    # ---- the same steps again with an event between every two kernels: per-kernel durations for the roofline --------
+    sim = make_sim(_abi.CFG_FLUSH_L2 | _abi.CFG_TIME_KERNELS)
+    barrier()
+    for _ in range(steps_run):
+        if not sim.step(timed=True):
+            break
+    barrier()
+    tm = sim.timings()
     sim.close()
 
     # ---- back-to-back graph replay (warm L2, the way the job really runs) -----------------------------------------
@@ -294,11 +317,21 @@ def main():
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        upd_b, exp_b = algorithmic_bytes(stats, pop.n_citizens, n_cells)
-        k_exp_s, k_upd_s = tm["k_expose"], tm["k_update"]
-        dominant = "k_expose" if k_exp_s >= k_upd_s else "k_update"
-        dom_bytes = float(exp_b.sum() if dominant == "k_expose" else upd_b.sum())
-        dom_s = k_exp_s if dominant == "k_expose" else k_upd_s
+        upd_b, exp_b, fused_b = algorithmic_bytes(stats, pop.n_citizens, n_cells)
+        f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
+        pt_steps = int((stats[:, f["pt_mode"]] != 0).sum())
+        if fused:
+            # the slot in front of k_step is empty in the fused pipeline: its duration is what one CUDA event costs
+            kernel_seconds = {"k_step": tm["k_expose"], "k_pt": tm["k_pt"], "k_tail_fused": tm["k_tail"], "empty_event_interval": tm["k_update"]}
+            dominant, dom_bytes, dom_s = "k_step", float(fused_b.sum()), tm["k_expose"]
+            launches = 2 * steps_run + pt_steps
+        else:
+            kernel_seconds = {k: tm[k] for k in ("k_update", "k_expose", "k_pt", "k_tail")}
+            k_exp_s, k_upd_s = tm["k_expose"], tm["k_update"]
+            dominant = "k_expose" if k_exp_s >= k_upd_s else "k_update"
+            dom_bytes = float(exp_b.sum() if dominant == "k_expose" else upd_b.sum())
+            dom_s = k_exp_s if dominant == "k_expose" else k_upd_s
+            launches = 3 * steps_run + pt_steps
         achieved = dom_bytes / dom_s / 1e9 if dom_s > 0 else 0.0
         out = {
             "metric": METRIC, "value": n_total * steps_run / dev_seconds, "unit": UNIT, "n_gpus": world,
@@ -316,11 +349,14 @@ def main():
             "e2e": {"value": n_total * n_e2e / e2e_seconds, "unit": UNIT, "h2d_bytes_per_step": h2d / max(n_e2e, 1),
                     "d2h_bytes_per_step": d2h / max(n_e2e, 1), "seconds": e2e_seconds,
                     "what": "esim_create + esim_import_population(host SoA) + esim_run(%d) + esim_read_stats + esim_read_state" % args.steps},
-            "gpu_launches": 4 * steps_run,
-            "kernel_seconds": {k: tm[k] for k in ("k_update", "k_expose", "k_pt", "k_tail")},
+            "gpu_launches": launches,
+            "kernel_seconds": kernel_seconds,
+            "kernel_seconds_note": "second pass over the same steps with a CUDA event between every two kernels (each event "
+                                   "adds ~2.5 us and ends the programmatic overlap of consecutive kernels)",
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": dom_bytes / max(steps_run, 1)},
+                         "frac": achieved / peak, "traffic": traffic_from_profile(dominant), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_bytes / max(steps_run, 1),
+                         "avg_launch_us": dom_s / max(steps_run, 1) * 1e6},
             "clocks": clock_info,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -30,6 +30,7 @@ CFG_RECORD_BUSES = 0x1
 CFG_NO_GRAPH = 0x2
 CFG_FLUSH_L2 = 0x4
 CFG_UNFUSED = 0x10
+CFG_TIME_KERNELS = 0x20
 CFG_PERSISTENT = 0x8
 EXCH_COUNTS = 0
 EXCH_TAIL = 1

@@ -61,6 +61,7 @@ def cuda_lib() -> C.CDLL:
     lib.esim_run.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.esim_read_stats.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(_abi.EsimStepStats)]
     lib.esim_steps_done.argtypes = [vp]
+    lib.esim_is_fused.argtypes = [vp]
     lib.esim_read_state.argtypes = [vp, C.POINTER(_abi.EsimStateView)]
     lib.esim_read_building_counts.argtypes = [vp, _abi.u32p, _abi.u32p]
     lib.esim_read_buses.argtypes = [vp, _abi.u32p, _abi.u32p]

@@ -140,6 +140,7 @@ struct EsimSim {
     std::vector<void*> peer_mappings;   // cudaIpcOpenMemHandle results
     DevBuf<unsigned int> barrier;       // grid barrier of the persistent kernel
     DevBuf<unsigned long long> pk_prof; // ESIM_TRACE: cycles per phase
+    DevBuf<unsigned long long> ktrace_min, ktrace_max;   // ESIM_KTRACE: device-side timeline of the step kernels
     bool use_persistent = false;
     bool fused = false;                 // single shard: one-pass step (k_step + k_tail_fused), three count buffers
     uint32_t world = 1, rank = 0, n_shared_bldgs = 0, n_shared_rooms = 0;
@@ -195,6 +196,7 @@ struct EsimSim {
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
         if (stream) cudaStreamSynchronize(stream);
+        ktrace_min.release(); ktrace_max.release();
         if (mailbox_private) cudaFreeHost(mailbox); else g_mailboxes.give(mailbox);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -276,6 +278,13 @@ void allreduce_counts(EsimSim* s, uint32_t parity) {
 }
 void allreduce_tail(EsimSim* s) {
     NCCLCK(nccl_api()->AllReduce(s->exch.p, s->exch.p, EXCH_WORDS, NCCL_UINT32, NCCL_SUM, s->comm, s->stream));
+}
+
+// ESIM_CFG_FLUSH_L2: overwrite 2x the L2 with scratch, then read it back so that the lines left in the L2 are clean
+void flush_l2(EsimSim* s) {
+    if (!s->l2_scratch.p) return;
+    CK(cudaMemsetAsync(s->l2_scratch.p, (int)(s->steps_done & 0xFF), s->l2_scratch.bytes(), s->stream));
+    launch_flush_sweep(s->l2_scratch.p, s->l2_scratch.bytes(), s->exch.p + 7, s->stream);   // exch[7] is a spare word
 }
 
 // one time step whose number has the given parity; `with_pt` / `next_has_pt`: see the specialised day graphs below
@@ -440,7 +449,38 @@ int esim_create(const EsimConfig* cfg, EsimSim** out) {
     return ESIM_OK;
 }
 
-void esim_destroy(EsimSim* s) { delete s; }
+// ESIM_KTRACE=1: per kernel the mean time from block entry to the end of the dependency wait, the mean run time, and the mean
+// gap between the end of a kernel and the start of the next one, over the last <= KTRACE_STEPS steps
+static void print_ktrace(EsimSim* s) {
+    if (!s->ktrace_min.p || s->steps_done < 8) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    std::vector<unsigned long long> mn(s->ktrace_min.n), mx(s->ktrace_max.n);
+    cudaMemcpy(mn.data(), s->ktrace_min.p, s->ktrace_min.bytes(), cudaMemcpyDeviceToHost);
+    cudaMemcpy(mx.data(), s->ktrace_max.p, s->ktrace_max.bytes(), cudaMemcpyDeviceToHost);
+    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose", "pt", "tail"};
+    const uint32_t last = s->steps_done, first = last > KTRACE_STEPS - 2 ? last - (KTRACE_STEPS - 2) : 2;
+    double wait[KTRACE_KERNELS] = {}, run[KTRACE_KERNELS] = {}, gap[KTRACE_KERNELS] = {};
+    uint32_t cnt[KTRACE_KERNELS] = {}, gcnt[KTRACE_KERNELS] = {};
+    double span = 0; uint32_t nspan = 0;
+    unsigned long long prev_end = 0, prev_begin0 = 0;
+    for (uint32_t t = first; t <= last; ++t)
+        for (uint32_t k = 0; k < KTRACE_KERNELS; ++k) {
+            const uint32_t slot = (t % KTRACE_STEPS) * KTRACE_KERNELS + k;
+            const unsigned long long enter = mn[slot * 2], begin = mn[slot * 2 + 1], end = mx[slot];
+            if (begin == ~0ull || end == 0 || end < begin) continue;
+            wait[k] += (double)(begin - enter); run[k] += (double)(end - begin); cnt[k]++;
+            if (prev_end && begin >= prev_end) { gap[k] += (double)(begin - prev_end); gcnt[k]++; }
+            if (k == 0) { if (prev_begin0) { span += (double)(begin - prev_begin0); nspan++; } prev_begin0 = begin; }
+            prev_end = end;
+        }
+    fprintf(stderr, "[esim] kernel timeline over steps %u..%u (ns): step-to-step %.0f\n", first, last, nspan ? span / nspan : 0.0);
+    for (uint32_t k = 0; k < KTRACE_KERNELS; ++k)
+        if (cnt[k]) fprintf(stderr, "[esim]   %-12s n=%-5u run %8.0f  entry->start %8.0f  gap after predecessor %8.0f\n", nm[k], cnt[k],
+                            run[k] / cnt[k], wait[k] / cnt[k], gcnt[k] ? gap[k] / gcnt[k] : 0.0);
+}
+
+void esim_destroy(EsimSim* s) { if (s) print_ktrace(s); delete s; }
 
 int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
     if (!s) return ESIM_ERR_INVALID_ARGUMENT;
@@ -595,6 +635,12 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.n_shared_b = s->n_shared_bldgs; v.n_shared_r = s->n_shared_rooms;
         v.tally_partial = s->tally_partial.p; v.n_update_blocks = n_update_blocks;
         v.ctrl = s->ctrl.p; v.stats = s->stats.p; v.max_steps = s->cfg.max_time_step;
+        if (getenv("ESIM_KTRACE")) {
+            s->ktrace_min.alloc((size_t)KTRACE_STEPS * KTRACE_KERNELS * 2); s->ktrace_max.alloc((size_t)KTRACE_STEPS * KTRACE_KERNELS);
+            CK(cudaMemsetAsync(s->ktrace_min.p, 0xFF, s->ktrace_min.bytes(), st));
+            CK(cudaMemsetAsync(s->ktrace_max.p, 0, s->ktrace_max.bytes(), st));
+            v.ktrace_min = s->ktrace_min.p; v.ktrace_max = s->ktrace_max.p;
+        }
         v.mp.exposed_time = te; v.mp.infected_time = ti; v.mp.vaccination_rate = s->cfg.vaccination_rate;
         v.mp.bus_capacity = s->cfg.bus_capacity;
         v.mp.th_lockdown = s->cfg.lockdown_threshold; v.mp.th_vaccination = s->cfg.vaccination_threshold;
@@ -609,6 +655,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         if (s->fused) { launch_boot_fused(v, st); CK(cudaGetLastError()); }
         if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH) && s->world == 1) capture_graphs(s);  // sharded: captured by esim_comm_init
         tr.mark("graph capture", st);
+        CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));   // the boot kernel may have changed it
         CK(cudaStreamSynchronize(st));
         s->imported = true;
         s->steps_done = 0;
@@ -626,9 +673,17 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
         const uint32_t parity = (before + 1u) & 1u;
         if (s->world > 1 && !s->comm && !s->v.p2p)
             throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
-        if (timed) {
+        const bool time_kernels = timed && (s->cfg.flags & ESIM_CFG_TIME_KERNELS);
+        if (timed && !time_kernels) {
+            // whole-step timing: the kernels follow each other exactly as in the captured graphs (programmatic dependent
+            // launches, no public-transport kernel in hours without riders - the host has just read the control block)
+            flush_l2(s);
+            CK(cudaEventRecord(s->ev[0], s->stream));
+            enqueue_step(s, parity, s->h_ctrl->pt_mode != ESIM_PT_NONE, true);
+            CK(cudaEventRecord(s->ev[4], s->stream));
+        } else if (timed) {
             const DevView& v = s->v;
-            if (s->l2_scratch.p) CK(cudaMemsetAsync(s->l2_scratch.p, (int)(s->steps_done & 0xFF), s->l2_scratch.bytes(), s->stream));
+            flush_l2(s);
             CK(cudaEventRecord(s->ev[0], s->stream));
             if (!s->fused) launch_update(v, s->stream);
             if (s->world > 1 && !v.p2p && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
@@ -651,7 +706,13 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
         fetch_ctrl(s);
         const int rc = after_steps(s);
         if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
-        if (timed && s->steps_done > before) {
+        if (timed && !time_kernels && s->steps_done > before) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[4]));
+            s->timings.total += ms * 1e-3;
+            s->timings.steps += 1;
+            s->step_total_ms[before] = ms;
+        } else if (timed && s->steps_done > before) {
             float ms[4];
             for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ms[k], s->ev[k], s->ev[k + 1]));
             EsimTimings& T = s->timings;
@@ -747,6 +808,7 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
 }
 
 int esim_steps_done(EsimSim* s) { return s ? (int)s->steps_done : ESIM_ERR_INVALID_ARGUMENT; }
+int esim_is_fused(EsimSim* s) { return s && s->imported ? (s->fused ? 1 : 0) : ESIM_ERR_INITIALIZATION; }
 
 int esim_read_stats(EsimSim* s, uint32_t first, uint32_t count, EsimStepStats* out) {
     return guarded(s, [&]() -> int {

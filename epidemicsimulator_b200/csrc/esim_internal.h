@@ -42,6 +42,8 @@ constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 
 constexpr uint32_t MAX_STEPS      = CS_EXPOSURE - EXPOSURE_BIAS - 1;
 constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer, see k_vax_prepare
 
+constexpr uint32_t KTRACE_STEPS = 1024, KTRACE_KERNELS = 4;   // kernels: 0 = update / step, 1 = expose, 2 = pt, 3 = tail
+
 // index of the count buffer that holds the infected occupants of step t
 __host__ __device__ inline uint32_t cnt_slot(uint32_t fused, uint32_t t) { return fused ? t % 3u : t & 1u; }
 
@@ -132,6 +134,10 @@ struct DevView {
     uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] candidate citizen of every draw of this step
     uint32_t* tally_partial;     // [n_update_blocks * 8] per-block S,E,I,R,V partial sums of k_update
     uint32_t n_update_blocks;
+    // ESIM_KTRACE=1: device-side timeline (%globaltimer) of the step kernels, [KTRACE_STEPS][KTRACE_KERNELS] slots each for
+    // the earliest block entry, the earliest start after the dependency wait and the latest block exit
+    unsigned long long* ktrace_min;   // [KTRACE_STEPS * KTRACE_KERNELS * 2]: enter, begin (atomicMin, initialised to ~0)
+    unsigned long long* ktrace_max;   // [KTRACE_STEPS * KTRACE_KERNELS]: end (atomicMax, initialised to 0)
     Ctrl* ctrl;
     EsimStepStats* stats;  // [max_steps]
     uint32_t max_steps;
@@ -148,6 +154,7 @@ void launch_step_fused(const DevView& v, cudaStream_t s);
 void launch_tail_fused(const DevView& v, cudaStream_t s);
 void launch_boot_fused(const DevView& v, cudaStream_t s);   // after import: k_update of step 1 + the first schedule
 uint32_t step_blocks(uint32_t n_pad);
+void launch_flush_sweep(const void* scratch, size_t bytes, uint32_t* sink, cudaStream_t s);   // ESIM_CFG_FLUSH_L2
 int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as int
 int  sm_count();
 void set_pdl(bool on);   // programmatic dependent launch of the step kernels (default on)

@@ -50,6 +50,27 @@ __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// device-side timeline (ESIM_KTRACE=1): one thread per block stamps %globaltimer around its work
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long x;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x));
+    return x;
+}
+struct KTrace {
+    unsigned long long enter;
+    __device__ __forceinline__ void start(const DevView& v) { if (v.ktrace_min && threadIdx.x == 0) enter = global_ns(); }
+    __device__ __forceinline__ void begin(const DevView& v, uint32_t t, uint32_t kernel) const {
+        if (v.ktrace_min && threadIdx.x == 0) {
+            const uint32_t slot = (t % KTRACE_STEPS) * KTRACE_KERNELS + kernel;
+            atomicMin(&v.ktrace_min[slot * 2u], enter);
+            atomicMin(&v.ktrace_min[slot * 2u + 1u], global_ns());
+        }
+    }
+    __device__ __forceinline__ void end(const DevView& v, uint32_t t, uint32_t kernel) const {
+        if (v.ktrace_min && threadIdx.x == 0) atomicMax(&v.ktrace_max[(t % KTRACE_STEPS) * KTRACE_KERNELS + kernel], global_ns());
+    }
+};
+
 __device__ __forceinline__ uint32_t warp_sum(uint32_t x) { return __reduce_add_sync(0xffffffffu, x); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
@@ -361,6 +382,9 @@ __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
 // tail (see tail_phase<.., true>); the schedule of step t + 1 is known because update_status only needs the infected share,
 // which the previous tail already had.
 constexpr int STEP_THREADS = 256;
+constexpr uint32_t STEP_PF = 2;   // prefetch distance in iterations
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__constant__ int g_pf = 1;        // ESIM_STEP_PF=0 switches the L2 prefetches off (experiments)
 
 template <bool EAGER, bool AT_WORK>
 __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt) {
@@ -381,6 +405,26 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
     const uint32_t* __restrict__ pos_next = c->next_at_work ? v.work_cell : v.home_cell;
     const uint4 pad4 = make_uint4(CS_PADDING, CS_PADDING, CS_PADDING, CS_PADDING);
 
+    // L2 prefetch of the streams, STEP_PF iterations ahead: one request per 128-byte line (8 quads), issued by every eighth
+    // lane.  A prefetch holds no register and no scoreboard slot, so the demand loads of later iterations find their lines
+    // in the L2 while HBM sees the requests of several iterations at once.
+    const bool pf_lane = (threadIdx.x & 7u) == 0u;
+    auto prefetch_pair = [&](uint32_t qa) {
+        if (!pf_lane || qa >= n_quads) return;
+        const uint32_t qb = qa + T;
+        prefetch_l2(cs4 + qa);
+        if (EAGER) { prefetch_l2(hc4 + qa); prefetch_l2(wc4 + qa); }
+        if (qb < n_quads) {
+            prefetch_l2(cs4 + qb);
+            if (EAGER) { prefetch_l2(hc4 + qb); prefetch_l2(wc4 + qb); }
+        }
+    };
+    if (g_pf) {
+#pragma unroll
+        for (uint32_t d = 1; d <= STEP_PF; ++d) prefetch_pair(gtid + d * 2u * T);
+        // the infected counts of step t: written by the previous launch, gathered at random below
+        for (uint32_t z = gtid; z < ((v.n_cells + 31u) >> 5); z += T) prefetch_l2(cnt + (z << 5));
+    }
     for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
 
     uint32_t n_exposed = 0;
@@ -388,6 +432,7 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
         const uint32_t q1 = q0 + T;
         const bool have1 = q1 < n_quads;
+        if (g_pf) prefetch_pair(q0 + (STEP_PF + 1u) * 2u * T);
         const uint4 wa = cs4[q0];
         const uint4 wb = have1 ? cs4[q1] : pad4;
         uint4 ha, ka, hb, kb;
@@ -404,7 +449,9 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
         // apply_exposures of step t
         if (sa) n_exposed += expose_quad<AT_WORK, false>(v, cnt, q0, w[0], ha, ka, t, mask_everywhere);
         if (sb) n_exposed += expose_quad<AT_WORK, false>(v, cnt, q1, w[1], hb, kb, t, mask_everywhere);
-        // generate_exposures of step t + 1 on the updated words
+        // generate_exposures of step t + 1 on the updated words.  Eight citizens that were never exposed add nothing to the
+        // cumulative counts: one test skips them (the common case for most of an epidemic).
+        if (((w[0][0] | w[0][1] | w[0][2] | w[0][3] | w[1][0] | w[1][1] | w[1][2] | w[1][3]) & CS_LOW16) == 0u) continue;
         uint32_t any_present_infected = 0;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -449,17 +496,172 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
     return n_exposed;
 }
 
-__global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) {
+// ---- k_step_tma: the same pass with the streaming reads staged through shared memory by bulk asynchronous copies ------------
+// Every block owns a contiguous range of quads and walks it in tiles of STEP_TILE quads.  One elected thread keeps
+// STEP_STAGES tiles of (state words [, household ids, workplace ids]) in flight with cp.async.bulk (TMA, SASS UBLKCP)
+// completing on an mbarrier per stage, so the memory-level parallelism of the stream no longer costs registers or
+// occupancy: a thread only ever holds the quad it is working on, and the latency of the dependent count gathers is the only
+// one left on the critical path of a tile.
+constexpr int STEP_TILE = STEP_THREADS;   // quads per tile: one per thread
+constexpr int STEP_STAGES = 4;
+struct StepSmem {
+    uint4 tile[STEP_STAGES][3][STEP_TILE];     // [stage][state | household | workplace][quad]
+    unsigned long long full[STEP_STAGES];      // mbarriers: the bytes of a stage have landed
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool EAGER, bool AT_WORK>
+__device__ __forceinline__ uint32_t step_stream_tma(const DevView& v, const Ctrl* __restrict__ c, StepSmem& sm, uint32_t* s_cnt) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_quads = v.n_pad >> 2;
+    const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
+    const uint4* __restrict__ hc4 = reinterpret_cast<const uint4*>(v.home_cell);
+    const uint4* __restrict__ wc4 = reinterpret_cast<const uint4*>(v.work_cell);
+    // this block's contiguous range of quads
+    const uint32_t q_lo = (uint32_t)(((uint64_t)blockIdx.x * n_quads) / gridDim.x);
+    const uint32_t q_hi = (uint32_t)(((uint64_t)(blockIdx.x + 1u) * n_quads) / gridDim.x);
+    const uint32_t n_tiles = (q_hi - q_lo + STEP_TILE - 1) / STEP_TILE;
+    auto issue = [&](uint32_t i) {   // elected thread: request tile i into its stage
+        const uint32_t s = i % STEP_STAGES, q = q_lo + i * STEP_TILE;
+        const uint32_t bytes = min((uint32_t)STEP_TILE, q_hi - q) * 16u;
+        mbar_expect_tx(&sm.full[s], EAGER ? 3u * bytes : bytes);
+        bulk_load(sm.tile[s][0], cs4 + q, bytes, &sm.full[s]);
+        if (EAGER) {
+            bulk_load(sm.tile[s][1], hc4 + q, bytes, &sm.full[s]);
+            bulk_load(sm.tile[s][2], wc4 + q, bytes, &sm.full[s]);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < STEP_STAGES; ++s) mbar_init(&sm.full[s], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (uint32_t i = 0; i < min((uint32_t)STEP_STAGES, n_tiles); ++i) issue(i);
+    }
+    const uint32_t t = c->t, t1 = t + 1u;
+    const uint32_t mask_everywhere = c->mask_cur == ESIM_MASK_EVERYWHERE;
+    const uint32_t* __restrict__ cnt = v.cnt[cnt_slot(1u, t)];
+    uint32_t* __restrict__ cnt_next = v.cnt[cnt_slot(1u, t1)];
+    uint4* __restrict__ cnt_zero = reinterpret_cast<uint4*>(v.cnt[cnt_slot(1u, t1 + 1u)]);
+    const uint32_t rider_mask = c->next_pt_mode != ESIM_PT_NONE ? CS_USES_PT : 0u;
+    const uint32_t e_lo = t1 + EXPOSURE_BIAS - v.mp.exposed_time;
+    const uint32_t i_lo = e_lo - 1u - v.mp.infected_time;
+    const uint32_t* __restrict__ pos_next = c->next_at_work ? v.work_cell : v.home_cell;
+    // zero the count buffer of step t + 2 while the first tiles are on their way
+    for (uint32_t z = blockIdx.x * blockDim.x + tid; z < ((v.n_cells + 3u) >> 2); z += gridDim.x * blockDim.x)
+        cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();   // the barriers are initialised before anybody waits on them
+
+    uint32_t n_exposed = 0;
+    uint32_t c_exp = 0, c_inf = 0, c_ei = 0, c_vax = 0;
+    for (uint32_t i = 0; i < n_tiles; ++i) {
+        const uint32_t s = i % STEP_STAGES;
+        const uint32_t q = q_lo + i * STEP_TILE + tid;
+        const bool active = q < q_hi;
+        mbar_wait(&sm.full[s], (i / STEP_STAGES) & 1u);
+        uint4 w4 = make_uint4(0u, 0u, 0u, 0u), h4 = w4, k4 = w4;
+        if (active) {
+            w4 = sm.tile[s][0][tid];
+            if (EAGER) { h4 = sm.tile[s][1][tid]; k4 = sm.tile[s][2][tid]; }
+        }
+        __syncthreads();   // everybody has taken its quad out of the stage: refill it
+        if (tid == 0 && i + STEP_STAGES < n_tiles) issue(i + STEP_STAGES);
+        if (!active) continue;
+        uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+        if (any_susceptible(w4)) {
+            if (!EAGER) { h4 = __ldg(hc4 + q); k4 = __ldg(wc4 + q); }
+            n_exposed += expose_quad<AT_WORK, false>(v, cnt, q, w, h4, k4, t, mask_everywhere);   // apply_exposures of step t
+        }
+        // generate_exposures of step t + 1 on the updated words
+        uint32_t any_present_infected = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t code = w[k] & CS_LOW16;
+            c_exp += code != 0u;
+            c_inf += code >= i_lo;
+            c_ei += code >= e_lo;
+            c_vax += code >> 15;
+            any_present_infected |= (code >= i_lo) & (code < e_lo) & ((w[k] & rider_mask) == 0u);
+        }
+        if (any_present_infected) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t code = w[k] & CS_LOW16;
+                if (code >= i_lo && code < e_lo && (w[k] & rider_mask) == 0u) {
+                    const uint32_t cell = __ldg(&pos_next[(q << 2) + (uint32_t)k]);
+                    atomicAdd(&cnt_next[cell], 1u);
+                    if (cell >= v.n_bldg) atomicAdd(&cnt_next[__ldg(&v.room_parent[cell - v.n_bldg])], 1u);
+                }
+            }
+        }
+    }
+    if (tid < 4) s_cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t r4[4] = {warp_sum(c_exp), warp_sum(c_inf), warp_sum(c_ei), warp_sum(c_vax)};
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (r4[k]) atomicAdd(&s_cnt[k], r4[k]);
+    }
+    __syncthreads();
+    if (tid < 8) v.tally_partial[blockIdx.x * 8u + tid] = tid < 4 ? s_cnt[tid] : 0u;
+    return n_exposed;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 4) k_step_tma(const DevView v) {
+    KTrace kt; kt.start(v);
+    pdl_prologue();
+    extern __shared__ __align__(128) unsigned char step_smem_raw[];
+    StepSmem& sm = *reinterpret_cast<StepSmem*>(step_smem_raw);
+    __shared__ uint32_t s_cnt[4];
+    const Ctrl* __restrict__ c = v.ctrl;
+    if (c->finished | c->abort_graph) return;
+    const uint32_t kt_t = c->t;
+    kt.begin(v, kt_t, 0);
+    const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
+    const uint32_t n_exposed = eager ? (at_work ? step_stream_tma<true, true>(v, c, sm, s_cnt) : step_stream_tma<true, false>(v, c, sm, s_cnt))
+                                     : (at_work ? step_stream_tma<false, true>(v, c, sm, s_cnt) : step_stream_tma<false, false>(v, c, sm, s_cnt));
+    const uint32_t s = warp_sum(n_exposed);
+    if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+    kt.end(v, kt_t, 0);
+}
+
+template <int OCC>
+__device__ __forceinline__ void k_step_body(const DevView& v) {
+    KTrace kt; kt.start(v);
     pdl_prologue();
     __shared__ uint32_t s_cnt[4];
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
+    const uint32_t kt_t = c->t;
+    kt.begin(v, kt_t, 0);
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
     const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true>(v, c, s_cnt) : step_stream<true, false>(v, c, s_cnt))
                                      : (at_work ? step_stream<false, true>(v, c, s_cnt) : step_stream<false, false>(v, c, s_cnt));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+    kt.end(v, kt_t, 0);
 }
+__global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) { k_step_body<3>(v); }
+__global__ void __launch_bounds__(STEP_THREADS, 4) k_step_occ4(const DevView v) { k_step_body<4>(v); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Public transport: one warp per route (source area, destination area).  Everybody who uses public transport rides at
@@ -1072,20 +1274,28 @@ constexpr size_t HT_BYTES = 3 * HT_SIZE * sizeof(uint32_t);
 constexpr int PT_THREADS = 128;  // 4 routes per block: small blocks start (and, on idle hours, retire) quickly
 
 __global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
+    KTrace kt; kt.start(v);
     pdl_prologue();
     __shared__ PtWarpSmem ws[PT_THREADS / 32];
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph || c->pt_mode == ESIM_PT_NONE) return;
-    pt_phase(v, &ws[threadIdx.x >> 5], c->t, c->mask_cur == ESIM_MASK_EVERYWHERE);
+    const uint32_t kt_t = c->t;
+    kt.begin(v, kt_t, 2);
+    pt_phase(v, &ws[threadIdx.x >> 5], kt_t, c->mask_cur == ESIM_MASK_EVERYWHERE);
+    kt.end(v, kt_t, 2);
 }
 
 // fused pipeline: v.n_update_blocks is the grid of k_step here (set by the launcher)
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail_fused(const DevView v) {
+    KTrace kt; kt.start(v);
     pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
     if (v.ctrl->finished | v.ctrl->abort_graph) return;
+    const uint32_t kt_t = v.ctrl->t;
+    kt.begin(v, kt_t, 3);
     tail_phase<TAIL_THREADS, true>(v, dyn_smem, sm, v.n_update_blocks);
+    kt.end(v, kt_t, 3);
 }
 
 // fused pipeline, once after the import: k_update has counted step 1; this turns its partial sums into Ctrl::tally, runs
@@ -1221,6 +1431,20 @@ int launch_persistent(const DevView& v, uint32_t n_steps, unsigned int* barrier_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// ESIM_CFG_FLUSH_L2: after the scratch buffer (2x the L2) has been overwritten, sweep it once more with loads: the L2 then holds
+// clean scratch lines only, so a timed step starts cold without also paying for the write-back of the flush itself.
+__global__ void __launch_bounds__(256) k_flush_sweep(const uint4* __restrict__ scratch, size_t n16, uint32_t* sink) {
+    uint32_t acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 x = __ldcg(scratch + i);
+        acc ^= x.x ^ x.y ^ x.z ^ x.w;
+    }
+    if (acc == 0x9E3779B9u) *sink = acc;   // never true for a memset pattern: keeps the loads alive
+}
+void launch_flush_sweep(const void* scratch, size_t bytes, uint32_t* sink, cudaStream_t s) {
+    k_flush_sweep<<<sm_count() * 8, 256, 0, s>>>(reinterpret_cast<const uint4*>(scratch), bytes / 16, sink);
+}
+
 static int g_sm_count = 0;
 
 int sm_count() {
@@ -1233,10 +1457,19 @@ int sm_count() {
     return g_sm_count;
 }
 
+static bool g_step_tma = false;         // ESIM_STEP_TMA=1 selects the bulk-copy staged k_step_tma (measured slower)
+static bool g_step_occ4 = true;         // ESIM_STEP_OCC4=0: the 80-register build of k_step (3 resident blocks per SM)
+static int g_step_blocks_per_sm = 4;    // k_step blocks per SM in the grid (3 are resident; more = several waves)
+
 int configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vax_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tail_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
+    if (const char* env = getenv("ESIM_STEP_TMA")) g_step_tma = env[0] == '1';
+    if (const char* env = getenv("ESIM_STEP_BLOCKS")) g_step_blocks_per_sm = atoi(env);
+    if (const char* env = getenv("ESIM_STEP_PF")) { const int on = env[0] != '0'; if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_pf, &on, sizeof(on)); }
+    if (const char* env = getenv("ESIM_STEP_OCC4")) { g_step_occ4 = env[0] == '1'; if (!g_step_occ4 && !getenv("ESIM_STEP_BLOCKS")) g_step_blocks_per_sm = 3; }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     // One shared-memory carve-out for every step kernel: switching the L1 / shared split between consecutive kernels costs
     // microseconds, which is what a step is made of.  ESIM_CARVEOUT (percent) overrides the default for experiments.
@@ -1291,11 +1524,14 @@ void launch_tail(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_tail, 1, TAIL_THREADS, HT_BYTES, s, v);
 }
 uint32_t step_blocks(uint32_t n_pad) {
-    // one resident wave: 3 blocks of 256 threads per SM, two quads per thread and iteration
-    return blocks_for(n_pad >> 2, STEP_THREADS, (uint32_t)sm_count() * 3u);
+    // one resident wave of 256-thread blocks
+    // k_step handles two quads per thread and iteration
+    return blocks_for(g_step_tma ? n_pad >> 2 : (n_pad + 7u) >> 3, STEP_THREADS, (uint32_t)sm_count() * (uint32_t)g_step_blocks_per_sm);
 }
 void launch_step_fused(const DevView& v, cudaStream_t s) {
-    launch_step_kernel(k_step, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+    if (g_step_tma) launch_step_kernel(k_step_tma, step_blocks(v.n_pad), STEP_THREADS, sizeof(StepSmem), s, v);
+    else if (g_step_occ4) launch_step_kernel(k_step_occ4, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+    else launch_step_kernel(k_step, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
 }
 void launch_tail_fused(const DevView& v, cudaStream_t s) {
     DevView vv = v;

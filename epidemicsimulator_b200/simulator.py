@@ -175,6 +175,11 @@ class Simulator:
     def steps_done(self) -> int:
         return self._check(self._lib.esim_steps_done(self._h))
 
+    @property
+    def fused(self) -> bool:
+        """True if the handle runs the fused one-pass step (k_step + k_tail_fused)."""
+        return self._check(self._lib.esim_is_fused(self._h)) == 1
+
     # -- sharded runs (one Simulator per GPU / rank) -------------------------------------------------------
     def attach_comm(self, dist) -> None:
         """Create the NCCL communicator of this shard group; `dist` is an initialised torch.distributed (any backend

@@ -75,6 +75,9 @@ extern "C" {
                                       phases instead of replaying CUDA graphs (single shard; currently slower) */
 #define ESIM_CFG_UNFUSED      0x10u /* single shard: use the three-kernel step (k_update, k_expose, k_tail) instead of the fused
                                        one-pass step (k_step, k_tail_fused); results are identical (parity tests run both)   */
+#define ESIM_CFG_TIME_KERNELS 0x20u /* esim_step_timed records a CUDA event between every two kernels (per-kernel split in
+                                       EsimTimings; each event costs ~2.5 us of stream time and ends the programmatic overlap
+                                       of consecutive kernels).  Without it only the whole step is timed.            */
 #define ESIM_CFG_FLUSH_L2     0x4u /* esim_step_timed overwrites a 256 MiB scratch buffer before every step, so
                                       that each timed step starts with a cold L2 (benchmark hygiene only)       */
 
@@ -205,8 +208,9 @@ void esim_destroy(EsimSim* sim);
 
 /* Simulator::step (simulator.rs:131-152): returns 1 = disease still exists, 0 = finished, <0 = error. */
 int esim_step(EsimSim* sim, EsimStepStats* out /* nullable */);
-/* Same as esim_step but launches the kernels one by one with CUDA events around each phase
- * (the reference's record_function_time, statistics.rs:173-175); accumulates into EsimTimings. */
+/* Same as esim_step but launches the kernels directly with CUDA events around the step - and, with
+ * ESIM_CFG_TIME_KERNELS, around each phase (the reference's record_function_time, statistics.rs:173-175);
+ * accumulates into EsimTimings. */
 int esim_step_timed(EsimSim* sim, EsimStepStats* out /* nullable */);
 /* Simulator::simulate (simulator.rs:108-127) without the dump: up to max_steps steps, device-resident
  * (no host synchronisation per step), stops after the step in which the disease disappears.
@@ -217,6 +221,8 @@ int esim_run(EsimSim* sim, uint32_t max_steps, uint32_t* steps_done /* nullable 
  * (index 0 = time_step 1).  Returns the number of entries written. */
 int esim_read_stats(EsimSim* sim, uint32_t first, uint32_t count, EsimStepStats* out);
 int esim_steps_done(EsimSim* sim);
+/* 1 = the handle runs the fused one-pass step (k_step + k_tail_fused), 0 = the three-kernel step; <0 = error. */
+int esim_is_fused(EsimSim* sim);
 
 /* Rebuild OutputArea.citizens / Citizen fields on the caller's side (simulator.rs:88-101 pub fields). */
 int esim_read_state(EsimSim* sim, EsimStateView* view);

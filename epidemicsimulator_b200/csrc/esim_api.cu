@@ -130,7 +130,7 @@ struct EsimSim {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevView v{};
-    DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt0, cnt1, cnt2, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
+    DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt_all, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
         rec_bus, rec_businf;
     DevBuf<unsigned long long> thr;
     DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
@@ -142,7 +142,8 @@ struct EsimSim {
     DevBuf<unsigned long long> pk_prof; // ESIM_TRACE: cycles per phase
     DevBuf<unsigned long long> ktrace_min, ktrace_max;   // ESIM_KTRACE: device-side timeline of the step kernels
     bool use_persistent = false;
-    bool fused = false;                 // single shard: one-pass step (k_step + k_tail_fused), three count buffers
+    bool fused = false;                 // one-pass step (k_step + k_tail_fused): single shard and peer-to-peer shards
+    size_t cnt_stride = 0;              // words between the three count buffers inside cnt_all
     uint32_t world = 1, rank = 0, n_shared_bldgs = 0, n_shared_rooms = 0;
     void* comm = nullptr;               // ncclComm_t
     DevBuf<Ctrl> ctrl;
@@ -192,7 +193,7 @@ struct EsimSim {
         for (void* m : peer_mappings) cudaIpcCloseMemHandle(m);
         exch.release(); vax_cand.release(); barrier.release(); pk_prof.release(); peer_mail.release(); peer_view.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt0.release(); cnt1.release(); cnt2.release(); tally_partial.release();
+        cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt_all.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
         if (stream) cudaStreamSynchronize(stream);
@@ -580,9 +581,11 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         build_thresholds(s->cfg, thr);
 
         const bool sharded_pop = p->n_shards > 1;
-        s->cnt0.alloc((size_t)B + R + 4, sharded_pop); s->cnt1.alloc((size_t)B + R + 4, sharded_pop);
+        // three count buffers in one allocation (one CUDA IPC handle for peers); sharded handles decide at connect time
+        // whether they run fused (esim_peer_connect) or not (esim_comm_init, esim_shard_step_*)
+        s->cnt_stride = ((size_t)B + R + 4 + 31) & ~(size_t)31;
+        s->cnt_all.alloc(3 * s->cnt_stride, sharded_pop);
         s->fused = p->n_shards <= 1 && !(s->cfg.flags & (ESIM_CFG_UNFUSED | ESIM_CFG_PERSISTENT)) && !getenv("ESIM_UNFUSED");
-        if (s->fused) s->cnt2.alloc((size_t)B + R + 4);
         if (sharded_pop) { s->peer_mail.alloc(MAIL_WORDS, true); CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st)); }
         s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
         s->pt_buscnt.alloc(std::max<uint32_t>(n_riders, 1));
@@ -596,15 +599,13 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         if (getenv("ESIM_TRACE")) { s->pk_prof.alloc(8); CK(cudaMemsetAsync(s->pk_prof.p, 0, s->pk_prof.bytes(), s->stream)); }
         s->world = p->n_shards > 1 ? p->n_shards : 1;
         s->n_shared_bldgs = p->n_shared_bldgs; s->n_shared_rooms = p->n_shared_rooms;
-        s->exch.alloc(EXCH_WORDS); s->vax_cand.alloc(ESIM_VAX_SHARD_DRAWS);
+        s->exch.alloc(FEXCH_WORDS); s->vax_cand.alloc(ESIM_VAX_SHARD_DRAWS);
         CK(cudaMemsetAsync(s->exch.p, 0, s->exch.bytes(), st));
         s->thr.alloc(512); s->ctrl.alloc(1); s->stats.alloc(s->cfg.max_time_step);
         if (s->cfg.flags & ESIM_CFG_FLUSH_L2) s->l2_scratch.alloc((size_t)256 << 20);  // 2x the 126 MB L2
         CK(cudaMemcpyAsync(s->thr.p, thr, sizeof(thr), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(s->cnt0.p, 0, s->cnt0.bytes(), st));
+        CK(cudaMemsetAsync(s->cnt_all.p, 0, s->cnt_all.bytes(), st));
         CK(cudaMemsetAsync(s->tally_partial.p, 0, s->tally_partial.bytes(), st));
-        CK(cudaMemsetAsync(s->cnt1.p, 0, s->cnt1.bytes(), st));
-        if (s->fused) CK(cudaMemsetAsync(s->cnt2.p, 0, s->cnt2.bytes(), st));
         if (rec) {
             CK(cudaMemsetAsync(s->rec_bus.p, 0xFF, s->rec_bus.bytes(), st));
             CK(cudaMemsetAsync(s->rec_businf.p, 0, s->rec_businf.bytes(), st));
@@ -612,7 +613,9 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         Ctrl c0;
         std::memset(&c0, 0, sizeof(c0));
         c0.eager_expose = 1;
-        c0.t = 1;  // the first hour is 1 (statistics.rs:167); everybody starts at home, off public transport (citizen.rs:156-160)
+        // the first hour is 1 (statistics.rs:167); everybody starts at home, off public transport (citizen.rs:156-160).
+        // The fused pipeline starts at 0: its boot pass (launch_boot_fused) runs as "step 0" and leaves t = 1.
+        c0.t = s->fused ? 0 : 1;
         std::memcpy(s->h_ctrl, &c0, sizeof(c0));
         CK(cudaMemcpyAsync(s->ctrl.p, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
         tr.mark("thresholds, allocations, memsets", st);
@@ -627,7 +630,8 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.n_routes = n_routes; v.n_riders = n_riders; v.record_buses = rec ? 1u : 0u;
         v.next_has_pt = 1;   // every launch sequence has a public-transport kernel unless a specialised graph says otherwise
         v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
-        v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt0.p; v.cnt[1] = s->cnt1.p; v.cnt[2] = s->cnt2.p; v.fused = s->fused ? 1u : 0u; v.thr = s->thr.p;
+        v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt_all.p; v.cnt[1] = s->cnt_all.p + s->cnt_stride; v.cnt[2] = s->cnt_all.p + 2 * s->cnt_stride;
+        v.fused = s->fused ? 1u : 0u; v.boot = 0; v.thr = s->thr.p;
         v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
         v.pt_buscnt = s->pt_buscnt.p; v.rec_bus = s->rec_bus.p; v.rec_businf = s->rec_businf.p;
         v.world = s->world; v.exch = s->exch.p; v.vax_cand = s->vax_cand.p;
@@ -649,7 +653,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.mp.n_global_citizens = n_global; v.mp.shard_lo = shard_lo;
 
         s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->gid.bytes() +
-                          s->room_parent.bytes() + s->cnt0.bytes() * (s->fused ? 3 : 2) + s->route_off.bytes() + s->riders.bytes() * 4 +
+                          s->room_parent.bytes() + s->cnt_all.bytes() + s->route_off.bytes() + s->riders.bytes() * 4 +
                           s->rec_bus.bytes() * 2 + s->stats.bytes();
         // fused pipeline: count step 1 and lay out the first schedule (k_update + k_boot_fused), once
         if (s->fused) { launch_boot_fused(v, st); CK(cudaGetLastError()); }
@@ -1040,8 +1044,8 @@ int esim_dump_statistics(EsimSim* s, const char* directory, const char* const* a
 // ---- sharded runs ----------------------------------------------------------------------------------------
 namespace {
 struct PeerInfo {   // what a rank publishes; padded to ESIM_PEER_INFO_BYTES
-    cudaIpcMemHandle_t cnt0, cnt1, mail;
-    uint32_t n_bldg, n_rooms, n_shared_b, n_shared_r, world, device;
+    cudaIpcMemHandle_t cnt, mail;
+    uint32_t n_bldg, n_rooms, n_shared_b, n_shared_r, world, device, cnt_stride, fused_ok;
 };
 static_assert(sizeof(PeerInfo) <= ESIM_PEER_INFO_BYTES, "peer info does not fit");
 }  // namespace
@@ -1053,8 +1057,9 @@ int esim_peer_info(EsimSim* s, uint8_t info[ESIM_PEER_INFO_BYTES]) {
         if (s->world < 2 || !s->peer_mail.p) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "not a sharded handle"};
         PeerInfo pi;
         std::memset(&pi, 0, sizeof(pi));
-        CK(cudaIpcGetMemHandle(&pi.cnt0, s->cnt0.p));
-        CK(cudaIpcGetMemHandle(&pi.cnt1, s->cnt1.p));
+        CK(cudaIpcGetMemHandle(&pi.cnt, s->cnt_all.p));
+        pi.cnt_stride = (uint32_t)s->cnt_stride;
+        pi.fused_ok = !(s->cfg.flags & (ESIM_CFG_UNFUSED | ESIM_CFG_PERSISTENT)) && !getenv("ESIM_UNFUSED") ? 1u : 0u;
         CK(cudaIpcGetMemHandle(&pi.mail, s->peer_mail.p));
         pi.n_bldg = s->v.n_bldg; pi.n_rooms = s->v.n_rooms; pi.n_shared_b = s->n_shared_bldgs; pi.n_shared_r = s->n_shared_rooms;
         pi.world = s->world; pi.device = (uint32_t)s->device;
@@ -1074,28 +1079,41 @@ int esim_peer_connect(EsimSim* s, uint32_t rank, uint32_t world, const uint8_t* 
         PeerView pv;
         std::memset(&pv, 0, sizeof(pv));
         s->v.rank = rank; s->rank = rank;
+        bool fused = true;   // every shard must run the same pipeline
         for (uint32_t p = 0; p < world; ++p) {
             PeerInfo pi;
             std::memcpy(&pi, all_infos + (size_t)p * ESIM_PEER_INFO_BYTES, sizeof(pi));
             if (pi.world != world || pi.n_shared_b != s->n_shared_bldgs || pi.n_shared_r != s->n_shared_rooms)
                 throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "peer describes a different sharding"};
             pv.n_bldg[p] = pi.n_bldg;
+            fused = fused && pi.fused_ok;
             if (p == rank) {
-                pv.cnt[0][p] = s->cnt0.p; pv.cnt[1][p] = s->cnt1.p; pv.mail[p] = s->peer_mail.p;
+                for (int k = 0; k < 3; ++k) pv.cnt[k][p] = s->v.cnt[k];
+                pv.mail[p] = s->peer_mail.p;
                 continue;
             }
-            void *m0 = nullptr, *m1 = nullptr, *mm = nullptr;
-            CK(cudaIpcOpenMemHandle(&m0, pi.cnt0, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(m0);
-            CK(cudaIpcOpenMemHandle(&m1, pi.cnt1, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(m1);
+            void *m0 = nullptr, *mm = nullptr;
+            CK(cudaIpcOpenMemHandle(&m0, pi.cnt, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(m0);
             CK(cudaIpcOpenMemHandle(&mm, pi.mail, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(mm);
-            pv.cnt[0][p] = (uint32_t*)m0; pv.cnt[1][p] = (uint32_t*)m1; pv.mail[p] = (uint32_t*)mm;
+            for (int k = 0; k < 3; ++k) pv.cnt[k][p] = (uint32_t*)m0 + (size_t)k * pi.cnt_stride;
+            pv.mail[p] = (uint32_t*)mm;
         }
         s->peer_view.alloc(1);
         CK(cudaMemcpyAsync(s->peer_view.p, &pv, sizeof(pv), cudaMemcpyHostToDevice, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         s->v.peer = s->peer_view.p;
         s->v.p2p = 1;
+        if (fused) {
+            // the fused pipeline over peer-to-peer shards: restart the control block at "step 0" and run the boot pass (its
+            // k_update pushes the infected occupants of step 1 to the peers, its tail exchanges the first class counts)
+            s->fused = true; s->v.fused = 1;
+            const uint32_t zero = 0;
+            CK(cudaMemcpyAsync(&s->ctrl.p->t, &zero, sizeof(zero), cudaMemcpyHostToDevice, s->stream));
+            launch_boot_fused(s->v, s->stream);
+            CK(cudaGetLastError());
+        }
         if (!(s->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(s);
+        CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         return ESIM_OK;
     });

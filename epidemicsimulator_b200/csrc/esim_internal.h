@@ -41,6 +41,10 @@ constexpr uint32_t CS_PADDING     = 0xFFFFu;
 constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 2
 constexpr uint32_t MAX_STEPS      = CS_EXPOSURE - EXPOSURE_BIAS - 1;
 constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer, see k_vax_prepare
+// fused pipeline: one nibble per candidate draw instead of one bit (8 = owned, eligible, first occurrence; low 3 bits = the
+// class k_step counted the citizen in for the next step, 4 = already vaccinated), so that every shard can correct the global
+// class counts for the citizens chosen on other shards without a second exchange
+constexpr uint32_t FEXCH_WORDS    = 8 + ESIM_VAX_SHARD_DRAWS / 8;
 
 constexpr uint32_t KTRACE_STEPS = 1024, KTRACE_KERNELS = 4;   // kernels: 0 = update / step, 1 = expose, 2 = pt, 3 = tail
 
@@ -51,15 +55,20 @@ __host__ __device__ inline uint32_t cnt_slot(uint32_t fused, uint32_t t) { retur
 // Every shard owns a mailbox in its own HBM that its peers write into:
 //   flag_a[r]  time step for which peer r has finished pushing its infected counts into this shard's count buffer
 //   flag_b[r]  time step for which peer r's tail vector has arrived
-//   vec_b[t & 1][r][EXCH_WORDS]  peer r's tail vector of step t (double-buffered: a peer can be at most one step ahead)
+//   flag_c[r]  (fused) peer r's tail has finished taking the citizens it vaccinated out of this shard's count buffer
+//   vec_b[t & 1][r][..]  peer r's tail vector of step t (double-buffered: a peer can be at most one step ahead)
+// Three-kernel pipeline: flags hold t.  Fused pipeline: flags hold t + 1 (its boot pass runs as "step 0"), flag_a is raised by
+// k_step of step t for the counts of step t + 1.
 constexpr uint32_t MAX_WORLD      = 8;
 constexpr uint32_t MAIL_FLAG_A    = 0;
 constexpr uint32_t MAIL_FLAG_B    = MAX_WORLD;
+constexpr uint32_t MAIL_FLAG_C    = 2 * MAX_WORLD;
 constexpr uint32_t MAIL_VEC_B     = 32;
-constexpr uint32_t MAIL_WORDS     = MAIL_VEC_B + 2 * MAX_WORLD * (8 + ESIM_VAX_SHARD_DRAWS / 32);
+constexpr uint32_t MAIL_VEC_STRIDE = FEXCH_WORDS;   // >= EXCH_WORDS: both pipelines use the same mailbox
+constexpr uint32_t MAIL_WORDS     = MAIL_VEC_B + 2 * MAX_WORLD * MAIL_VEC_STRIDE;
 struct PeerView {                       // lives in device memory: kernel parameters stay small
     uint32_t n_bldg[MAX_WORLD];         // peers' n_bldg (their room cells start there)
-    uint32_t* cnt[2][MAX_WORLD];        // peers' count buffers
+    uint32_t* cnt[3][MAX_WORLD];        // peers' count buffers
     uint32_t* mail[MAX_WORLD];          // peers' mailboxes ([rank] = own)
 };
 
@@ -116,6 +125,7 @@ struct DevView {
                            // cnt[t & 1] while k_update zeroes cnt[(t + 1) & 1] for the next step.  Fused pipeline: k_step of
                            // step t reads cnt[t % 3], accumulates step t + 1 into cnt[(t + 1) % 3] and zeroes cnt[(t + 2) % 3].
     uint32_t fused;        // 1 = fused pipeline (three count buffers)
+    uint32_t boot;         // fused pipeline, boot pass: k_update counts step Ctrl::t + 1 (Ctrl::t is still 0)
     const unsigned long long* thr;  // [2][256] integer trial thresholds
     // public transport
     const uint32_t* route_off;   // [n_routes + 1]
@@ -130,7 +140,7 @@ struct DevView {
     uint32_t n_shared_b, n_shared_r;   // the first cells of the building / room ranges exist on every shard
     const PeerView* peer;        // device memory, valid when p2p
     uint32_t world;              // number of shards (1 = the whole population is here)
-    uint32_t* exch;              // [EXCH_WORDS] second exchange buffer of a sharded step
+    uint32_t* exch;              // [FEXCH_WORDS] second exchange buffer of a sharded step
     uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] candidate citizen of every draw of this step
     uint32_t* tally_partial;     // [n_update_blocks * 8] per-block S,E,I,R,V partial sums of k_update
     uint32_t n_update_blocks;
@@ -152,7 +162,7 @@ void launch_vax_prepare(const DevView& v, cudaStream_t s);  // sharded runs only
 // fused pipeline (single shard): k_step = apply_exposures of step t + generate_exposures of step t + 1 in one pass
 void launch_step_fused(const DevView& v, cudaStream_t s);
 void launch_tail_fused(const DevView& v, cudaStream_t s);
-void launch_boot_fused(const DevView& v, cudaStream_t s);   // after import: k_update of step 1 + the first schedule
+void launch_boot_fused(const DevView& v, cudaStream_t s);   // once, with Ctrl::t == 0: k_update counts step 1, the tail runs as "step 0"
 uint32_t step_blocks(uint32_t n_pad);
 void launch_flush_sweep(const void* scratch, size_t bytes, uint32_t* sink, cudaStream_t s);   // ESIM_CFG_FLUSH_L2
 int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as int

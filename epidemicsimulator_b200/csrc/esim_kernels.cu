@@ -83,20 +83,35 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 // An infected citizen standing in a cell that other shards reference adds itself to their count buffers as well
 // (system-scope reductions over NVLink); after the flag exchange every shard holds the global count of its shared cells.
-__device__ __forceinline__ bool push_to_peers(const DevView& v, uint32_t parity, uint32_t cell) {
+// `slot` = count buffer of the step being counted; `delta` = +1 (an infected occupant) or -1 (it has just been vaccinated)
+__device__ __forceinline__ bool push_to_peers(const DevView& v, uint32_t slot, uint32_t cell, uint32_t delta = 1u) {
     const PeerView& pv = *v.peer;
     if (cell < v.n_shared_b) {
         for (uint32_t p = 0; p < v.world; ++p)
-            if (p != v.rank) atomicAdd_system(pv.cnt[parity][p] + cell, 1u);
+            if (p != v.rank) atomicAdd_system(pv.cnt[slot][p] + cell, delta);
         return true;
     }
     if (cell >= v.n_bldg && cell - v.n_bldg < v.n_shared_r) {
         const uint32_t r = cell - v.n_bldg;
         for (uint32_t p = 0; p < v.world; ++p)
-            if (p != v.rank) atomicAdd_system(pv.cnt[parity][p] + pv.n_bldg[p] + r, 1u);
+            if (p != v.rank) atomicAdd_system(pv.cnt[slot][p] + pv.n_bldg[p] + r, delta);
         return true;
     }
     return false;
+}
+// the last block of a grid to get here tells every peer that this shard's pushes for step `value` are complete.  One thread
+// fences for its block after the barrier; the fence is system-wide only if the block really wrote to a peer.
+__device__ __forceinline__ void publish_counts_done(const DevView& v, bool pushed, uint32_t value) {
+    const int any_pushed = __syncthreads_or(pushed);
+    if (threadIdx.x == 0) {
+        if (any_pushed) __threadfence_system(); else __threadfence();
+        if (atomicAdd(&v.ctrl->blocks_done, 1u) == gridDim.x - 1u) {
+            v.ctrl->blocks_done = 0;
+            __threadfence_system();
+            for (uint32_t p = 0; p < v.world; ++p)
+                if (p != v.rank) st_release_sys(v.peer->mail[p] + MAIL_FLAG_A + v.rank, value);
+        }
+    }
 }
 // thread 0 of the block waits until every peer's flag has reached `t`; bounded, so that a lost peer raises an error
 // instead of hanging the GPU
@@ -146,7 +161,7 @@ __device__ __forceinline__ bool update_phase(const DevView& v, const Ctrl* __res
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
     const uint4 none4 = make_uint4(0u, 0u, 0u, 0u);   // quads past the end: an all-zero word adds nothing to the cumulative counts
-    const uint32_t t = c->t, at_work = c->at_work;
+    const uint32_t t = c->t + v.boot, at_work = c->at_work;
     const uint32_t vax_all = c->vax_all_pending, vax_start = c->vax_start_step;
     // riders only count on their bus (simulator.rs:181-198): while public transport runs, a rider is never "present"
     const uint32_t rider_mask = c->pt_mode != ESIM_PT_NONE ? CS_USES_PT : 0u;
@@ -201,11 +216,11 @@ __device__ __forceinline__ bool update_phase(const DevView& v, const Ctrl* __res
                     if (code >= i_lo && code < e_lo && (w[k] & rider_mask) == 0u) {
                         const uint32_t cell = pos[((q0 + u * T) << 2) + (uint32_t)k];
                         atomicAdd(&cnt[cell], 1u);
-                        if (v.p2p) pushed |= push_to_peers(v, t & 1u, cell);
+                        if (v.p2p) pushed |= push_to_peers(v, cnt_slot(v.fused, t), cell);
                         if (cell >= v.n_bldg) {
                             const uint32_t school = v.room_parent[cell - v.n_bldg];
                             atomicAdd(&cnt[school], 1u);
-                            if (v.p2p) pushed |= push_to_peers(v, t & 1u, school);
+                            if (v.p2p) pushed |= push_to_peers(v, cnt_slot(v.fused, t), school);
                         }
                     }
                 }
@@ -231,23 +246,9 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     __shared__ uint32_t s_cnt[4];
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
-    const uint32_t t = c->t;
+    const uint32_t t = c->t + v.boot;
     const bool pushed = update_phase(v, c, s_cnt);
-    if (v.p2p && (v.n_shared_b | v.n_shared_r)) {
-        // The last block to finish tells every peer that this shard's counts of step t are complete.  One thread fences for
-        // its block after the barrier (the pattern of a cooperative grid sync); the fence is system-wide only if the block
-        // really wrote to a peer.
-        const int any_pushed = __syncthreads_or(pushed);
-        if (threadIdx.x == 0) {
-            if (any_pushed) __threadfence_system(); else __threadfence();
-            if (atomicAdd(&v.ctrl->blocks_done, 1u) == gridDim.x - 1u) {
-                v.ctrl->blocks_done = 0;
-                __threadfence_system();
-                for (uint32_t p = 0; p < v.world; ++p)
-                    if (p != v.rank) st_release_sys(v.peer->mail[p] + MAIL_FLAG_A + v.rank, t);
-            }
-        }
-    }
+    if (v.p2p && (v.n_shared_b | v.n_shared_r)) publish_counts_done(v, pushed, t);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -387,7 +388,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __constant__ int g_pf = 1;        // ESIM_STEP_PF=0 switches the L2 prefetches off (experiments)
 
 template <bool EAGER, bool AT_WORK>
-__device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt) {
+__device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt, bool& pushed) {
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
@@ -476,7 +477,12 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
                     if (code >= i_lo && code < e_lo && (w[u][k] & rider_mask) == 0u) {
                         const uint32_t cell = __ldg(&pos_next[((u ? q1 : q0) << 2) + (uint32_t)k]);
                         atomicAdd(&cnt_next[cell], 1u);
-                        if (cell >= v.n_bldg) atomicAdd(&cnt_next[__ldg(&v.room_parent[cell - v.n_bldg])], 1u);
+                        if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), cell);
+                        if (cell >= v.n_bldg) {
+                            const uint32_t school = __ldg(&v.room_parent[cell - v.n_bldg]);
+                            atomicAdd(&cnt_next[school], 1u);
+                            if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), school);
+                        }
                     }
                 }
             }
@@ -652,12 +658,19 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
     const uint32_t kt_t = c->t;
+    if (v.p2p) {
+        // peers' infected occupants of step t (pushed by their k_step of step t - 1) and their vaccination corrections
+        // (tail of step t - 1) have landed in this shard's count buffer
+        if (v.n_shared_b | v.n_shared_r) { wait_for_peers(v, MAIL_FLAG_A, kt_t); wait_for_peers(v, MAIL_FLAG_C, kt_t); }
+    }
     kt.begin(v, kt_t, 0);
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
-    const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true>(v, c, s_cnt) : step_stream<true, false>(v, c, s_cnt))
-                                     : (at_work ? step_stream<false, true>(v, c, s_cnt) : step_stream<false, false>(v, c, s_cnt));
+    bool pushed = false;
+    const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true>(v, c, s_cnt, pushed) : step_stream<true, false>(v, c, s_cnt, pushed))
+                                     : (at_work ? step_stream<false, true>(v, c, s_cnt, pushed) : step_stream<false, false>(v, c, s_cnt, pushed));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+    if (v.p2p && (v.n_shared_b | v.n_shared_r)) publish_counts_done(v, pushed, kt_t + 1u);
     kt.end(v, kt_t, 0);
 }
 __global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) { k_step_body<3>(v); }
@@ -876,7 +889,12 @@ __device__ __forceinline__ void vaccinate_counted(const DevView& v, TailSmem& sm
         uint32_t* cnt_next = v.cnt[cnt_slot(1u, t1)];
         const uint32_t cell = sm.c.next_at_work ? v.work_cell[local] : v.home_cell[local];
         atomicSub(&cnt_next[cell], 1u);
-        if (cell >= v.n_bldg) atomicSub(&cnt_next[v.room_parent[cell - v.n_bldg]], 1u);
+        if (v.p2p) push_to_peers(v, cnt_slot(1u, t1), cell, 0xFFFFFFFFu);
+        if (cell >= v.n_bldg) {
+            const uint32_t school = v.room_parent[cell - v.n_bldg];
+            atomicSub(&cnt_next[school], 1u);
+            if (v.p2p) push_to_peers(v, cnt_slot(1u, t1), school, 0xFFFFFFFFu);
+        }
     }
 }
 
@@ -899,13 +917,28 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
     if (tid < 8) { sm.tally[tid] = 0; sm.fix[tid] = 0; }
     __syncthreads();
     const bool sharded = !FUSED && v.world > 1;
+    const bool fsharded = FUSED && v.world > 1;   // fused pipeline over peer-to-peer shards
+    if (fsharded) {
+        // vax_prepare_fused has sent this shard's vector; add up the vectors of all shards in a fixed order
+        wait_for_peers(v, MAIL_FLAG_B, sm.c.t + 1u);
+        const uint32_t* mail = v.peer->mail[v.rank] + MAIL_VEC_B + (sm.c.t & 1u) * MAX_WORLD * MAIL_VEC_STRIDE;
+        for (uint32_t h = tid; h < FEXCH_WORDS; h += NT) {
+            uint32_t sum = 0;
+            for (uint32_t p = 0; p < v.world; ++p) sum += __ldcg(mail + p * MAIL_VEC_STRIDE + h);
+            v.exch[h] = sum;
+        }
+        __syncthreads();
+        if (tid < 5) sm.tally[tid] = __ldcg(&v.exch[tid]);          // class counts of step t + 1 as k_step saw them, all shards
+        if (tid == 5) sm.c.new_exp_bldg = __ldcg(&v.exch[5]);
+        if (tid == 6) sm.c.new_exp_pt = __ldcg(&v.exch[6]);
+    }
     if (sharded && v.p2p) {
         // sum the tail vectors of all shards (fixed order) into the exchange buffer the code below reads
         wait_for_peers(v, MAIL_FLAG_B, sm.c.t);
-        const uint32_t* mail = v.peer->mail[v.rank] + MAIL_VEC_B + (sm.c.t & 1u) * MAX_WORLD * EXCH_WORDS;
+        const uint32_t* mail = v.peer->mail[v.rank] + MAIL_VEC_B + (sm.c.t & 1u) * MAX_WORLD * MAIL_VEC_STRIDE;
         for (uint32_t h = tid; h < EXCH_WORDS; h += NT) {
             uint32_t sum = 0;
-            for (uint32_t p = 0; p < v.world; ++p) sum += __ldcg(mail + p * EXCH_WORDS + h);
+            for (uint32_t p = 0; p < v.world; ++p) sum += __ldcg(mail + p * MAIL_VEC_STRIDE + h);
             v.exch[h] = sum;
         }
         __syncthreads();
@@ -915,7 +948,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         if (tid < 5) sm.tally[tid] = __ldcg(&v.exch[tid]);
         if (tid == 5) sm.c.new_exp_bldg = __ldcg(&v.exch[5]);
         if (tid == 6) sm.c.new_exp_pt = __ldcg(&v.exch[6]);
-    } else {   // S/E/I/R/V = sum of k_update's per-block partials (8 words per block, 5 used)
+    } else if (!fsharded) {   // S/E/I/R/V = sum of k_update's per-block partials (8 words per block, 5 used)
         uint32_t part = 0;
         for (uint32_t z = tid; z < n_partial_blocks * 8u; z += NT) part += __ldcg(&v.tally_partial[z]);
         // threads tid, tid+8, ... hold the same counter: NT is a multiple of 8
@@ -924,7 +957,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         if (lane < 8 && part) atomicAdd(&sm.tally[lane], part);
     }
     __syncthreads();
-    if (!sharded && tid == 0) {
+    if (!sharded && !fsharded && tid == 0) {
         uint32_t cls[5];
         classes_from_cumulative(sm.tally, v.n_pad, v.n, cls);
         for (int k = 0; k < 5; ++k) sm.tally[k] = cls[k];
@@ -970,7 +1003,58 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
     const uint32_t K = sm.k;
     if (K > 0) {
         const uint32_t vax_start = sm.c.vax_start_step;
-        if (sharded && !(K == sm.c.n_elig || K > MAX_VAX_PER_STEP)) {
+        if (fsharded) {
+            // One nibble per candidate draw, summed over the shards (only the owner of a candidate writes its nibble): bit 3 =
+            // eligible first occurrence, bits 0-2 = the class k_step counted the citizen in for step t + 1.  The first K
+            // marked draws are the picks; every shard corrects the global class counts for all of them and applies its own.
+            const uint32_t* nib = v.exch + 8;
+            constexpr uint32_t NW = VAX_SHARD_DRAWS / 8;   // nibble words
+            uint32_t pc = 0;
+            if (tid < NW) pc = __popc(__ldcg(&nib[tid]) & 0x88888888u);
+            uint32_t incl = pc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += y;
+            }
+            if (lane == 31) sm.scan[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                const uint32_t x = lane < NT / 32 ? sm.scan[lane] : 0u;
+                uint32_t inc2 = x;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, inc2, d);
+                    if (lane >= (uint32_t)d) inc2 += y;
+                }
+                sm.scan[lane] = inc2 - x;
+                if (lane == 31) sm.batch_total = inc2;
+            }
+            __syncthreads();
+            if (tid < NW) {
+                const uint32_t word = __ldcg(&nib[tid]);
+                uint32_t rank = sm.scan[wid] + (incl - pc);   // marked draws before this word
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    const uint32_t nb = (word >> (4u * k)) & 15u;
+                    if (!(nb & 8u)) continue;
+                    if (rank < K) {
+                        const uint32_t cls = nb & 7u;
+                        const uint32_t cand = __ldcg(&v.vax_cand[tid * 8u + k]);
+                        const uint32_t local = cand - v.mp.shard_lo;
+                        if (local < v.n) vaccinate_counted(v, sm, local);        // the owner: state word + count buffers
+                        else if (cls < 4u) atomicAdd(&sm.fix[cls], 1u);           // somebody else's citizen: class counts only
+                    }
+                    ++rank;
+                }
+            }
+            if (tid == 0) {
+                // more draws needed than VAX_SHARD_DRAWS: in practice only when the whole eligible set is chosen (a programme that
+                // started with fewer candidates than the hourly rate), which the sharded pipelines do not support
+                if (sm.batch_total < K) sm.c.error = (uint32_t)(-ESIM_ERR_SIMULATION);
+                sm.accepted = min(K, sm.batch_total);
+            }
+        } else if (sharded && !(K == sm.c.n_elig || K > MAX_VAX_PER_STEP)) {
             // every shard marked, in the all-reduced mask, the draws whose candidate it owns and that are eligible first
             // occurrences; the first K set bits are the picks, and each shard applies the ones it owns
             const uint32_t* mask = v.exch + 8;
@@ -1120,9 +1204,10 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         s.vaccine_eligible = c->vax_some ? c->n_elig : 0u;
         s.vaccinated_now = sm.accepted;
         sm.stats = s;
-        // StatisticEntry::disease_exists (statistics.rs:289-291)
-        if (!(s.exposed != 0 || s.infected != 0 || s.susceptible != 0)) c->finished = 1;
+        // StatisticEntry::disease_exists (statistics.rs:289-291); the boot pass of the fused pipeline (t == 0) records nothing
+        if (!(FUSED && t == 0u) && !(s.exposed != 0 || s.infected != 0 || s.susceptible != 0)) c->finished = 1;
         const uint32_t nt = t + 1;
+        uint32_t fused_next_susceptible = 0;
         c->mask_cur = c->mask_kind;   // the exposures of the next step see the status computed by step t (simulator.rs:262-268)
         if (FUSED) {
             // final class counts of step t + 1: k_step's counts, the public-transport exposures of step t (counted Susceptible,
@@ -1130,6 +1215,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
             uint32_t n1[5] = {sm.tally[0] - c->new_exp_pt, sm.tally[1] + c->new_exp_pt, sm.tally[2], sm.tally[3], sm.tally[4]};
             for (int k = 0; k < 5; ++k) { n1[k] -= sm.fix[k]; n1[4] += sm.fix[k]; }
             for (int k = 0; k < 5; ++k) c->tally[k] = n1[k];
+            fused_next_susceptible = n1[0];
             // apply_interventions of step t + 1 only looks at the infected share of these counts (simulator.rs:456-458)
             const double p1 = (double)n1[2] / (double)(n1[0] + n1[1] + n1[2] + n1[3] + n1[4]);
             c->vax_event = update_interventions(c, v.mp, p1) ? 1u : 0u;
@@ -1162,7 +1248,8 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         // froze the riders on their buses), the rest of that graph must not run
         if (!v.next_has_pt && c->pt_mode != ESIM_PT_NONE && v.n_routes) c->abort_graph = 1;
         // k_expose requests the cell ids together with the state words while most citizens are susceptible
-        c->eager_expose = (uint64_t)s.susceptible * 4u > (uint64_t)(s.susceptible + s.exposed + s.infected + s.recovered + s.vaccinated) ? 1u : 0u;
+        const uint32_t s_next = FUSED ? fused_next_susceptible : s.susceptible;
+        c->eager_expose = (uint64_t)s_next * 4u > (uint64_t)v.mp.n_global_citizens ? 1u : 0u;
     }
     __syncthreads();
     // write the control block and the statistics entry back, coalesced
@@ -1252,7 +1339,7 @@ __device__ __forceinline__ void vax_prepare_phase(const DevView& v, uint32_t* dy
     if (v.p2p) {
         // hand the vector to every shard (including this one) and raise the arrival flag
         __syncthreads();
-        const uint32_t slot = MAIL_VEC_B + ((t & 1u) * MAX_WORLD + v.rank) * EXCH_WORDS;
+        const uint32_t slot = MAIL_VEC_B + ((t & 1u) * MAX_WORLD + v.rank) * MAIL_VEC_STRIDE;
         for (uint32_t p = 0; p < v.world; ++p)
             for (uint32_t h = tid; h < EXCH_WORDS; h += TAIL_THREADS) v.peer->mail[p][slot + h] = v.exch[h];
         __threadfence_system();
@@ -1285,7 +1372,99 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
     kt.end(v, kt_t, 2);
 }
 
-// fused pipeline: v.n_update_blocks is the grid of k_step here (set by the launcher)
+// Fused pipeline over peer-to-peer shards, first part of the tail of step t: this shard's vector
+//   [0..4] class counts of step t + 1 as k_step counted them   [5..6] building / public-transport exposures of step t
+//   [8 + j/8] nibble j%8: candidate draw j of the vaccination stream is owned by this shard, eligible and the first
+//   occurrence of its citizen (bit 3), and the class the citizen was counted in (bits 0-2, 4 = already vaccinated)
+// goes to every shard's mailbox.  `dyn_smem`: at least VP_SMEM bytes.  `n_blocks`: grid of the kernel that left the partial sums.
+__device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dyn_smem, uint32_t n_blocks) {
+    constexpr uint32_t NW = VAX_SHARD_DRAWS / 8;
+    uint32_t* keys = dyn_smem;                 // [VP_HT]
+    uint32_t* minj = dyn_smem + VP_HT;         // [VP_HT]
+    uint32_t* nib = dyn_smem + 2 * VP_HT;      // [NW]
+    __shared__ uint32_t s_tally[8];
+    const Ctrl* __restrict__ c = v.ctrl;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t t = c->t;
+    // update_status of step t has already run (previous tail): the programme is active in this step iff vax_some
+    const bool vaccinate = c->vax_some != 0 && t != 0u;
+    if (tid < 8) s_tally[tid] = 0;
+    if (vaccinate) for (uint32_t h = tid; h < VP_HT; h += TAIL_THREADS) { keys[h] = HT_EMPTY; minj[h] = 0xFFFFFFFFu; }
+    for (uint32_t h = tid; h < NW; h += TAIL_THREADS) nib[h] = 0;
+    __syncthreads();
+    {
+        uint32_t part = 0;
+        for (uint32_t z = tid; z < n_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        part += __shfl_xor_sync(0xffffffffu, part, 16);
+        if (lane < 8 && part) atomicAdd(&s_tally[lane], part);
+    }
+    // the snapshot of a Vaccination event raised for step t is taken by this tail: everybody Susceptible now is eligible, which
+    // is what vax_eligible(w, t) says (nobody can have been exposed after step t yet)
+    const uint32_t vax_start = c->vax_event ? t : c->vax_start_step;
+    constexpr int PER = VAX_SHARD_DRAWS / TAIL_THREADS;
+    uint32_t wv[PER], slot[PER];
+    bool owned[PER];
+    if (vaccinate) {
+        uint32_t cands[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {   // all candidate draws and state-word gathers of the thread in flight together
+            const uint32_t j = tid * PER + q;
+            cands[q] = vax_candidate(((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo, j, t, v.mp.n_global_citizens);
+            v.vax_cand[j] = cands[q];
+            const uint32_t local = cands[q] - v.mp.shard_lo;
+            owned[q] = local < v.n;
+            wv[q] = owned[q] ? __ldcg(&v.cstate[local]) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const uint32_t j = tid * PER + q;
+            slot[q] = 0;
+            if (owned[q]) {
+                uint32_t h = (cands[q] * 2654435761u) >> 20 & (VP_HT - 1);
+                while (true) {
+                    const uint32_t prev = atomicCAS(&keys[h], HT_EMPTY, cands[q]);
+                    if (prev == HT_EMPTY || prev == cands[q]) break;
+                    h = (h + 1) & (VP_HT - 1);
+                }
+                slot[q] = h;
+                atomicMin(&minj[h], j);
+            }
+        }
+    }
+    __syncthreads();
+    if (vaccinate) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const uint32_t j = tid * PER + q;
+            if (owned[q] && minj[slot[q]] == j && vax_eligible(wv[q], vax_start)) {
+                const uint32_t cls = (wv[q] & CS_VACCINATED) ? 4u : (uint32_t)status_at(wv[q], t + 1u, v.mp.exposed_time, v.mp.infected_time);
+                atomicOr(&nib[j >> 3], (8u | cls) << (4u * (j & 7u)));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t cls[5];
+        classes_from_cumulative(s_tally, v.n_pad, v.n, cls);
+        for (int k = 0; k < 5; ++k) v.exch[k] = cls[k];
+    }
+    if (tid == 5) v.exch[5] = c->new_exp_bldg;
+    if (tid == 6) v.exch[6] = c->new_exp_pt;
+    if (tid == 7) v.exch[7] = 0;
+    for (uint32_t h = tid; h < NW; h += TAIL_THREADS) v.exch[8 + h] = nib[h];
+    __syncthreads();
+    // hand the vector to every shard (including this one) and raise the arrival flag
+    const uint32_t slot_v = MAIL_VEC_B + ((t & 1u) * MAX_WORLD + v.rank) * MAIL_VEC_STRIDE;
+    for (uint32_t p = 0; p < v.world; ++p)
+        for (uint32_t h = tid; h < FEXCH_WORDS; h += TAIL_THREADS) v.peer->mail[p][slot_v + h] = v.exch[h];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < v.world && tid != v.rank) st_release_sys(v.peer->mail[tid] + MAIL_FLAG_B + v.rank, t + 1u);
+    __syncthreads();
+}
+
+// fused pipeline: v.n_update_blocks is the grid of the kernel that left the partial sums (k_step, or k_update in the boot pass)
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail_fused(const DevView v) {
     KTrace kt; kt.start(v);
     pdl_prologue();
@@ -1294,35 +1473,15 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_fused(const DevView v) {
     if (v.ctrl->finished | v.ctrl->abort_graph) return;
     const uint32_t kt_t = v.ctrl->t;
     kt.begin(v, kt_t, 3);
+    if (v.world > 1) vax_prepare_fused(v, dyn_smem, v.n_update_blocks);
     tail_phase<TAIL_THREADS, true>(v, dyn_smem, sm, v.n_update_blocks);
-    kt.end(v, kt_t, 3);
-}
-
-// fused pipeline, once after the import: k_update has counted step 1; this turns its partial sums into Ctrl::tally, runs
-// update_status of step 1 and lays out the schedule of steps 1 and 2 (everybody starts at home, citizen.rs:156-160)
-__global__ void __launch_bounds__(TAIL_THREADS) k_boot_fused(const DevView v) {
-    __shared__ uint32_t s_tally[8];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    if (tid < 8) s_tally[tid] = 0;
-    __syncthreads();
-    uint32_t part = 0;
-    for (uint32_t z = tid; z < v.n_update_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    part += __shfl_xor_sync(0xffffffffu, part, 16);
-    if (lane < 8 && part) atomicAdd(&s_tally[lane], part);
-    __syncthreads();
-    if (tid == 0) {
-        Ctrl* c = v.ctrl;
-        uint32_t cls[5];
-        classes_from_cumulative(s_tally, v.n_pad, v.n, cls);
-        for (int k = 0; k < 5; ++k) c->tally[k] = cls[k];
-        c->mask_cur = c->mask_kind;
-        const double p1 = (double)cls[2] / (double)(cls[0] + cls[1] + cls[2] + cls[3] + cls[4]);
-        c->vax_event = update_interventions(c, v.mp, p1) ? 1u : 0u;
-        c->at_work = 0; c->pt_mode = ESIM_PT_NONE;            // hour 1
-        c->next_at_work = 0; c->next_pt_mode = ESIM_PT_NONE;  // hour 2, with or without lockdown
-        c->eager_expose = (uint64_t)cls[0] * 4u > (uint64_t)v.n ? 1u : 0u;
+    if (v.world > 1 && (v.n_shared_b | v.n_shared_r)) {
+        // the corrections this tail pushed into peers' count buffers are complete
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < v.world && threadIdx.x != v.rank) st_release_sys(v.peer->mail[threadIdx.x] + MAIL_FLAG_C + v.rank, kt_t + 1u);
     }
+    kt.end(v, kt_t, 3);
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
@@ -1529,7 +1688,7 @@ uint32_t step_blocks(uint32_t n_pad) {
     return blocks_for(g_step_tma ? n_pad >> 2 : (n_pad + 7u) >> 3, STEP_THREADS, (uint32_t)sm_count() * (uint32_t)g_step_blocks_per_sm);
 }
 void launch_step_fused(const DevView& v, cudaStream_t s) {
-    if (g_step_tma) launch_step_kernel(k_step_tma, step_blocks(v.n_pad), STEP_THREADS, sizeof(StepSmem), s, v);
+    if (g_step_tma && !v.p2p) launch_step_kernel(k_step_tma, step_blocks(v.n_pad), STEP_THREADS, sizeof(StepSmem), s, v);
     else if (g_step_occ4) launch_step_kernel(k_step_occ4, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
     else launch_step_kernel(k_step, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
 }
@@ -1539,8 +1698,12 @@ void launch_tail_fused(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);
 }
 void launch_boot_fused(const DevView& v, cudaStream_t s) {
-    launch_update(v, s);
-    k_boot_fused<<<1, TAIL_THREADS, 0, s>>>(v);
+    // Ctrl::t == 0: k_update counts step 1 (class tally, infected occupants, pushes to peers), then the tail runs as "step 0":
+    // it records nothing, turns the partial sums into Ctrl::tally, runs update_status of step 1 and lays out the schedule
+    DevView vv = v;
+    vv.boot = 1;
+    launch_update(vv, s);
+    launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);   // n_update_blocks = grid of k_update
 }
 void launch_vax_prepare(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_vax_prepare, 1, TAIL_THREADS, VP_SMEM, s, v);

@@ -233,18 +233,23 @@ def test_error_paths():
 def test_timed_steps_equal_graph_steps():
     pop = synthetic_population(n_areas=50, areas_per_school=10)
     cfg = dict(exposure_chance=0.01, seed=8)
-    a = _sim(pop, flags=_abi.CFG_FLUSH_L2, **cfg)
+    a = _sim(pop, flags=_abi.CFG_FLUSH_L2 | _abi.CFG_TIME_KERNELS, **cfg)   # an event between every two kernels
     b = _sim(pop, **cfg)
     c = _sim(pop, flags=_abi.CFG_NO_GRAPH, **cfg)
+    d = _sim(pop, flags=_abi.CFG_FLUSH_L2, **cfg)                          # events around the whole step only
     for _ in range(100):
         a.step(timed=True)
+        d.step(timed=True)
     b.run(100)
     for _ in range(100):
         c.step()
     assert np.array_equal(a.statistics(), b.statistics()) and np.array_equal(a.statistics(), c.statistics())
+    assert np.array_equal(a.statistics(), d.statistics())
     t = a.timings()
     assert t["steps"] == 100 and t["total"] > 0 and abs(t["generate_exposures"] + t["apply_exposures"] + t["apply_interventions"] - t["total"]) < 1e-6
-    a.close(); b.close(); c.close()
+    td = d.timings()
+    assert td["steps"] == 100 and 0 < td["total"] < t["total"]   # no per-kernel events: less stream time per step
+    a.close(); b.close(); c.close(); d.close()
 
 
 @pytest.mark.parametrize("onset", [8, 16, 11, 20])

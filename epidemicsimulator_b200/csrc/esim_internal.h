@@ -64,8 +64,13 @@ constexpr uint32_t MAIL_FLAG_A    = 0;
 constexpr uint32_t MAIL_FLAG_B    = MAX_WORLD;
 constexpr uint32_t MAIL_FLAG_C    = 2 * MAX_WORLD;
 constexpr uint32_t MAIL_VEC_B     = 32;
-constexpr uint32_t MAIL_VEC_STRIDE = FEXCH_WORDS;   // >= EXCH_WORDS: both pipelines use the same mailbox
-constexpr uint32_t MAIL_WORDS     = MAIL_VEC_B + 2 * MAX_WORLD * MAIL_VEC_STRIDE;
+constexpr uint32_t MAIL_VEC_STRIDE = EXCH_WORDS;
+// Fused pipeline: the tail vectors travel as (value, tag) pairs written with one 8-byte store each (tag = t + 1); the receiver
+// spins on the tag of every pair it needs, so neither a system-wide fence nor a separate arrival flag is on the critical path.
+//   ll[t & 1][r][FEXCH_WORDS] pairs of peer r
+constexpr uint32_t MAIL_LL        = MAIL_VEC_B + 2 * MAX_WORLD * MAIL_VEC_STRIDE;   // first word of the pair region (8-byte aligned)
+constexpr uint32_t MAIL_WORDS     = MAIL_LL + 2 * (2 * MAX_WORLD * FEXCH_WORDS);
+static_assert(MAIL_LL % 2 == 0, "pairs must be 8-byte aligned");
 struct PeerView {                       // lives in device memory: kernel parameters stay small
     uint32_t n_bldg[MAX_WORLD];         // peers' n_bldg (their room cells start there)
     uint32_t* cnt[3][MAX_WORLD];        // peers' count buffers
@@ -98,7 +103,7 @@ struct Ctrl {
     uint32_t next_at_work, next_pt_mode;
     uint32_t vax_event;      // update_status raised the Vaccination event for step t: the tail of step t takes the snapshot
     uint32_t vax_all_done;   // the whole eligible set has been vaccinated once: choosing all of it again changes nothing
-    uint32_t pad[1];
+    uint32_t pushed_any;     // fused peer-to-peer shards: k_step (or the boot k_update) added to a peer's count buffer
 };
 
 struct ModelParams {

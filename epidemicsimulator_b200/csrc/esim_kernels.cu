@@ -81,6 +81,19 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
     return x;
 }
+// (value, tag) pairs of the fused tail exchange: one 8-byte store / load each, so a pair is never seen half-written
+__device__ __forceinline__ void st_pair_sys(uint32_t* p, uint32_t value, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(value), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_pair_wait(const uint32_t* p, uint32_t tag, uint32_t* error_word) {
+    uint32_t value, seen, spins = 0;
+    while (true) {
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(value), "=r"(seen) : "l"(p) : "memory");
+        if (seen == tag) return value;
+        if (++spins > (1u << 22)) { *error_word = (uint32_t)(-ESIM_ERR_COMM); return 0u; }   // a lost peer raises an error
+        __nanosleep(32);
+    }
+}
 // An infected citizen standing in a cell that other shards reference adds itself to their count buffers as well
 // (system-scope reductions over NVLink); after the flag exchange every shard holds the global count of its shared cells.
 // `slot` = count buffer of the step being counted; `delta` = +1 (an infected occupant) or -1 (it has just been vaccinated)
@@ -116,15 +129,12 @@ __device__ __forceinline__ void publish_counts_done(const DevView& v, bool pushe
 // thread 0 of the block waits until every peer's flag has reached `t`; bounded, so that a lost peer raises an error
 // instead of hanging the GPU
 __device__ __forceinline__ void wait_for_peers(const DevView& v, uint32_t flag_base, uint32_t t) {
-    if (threadIdx.x == 0) {
-        const uint32_t* mail = v.peer->mail[v.rank];
-        for (uint32_t p = 0; p < v.world; ++p) {
-            if (p == v.rank) continue;
-            uint32_t spins = 0;
-            while (ld_acquire_sys(mail + flag_base + p) < t) {
-                if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_COMM); break; }
-                __nanosleep(64);
-            }
+    if (threadIdx.x < v.world && threadIdx.x != v.rank) {   // one lane per peer: the polls overlap
+        const uint32_t* flag = v.peer->mail[v.rank] + flag_base + threadIdx.x;
+        uint32_t spins = 0;
+        while (ld_acquire_sys(flag) < t) {
+            if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_COMM); break; }
+            __nanosleep(64);
         }
     }
     __syncthreads();
@@ -248,7 +258,10 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
     if (c->finished | c->abort_graph) return;
     const uint32_t t = c->t + v.boot;
     const bool pushed = update_phase(v, c, s_cnt);
-    if (v.p2p && (v.n_shared_b | v.n_shared_r)) publish_counts_done(v, pushed, t);
+    if (v.p2p && (v.n_shared_b | v.n_shared_r)) {
+        if (!v.fused) publish_counts_done(v, pushed, t);
+        else if (pushed) v.ctrl->pushed_any = 1u;   // boot pass of the fused pipeline: the tail fences before it sends
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -658,11 +671,10 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
     const uint32_t kt_t = c->t;
-    if (v.p2p) {
-        // peers' infected occupants of step t (pushed by their k_step of step t - 1) and their vaccination corrections
-        // (tail of step t - 1) have landed in this shard's count buffer
-        if (v.n_shared_b | v.n_shared_r) { wait_for_peers(v, MAIL_FLAG_A, kt_t); wait_for_peers(v, MAIL_FLAG_C, kt_t); }
-    }
+    // Peer-to-peer shards.  The peers' infected occupants of step t (pushed by their k_step of step t - 1) were fenced before
+    // they sent the tail vector this shard has already consumed; what may still be in flight are the corrections of their tail
+    // of step t - 1, which only exist once the vaccination programme runs (vax_some is latched and replicated).
+    if (v.p2p && (v.n_shared_b | v.n_shared_r) && c->vax_some) wait_for_peers(v, MAIL_FLAG_C, kt_t);
     kt.begin(v, kt_t, 0);
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
     bool pushed = false;
@@ -670,7 +682,7 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
                                      : (at_work ? step_stream<false, true>(v, c, s_cnt, pushed) : step_stream<false, false>(v, c, s_cnt, pushed));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
-    if (v.p2p && (v.n_shared_b | v.n_shared_r)) publish_counts_done(v, pushed, kt_t + 1u);
+    if (pushed) v.ctrl->pushed_any = 1u;   // the tail fences system-wide before it sends its vector
     kt.end(v, kt_t, 0);
 }
 __global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) { k_step_body<3>(v); }
@@ -889,12 +901,14 @@ __device__ __forceinline__ void vaccinate_counted(const DevView& v, TailSmem& sm
         uint32_t* cnt_next = v.cnt[cnt_slot(1u, t1)];
         const uint32_t cell = sm.c.next_at_work ? v.work_cell[local] : v.home_cell[local];
         atomicSub(&cnt_next[cell], 1u);
-        if (v.p2p) push_to_peers(v, cnt_slot(1u, t1), cell, 0xFFFFFFFFu);
+        bool pushed = false;
+        if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), cell, 0xFFFFFFFFu);
         if (cell >= v.n_bldg) {
             const uint32_t school = v.room_parent[cell - v.n_bldg];
             atomicSub(&cnt_next[school], 1u);
-            if (v.p2p) push_to_peers(v, cnt_slot(1u, t1), school, 0xFFFFFFFFu);
+            if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), school, 0xFFFFFFFFu);
         }
+        if (pushed) sm.fix[7] = 1u;   // this tail wrote into peers' count buffers
     }
 }
 
@@ -919,12 +933,13 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
     const bool sharded = !FUSED && v.world > 1;
     const bool fsharded = FUSED && v.world > 1;   // fused pipeline over peer-to-peer shards
     if (fsharded) {
-        // vax_prepare_fused has sent this shard's vector; add up the vectors of all shards in a fixed order
-        wait_for_peers(v, MAIL_FLAG_B, sm.c.t + 1u);
-        const uint32_t* mail = v.peer->mail[v.rank] + MAIL_VEC_B + (sm.c.t & 1u) * MAX_WORLD * MAIL_VEC_STRIDE;
-        for (uint32_t h = tid; h < FEXCH_WORDS; h += NT) {
+        // vax_prepare_fused has sent this shard's vector; add up the vectors of all shards in a fixed order, spinning on the tag
+        // of every pair (the nibbles only travel while the vaccination programme runs)
+        const uint32_t n_words = (sm.c.vax_some != 0 && sm.c.t != 0u) ? FEXCH_WORDS : 8u;
+        const uint32_t* mail = v.peer->mail[v.rank] + MAIL_LL + 2u * (sm.c.t & 1u) * MAX_WORLD * FEXCH_WORDS;
+        for (uint32_t h = tid; h < n_words; h += NT) {
             uint32_t sum = 0;
-            for (uint32_t p = 0; p < v.world; ++p) sum += __ldcg(mail + p * MAIL_VEC_STRIDE + h);
+            for (uint32_t p = 0; p < v.world; ++p) sum += ld_pair_wait(mail + 2u * (p * FEXCH_WORDS + h), sm.c.t + 1u, &v.ctrl->error);
             v.exch[h] = sum;
         }
         __syncthreads();
@@ -1191,6 +1206,13 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         }
     }
     __syncthreads();
+    if (fsharded && (v.n_shared_b | v.n_shared_r)) {
+        // tell the peers that the corrections this tail pushed into their count buffers (if any) are complete: their next k_step
+        // waits for it.  Raised before the scalar epilogue so that the flag travels while this block finishes.
+        if (sm.fix[7]) __threadfence_system();
+        __syncthreads();
+        if (tid < v.world && tid != v.rank) st_release_sys(v.peer->mail[tid] + MAIL_FLAG_C + v.rank, sm.c.t + 1u);
+    }
 
     if (tid == 0) {
         Ctrl* c = &sm.c;
@@ -1242,6 +1264,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
             c->tally[0] = c->tally[1] = c->tally[2] = c->tally[3] = c->tally[4] = 0;
         }
         c->t = nt;
+        c->pushed_any = 0;
         c->new_exp_bldg = 0; c->new_exp_pt = 0;
         c->vaccinated_now = sm.accepted;
         // a specialised day graph has no public-transport kernel in most slots: if the next hour needs one after all (lockdown
@@ -1444,23 +1467,25 @@ __device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dy
         }
     }
     __syncthreads();
+    __shared__ uint32_t s_head[8];
     if (tid == 0) {
         uint32_t cls[5];
         classes_from_cumulative(s_tally, v.n_pad, v.n, cls);
-        for (int k = 0; k < 5; ++k) v.exch[k] = cls[k];
+        for (int k = 0; k < 5; ++k) s_head[k] = cls[k];
+        s_head[5] = c->new_exp_bldg; s_head[6] = c->new_exp_pt; s_head[7] = 0;
     }
-    if (tid == 5) v.exch[5] = c->new_exp_bldg;
-    if (tid == 6) v.exch[6] = c->new_exp_pt;
-    if (tid == 7) v.exch[7] = 0;
-    for (uint32_t h = tid; h < NW; h += TAIL_THREADS) v.exch[8 + h] = nib[h];
     __syncthreads();
-    // hand the vector to every shard (including this one) and raise the arrival flag
-    const uint32_t slot_v = MAIL_VEC_B + ((t & 1u) * MAX_WORLD + v.rank) * MAIL_VEC_STRIDE;
-    for (uint32_t p = 0; p < v.world; ++p)
-        for (uint32_t h = tid; h < FEXCH_WORDS; h += TAIL_THREADS) v.peer->mail[p][slot_v + h] = v.exch[h];
-    __threadfence_system();
-    __syncthreads();
-    if (tid < v.world && tid != v.rank) st_release_sys(v.peer->mail[tid] + MAIL_FLAG_B + v.rank, t + 1u);
+    // hand the vector to every shard (including this one) as (value, tag) pairs; the nibbles only travel while the
+    // programme runs (every shard knows: the intervention state is replicated)
+    const uint32_t n_words = vaccinate ? FEXCH_WORDS : 8u;
+    const uint32_t slot_v = MAIL_LL + 2u * ((t & 1u) * MAX_WORLD + v.rank) * FEXCH_WORDS;
+    // The pairs double as "this shard's count pushes for step t + 1 are complete": the previous grid's remote reductions are
+    // visible to this grid (it waited for that grid), and the fence makes them precede the pairs for every observer.
+    if (c->pushed_any) __threadfence_system();
+    for (uint32_t h = tid; h < n_words; h += TAIL_THREADS) {
+        const uint32_t value = h < 8u ? s_head[h] : nib[h - 8u];
+        for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(v.peer->mail[p] + slot_v + 2u * h, value, t + 1u);
+    }
     __syncthreads();
 }
 
@@ -1475,12 +1500,6 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_fused(const DevView v) {
     kt.begin(v, kt_t, 3);
     if (v.world > 1) vax_prepare_fused(v, dyn_smem, v.n_update_blocks);
     tail_phase<TAIL_THREADS, true>(v, dyn_smem, sm, v.n_update_blocks);
-    if (v.world > 1 && (v.n_shared_b | v.n_shared_r)) {
-        // the corrections this tail pushed into peers' count buffers are complete
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < v.world && threadIdx.x != v.rank) st_release_sys(v.peer->mail[threadIdx.x] + MAIL_FLAG_C + v.rank, kt_t + 1u);
-    }
     kt.end(v, kt_t, 3);
 }
 

@@ -2,13 +2,14 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from functools import lru_cache
 from pathlib import Path
 
 from . import _abi
 
 PKG = Path(__file__).resolve().parent
-CUDA_LIB = PKG / "libesim_b200.so"
+CUDA_LIB = Path(os.environ["ESIM_B200_LIB"]) if os.environ.get("ESIM_B200_LIB") else PKG / "libesim_b200.so"   # override: A/B runs
 HOST_LIB = PKG / "libesim_host.so"
 
 

@@ -459,26 +459,34 @@ static void print_ktrace(EsimSim* s) {
     std::vector<unsigned long long> mn(s->ktrace_min.n), mx(s->ktrace_max.n);
     cudaMemcpy(mn.data(), s->ktrace_min.p, s->ktrace_min.bytes(), cudaMemcpyDeviceToHost);
     cudaMemcpy(mx.data(), s->ktrace_max.p, s->ktrace_max.bytes(), cudaMemcpyDeviceToHost);
-    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose", "pt", "tail"};
+    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose/xchg", "pt", "tail", "tail:send", "spare"};
     const uint32_t last = s->steps_done, first = last > KTRACE_STEPS - 2 ? last - (KTRACE_STEPS - 2) : 2;
-    double wait[KTRACE_KERNELS] = {}, run[KTRACE_KERNELS] = {}, gap[KTRACE_KERNELS] = {};
-    uint32_t cnt[KTRACE_KERNELS] = {}, gcnt[KTRACE_KERNELS] = {};
-    double span = 0; uint32_t nspan = 0;
-    unsigned long long prev_end = 0, prev_begin0 = 0;
-    for (uint32_t t = first; t <= last; ++t)
+    // everything relative to the end of slot 0 (k_update / k_step) of the same step
+    double run[KTRACE_KERNELS] = {}, b_rel[KTRACE_KERNELS] = {}, e_rel[KTRACE_KERNELS] = {}, wait[KTRACE_KERNELS] = {};
+    uint32_t cnt[KTRACE_KERNELS] = {};
+    double span = 0, next_gap = 0; uint32_t nspan = 0, ngap = 0;
+    unsigned long long prev_begin0 = 0, prev_tail_end = 0;
+    for (uint32_t t = first; t <= last; ++t) {
+        const uint32_t base = (t % KTRACE_STEPS) * KTRACE_KERNELS;
+        const unsigned long long b0 = mn[base * 2 + 1], e0 = mx[base];
+        if (b0 == ~0ull || e0 == 0 || e0 < b0) continue;
+        if (prev_begin0 && b0 > prev_begin0) { span += (double)(b0 - prev_begin0); nspan++; }
+        if (prev_tail_end && b0 > prev_tail_end) { next_gap += (double)(b0 - prev_tail_end); ngap++; }
+        prev_begin0 = b0;
         for (uint32_t k = 0; k < KTRACE_KERNELS; ++k) {
-            const uint32_t slot = (t % KTRACE_STEPS) * KTRACE_KERNELS + k;
-            const unsigned long long enter = mn[slot * 2], begin = mn[slot * 2 + 1], end = mx[slot];
+            const unsigned long long enter = mn[(base + k) * 2], begin = mn[(base + k) * 2 + 1], end = mx[base + k];
             if (begin == ~0ull || end == 0 || end < begin) continue;
-            wait[k] += (double)(begin - enter); run[k] += (double)(end - begin); cnt[k]++;
-            if (prev_end && begin >= prev_end) { gap[k] += (double)(begin - prev_end); gcnt[k]++; }
-            if (k == 0) { if (prev_begin0) { span += (double)(begin - prev_begin0); nspan++; } prev_begin0 = begin; }
-            prev_end = end;
+            run[k] += (double)(end - begin); cnt[k]++;
+            b_rel[k] += (double)begin - (double)e0; e_rel[k] += (double)end - (double)e0;
+            if (enter && enter <= begin) wait[k] += (double)(begin - enter);
+            if (k == 3) prev_tail_end = end;
         }
-    fprintf(stderr, "[esim] kernel timeline over steps %u..%u (ns): step-to-step %.0f\n", first, last, nspan ? span / nspan : 0.0);
+    }
+    fprintf(stderr, "[esim] kernel timeline over steps %u..%u (ns): step-to-step %.0f, tail end -> next step start %.0f\n", first, last,
+            nspan ? span / nspan : 0.0, ngap ? next_gap / ngap : 0.0);
     for (uint32_t k = 0; k < KTRACE_KERNELS; ++k)
-        if (cnt[k]) fprintf(stderr, "[esim]   %-12s n=%-5u run %8.0f  entry->start %8.0f  gap after predecessor %8.0f\n", nm[k], cnt[k],
-                            run[k] / cnt[k], wait[k] / cnt[k], gcnt[k] ? gap[k] / gcnt[k] : 0.0);
+        if (cnt[k]) fprintf(stderr, "[esim]   %-12s n=%-5u run %7.0f  begin %+8.0f  end %+8.0f (relative to the end of update/step)  entry->begin %7.0f\n",
+                            nm[k], cnt[k], run[k] / cnt[k], b_rel[k] / cnt[k], e_rel[k] / cnt[k], wait[k] / cnt[k]);
 }
 
 void esim_destroy(EsimSim* s) { if (s) print_ktrace(s); delete s; }

@@ -46,7 +46,7 @@ constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second ex
 // class counts for the citizens chosen on other shards without a second exchange
 constexpr uint32_t FEXCH_WORDS    = 8 + ESIM_VAX_SHARD_DRAWS / 8;
 
-constexpr uint32_t KTRACE_STEPS = 1024, KTRACE_KERNELS = 4;   // kernels: 0 = update / step, 1 = expose, 2 = pt, 3 = tail
+constexpr uint32_t KTRACE_STEPS = 1024, KTRACE_KERNELS = 6;   // 0 = update / step, 1 = expose or exchange wait, 2 = pt, 3 = tail, 4 = tail: loads -> vector sent, 5 = spare
 
 // index of the count buffer that holds the infected occupants of step t
 __host__ __device__ inline uint32_t cnt_slot(uint32_t fused, uint32_t t) { return fused ? t % 3u : t & 1u; }

@@ -400,7 +400,7 @@ constexpr uint32_t STEP_PF = 2;   // prefetch distance in iterations
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __constant__ int g_pf = 1;        // ESIM_STEP_PF=0 switches the L2 prefetches off (experiments)
 
-template <bool EAGER, bool AT_WORK>
+template <bool EAGER, bool AT_WORK, bool P2P>
 __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt, bool& pushed) {
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
@@ -490,11 +490,11 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
                     if (code >= i_lo && code < e_lo && (w[u][k] & rider_mask) == 0u) {
                         const uint32_t cell = __ldg(&pos_next[((u ? q1 : q0) << 2) + (uint32_t)k]);
                         atomicAdd(&cnt_next[cell], 1u);
-                        if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), cell);
+                        if (P2P) pushed |= push_to_peers(v, cnt_slot(1u, t1), cell);
                         if (cell >= v.n_bldg) {
                             const uint32_t school = __ldg(&v.room_parent[cell - v.n_bldg]);
                             atomicAdd(&cnt_next[school], 1u);
-                            if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), school);
+                            if (P2P) pushed |= push_to_peers(v, cnt_slot(1u, t1), school);
                         }
                     }
                 }
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) k_step_tma(const DevView v) {
     kt.end(v, kt_t, 0);
 }
 
-template <int OCC>
+template <int OCC, bool P2P>
 __device__ __forceinline__ void k_step_body(const DevView& v) {
     KTrace kt; kt.start(v);
     pdl_prologue();
@@ -674,19 +674,21 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     // Peer-to-peer shards.  The peers' infected occupants of step t (pushed by their k_step of step t - 1) were fenced before
     // they sent the tail vector this shard has already consumed; what may still be in flight are the corrections of their tail
     // of step t - 1, which only exist once the vaccination programme runs (vax_some is latched and replicated).
-    if (v.p2p && (v.n_shared_b | v.n_shared_r) && c->vax_some) wait_for_peers(v, MAIL_FLAG_C, kt_t);
+    if (P2P && (v.n_shared_b | v.n_shared_r) && c->vax_some) wait_for_peers(v, MAIL_FLAG_C, kt_t);
     kt.begin(v, kt_t, 0);
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
     bool pushed = false;
-    const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true>(v, c, s_cnt, pushed) : step_stream<true, false>(v, c, s_cnt, pushed))
-                                     : (at_work ? step_stream<false, true>(v, c, s_cnt, pushed) : step_stream<false, false>(v, c, s_cnt, pushed));
+    const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true, P2P>(v, c, s_cnt, pushed) : step_stream<true, false, P2P>(v, c, s_cnt, pushed))
+                                     : (at_work ? step_stream<false, true, P2P>(v, c, s_cnt, pushed) : step_stream<false, false, P2P>(v, c, s_cnt, pushed));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
-    if (pushed) v.ctrl->pushed_any = 1u;   // the tail fences system-wide before it sends its vector
+    if (P2P && pushed) v.ctrl->pushed_any = 1u;   // the tail fences system-wide before it sends its vector
     kt.end(v, kt_t, 0);
 }
-__global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) { k_step_body<3>(v); }
-__global__ void __launch_bounds__(STEP_THREADS, 4) k_step_occ4(const DevView v) { k_step_body<4>(v); }
+__global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) { k_step_body<3, false>(v); }
+__global__ void __launch_bounds__(STEP_THREADS, 4) k_step_occ4(const DevView v) { k_step_body<4, false>(v); }
+__global__ void __launch_bounds__(STEP_THREADS, 4) k_step_p2p(const DevView v) { k_step_body<4, true>(v); }   // peer-to-peer shards
+__global__ void __launch_bounds__(STEP_THREADS, 3) k_step_p2p_occ3(const DevView v) { k_step_body<3, true>(v); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Public transport: one warp per route (source area, destination area).  Everybody who uses public transport rides at
@@ -887,10 +889,12 @@ struct TailSmem {
     uint32_t tally[8];
     uint32_t fix[8];             // fused: citizens vaccinated now, by the class k_step counted them in for the next step
     uint32_t k, accepted, batch_total;
+    uint32_t* mail[MAX_WORLD];   // fused peer-to-peer shards: the mailboxes (own and peers'), read once from PeerView
 };
 
 // Fused pipeline: k_step has already counted citizen `local` for step t + 1 (class tally, infected occupants of its building)
 // when the tail of step t vaccinates it (simulator.rs:549-552): take it out of both again.
+template <bool P2P>
 __device__ __forceinline__ void vaccinate_counted(const DevView& v, TailSmem& sm, uint32_t local) {
     const uint32_t old = atomicOr(&v.cstate[local], CS_VACCINATED);
     if (old & CS_VACCINATED) return;    // already Vaccinated (chosen citizens stay in the eligible set): nothing changes
@@ -902,11 +906,11 @@ __device__ __forceinline__ void vaccinate_counted(const DevView& v, TailSmem& sm
         const uint32_t cell = sm.c.next_at_work ? v.work_cell[local] : v.home_cell[local];
         atomicSub(&cnt_next[cell], 1u);
         bool pushed = false;
-        if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), cell, 0xFFFFFFFFu);
+        if (P2P) pushed |= push_to_peers(v, cnt_slot(1u, t1), cell, 0xFFFFFFFFu);
         if (cell >= v.n_bldg) {
             const uint32_t school = v.room_parent[cell - v.n_bldg];
             atomicSub(&cnt_next[school], 1u);
-            if (v.p2p) pushed |= push_to_peers(v, cnt_slot(1u, t1), school, 0xFFFFFFFFu);
+            if (P2P) pushed |= push_to_peers(v, cnt_slot(1u, t1), school, 0xFFFFFFFFu);
         }
         if (pushed) sm.fix[7] = 1u;   // this tail wrote into peers' count buffers
     }
@@ -919,33 +923,57 @@ __device__ __forceinline__ void vaccinate_counted(const DevView& v, TailSmem& sm
 // apply_interventions of step t, and at_work / pt_mode / mask_cur describe step t.  The tail records the statistics of step t,
 // draws the vaccination picks of step t, corrects the counts of step t + 1 for them, runs update_status of step t + 1 on the
 // corrected counts (it needs nothing else, statistics.rs:252-254) and derives the schedule of step t + 2 from it.
-template <int NT, bool FUSED = false>
+// PRELOADED: the caller has already copied the control block into sm.c and cleared sm.tally / sm.fix.
+template <int NT, bool FUSED = false, bool FSHARDED = false, bool PRELOADED = false>
 __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailSmem& sm, uint32_t n_partial_blocks) {
     constexpr int PER = VAX_BATCH / NT;   // draws per thread and round
     uint32_t* acc_keys = ht;                  // citizens chosen in this step
     uint32_t* bat_keys = ht + HT_SIZE;        // candidates of the current batch
     uint32_t* bat_minj = ht + 2 * HT_SIZE;    // first draw index of each candidate
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    // one coalesced read of the control block (L2: other blocks updated it with atomics)
-    if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + tid);
-    if (tid < 8) { sm.tally[tid] = 0; sm.fix[tid] = 0; }
-    __syncthreads();
+    if (!PRELOADED) {
+        // one coalesced read of the control block (L2: other blocks updated it with atomics)
+        if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + tid);
+        if (tid < 8) { sm.tally[tid] = 0; sm.fix[tid] = 0; }
+        __syncthreads();
+    }
     const bool sharded = !FUSED && v.world > 1;
-    const bool fsharded = FUSED && v.world > 1;   // fused pipeline over peer-to-peer shards
+    constexpr bool fsharded = FUSED && FSHARDED;   // fused pipeline over peer-to-peer shards
     if (fsharded) {
         // vax_prepare_fused has sent this shard's vector; add up the vectors of all shards in a fixed order, spinning on the tag
         // of every pair (the nibbles only travel while the vaccination programme runs)
         const uint32_t n_words = (sm.c.vax_some != 0 && sm.c.t != 0u) ? FEXCH_WORDS : 8u;
-        const uint32_t* mail = v.peer->mail[v.rank] + MAIL_LL + 2u * (sm.c.t & 1u) * MAX_WORLD * FEXCH_WORDS;
-        for (uint32_t h = tid; h < n_words; h += NT) {
-            uint32_t sum = 0;
-            for (uint32_t p = 0; p < v.world; ++p) sum += ld_pair_wait(mail + 2u * (p * FEXCH_WORDS + h), sm.c.t + 1u, &v.ctrl->error);
-            v.exch[h] = sum;
+        const uint32_t* mail = sm.mail[v.rank] + MAIL_LL + 2u * (sm.c.t & 1u) * MAX_WORLD * FEXCH_WORDS;
+        uint32_t* sum = ht;   // [FEXCH_WORDS] in shared memory (the hash tables are not used by sharded picks)
+        for (uint32_t h = tid; h < n_words; h += NT) sum[h] = 0;
+        __syncthreads();
+        // one pair per thread and round, all rounds of a thread requested before the first tag is examined: the reads of the
+        // whole vector set overlap (one round trip instead of one per shard)
+        constexpr uint32_t ROUNDS = (FEXCH_WORDS * MAX_WORLD + NT - 1) / NT;
+        const uint32_t total = n_words * v.world, tag = sm.c.t + 1u;
+        KTrace kx; kx.enter = 0; kx.begin(v, sm.c.t, 1);   // timeline slot 1 = waiting for the peers' vectors
+        uint32_t val[ROUNDS], seen[ROUNDS];
+#pragma unroll
+        for (uint32_t r = 0; r < ROUNDS; ++r) {
+            const uint32_t idx = tid + r * NT;
+            seen[r] = tag; val[r] = 0;
+            if (idx < total) {
+                const uint32_t* pp = mail + 2u * ((idx / n_words) * FEXCH_WORDS + idx % n_words);
+                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[r]), "=r"(seen[r]) : "l"(pp) : "memory");
+            }
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < ROUNDS; ++r) {
+            const uint32_t idx = tid + r * NT;
+            if (idx >= total) continue;
+            if (seen[r] != tag) val[r] = ld_pair_wait(mail + 2u * ((idx / n_words) * FEXCH_WORDS + idx % n_words), tag, &v.ctrl->error);
+            if (val[r]) atomicAdd(&sum[idx % n_words], val[r]);
         }
         __syncthreads();
-        if (tid < 5) sm.tally[tid] = __ldcg(&v.exch[tid]);          // class counts of step t + 1 as k_step saw them, all shards
-        if (tid == 5) sm.c.new_exp_bldg = __ldcg(&v.exch[5]);
-        if (tid == 6) sm.c.new_exp_pt = __ldcg(&v.exch[6]);
+        kx.end(v, sm.c.t, 1);
+        if (tid < 5) sm.tally[tid] = sum[tid];          // class counts of step t + 1 as k_step saw them, all shards
+        if (tid == 5) sm.c.new_exp_bldg = sum[5];
+        if (tid == 6) sm.c.new_exp_pt = sum[6];
     }
     if (sharded && v.p2p) {
         // sum the tail vectors of all shards (fixed order) into the exchange buffer the code below reads
@@ -1022,10 +1050,10 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
             // One nibble per candidate draw, summed over the shards (only the owner of a candidate writes its nibble): bit 3 =
             // eligible first occurrence, bits 0-2 = the class k_step counted the citizen in for step t + 1.  The first K
             // marked draws are the picks; every shard corrects the global class counts for all of them and applies its own.
-            const uint32_t* nib = v.exch + 8;
+            const uint32_t* nib = ht + 8;                  // the summed vector in shared memory, see above
             constexpr uint32_t NW = VAX_SHARD_DRAWS / 8;   // nibble words
             uint32_t pc = 0;
-            if (tid < NW) pc = __popc(__ldcg(&nib[tid]) & 0x88888888u);
+            if (tid < NW) pc = __popc(nib[tid] & 0x88888888u);
             uint32_t incl = pc;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -1047,7 +1075,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
             }
             __syncthreads();
             if (tid < NW) {
-                const uint32_t word = __ldcg(&nib[tid]);
+                const uint32_t word = nib[tid];
                 uint32_t rank = sm.scan[wid] + (incl - pc);   // marked draws before this word
 #pragma unroll
                 for (uint32_t k = 0; k < 8; ++k) {
@@ -1057,7 +1085,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                         const uint32_t cls = nb & 7u;
                         const uint32_t cand = __ldcg(&v.vax_cand[tid * 8u + k]);
                         const uint32_t local = cand - v.mp.shard_lo;
-                        if (local < v.n) vaccinate_counted(v, sm, local);        // the owner: state word + count buffers
+                        if (local < v.n) vaccinate_counted<FSHARDED>(v, sm, local);        // the owner: state word + count buffers
                         else if (cls < 4u) atomicAdd(&sm.fix[cls], 1u);           // somebody else's citizen: class counts only
                     }
                     ++rank;
@@ -1120,7 +1148,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
             if (!sm.c.vax_all_done) {
                 for (uint32_t i = tid; i < v.n; i += NT) {
                     const uint32_t w = __ldcg(&v.cstate[i]);
-                    if (!(w & CS_VACCINATED) && vax_eligible(w, vax_start)) vaccinate_counted(v, sm, i);
+                    if (!(w & CS_VACCINATED) && vax_eligible(w, vax_start)) vaccinate_counted<FSHARDED>(v, sm, i);
                 }
             }
             if (tid == 0) {
@@ -1190,7 +1218,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
                 for (int q = 0; q < PER; ++q) {
                     if (flag[q]) {
                         if (rank < K) {
-                            if (FUSED) vaccinate_counted(v, sm, cand[q] - v.mp.shard_lo);
+                            if (FUSED) vaccinate_counted<FSHARDED>(v, sm, cand[q] - v.mp.shard_lo);
                             else atomicOr(&v.cstate[cand[q] - v.mp.shard_lo], CS_VACCINATED);
                             ht_insert(acc_keys, cand[q]);
                         }
@@ -1209,9 +1237,10 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
     if (fsharded && (v.n_shared_b | v.n_shared_r)) {
         // tell the peers that the corrections this tail pushed into their count buffers (if any) are complete: their next k_step
         // waits for it.  Raised before the scalar epilogue so that the flag travels while this block finishes.
-        if (sm.fix[7]) __threadfence_system();
+        __syncthreads();                                   // every thread's corrections are issued
+        if (tid == 0 && sm.fix[7]) __threadfence_system();   // cumulative: covers the other threads' reductions observed through the barrier
         __syncthreads();
-        if (tid < v.world && tid != v.rank) st_release_sys(v.peer->mail[tid] + MAIL_FLAG_C + v.rank, sm.c.t + 1u);
+        if (tid < v.world && tid != v.rank) st_release_sys(sm.mail[tid] + MAIL_FLAG_C + v.rank, sm.c.t + 1u);
     }
 
     if (tid == 0) {
@@ -1372,7 +1401,7 @@ __device__ __forceinline__ void vax_prepare_phase(const DevView& v, uint32_t* dy
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS) k_vax_prepare(const DevView v) {
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_vax_prepare(const DevView v) {
     pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
     if (v.ctrl->finished | v.ctrl->abort_graph) return;
@@ -1400,28 +1429,27 @@ __global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
 //   [8 + j/8] nibble j%8: candidate draw j of the vaccination stream is owned by this shard, eligible and the first
 //   occurrence of its citizen (bit 3), and the class the citizen was counted in (bits 0-2, 4 = already vaccinated)
 // goes to every shard's mailbox.  `dyn_smem`: at least VP_SMEM bytes.  `n_blocks`: grid of the kernel that left the partial sums.
-__device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dyn_smem, uint32_t n_blocks) {
+// `part` = this thread's share of the partial sums (threads tid, tid + 8, ... hold the same counter), loaded by the caller
+// together with the control block so that the two memory round trips overlap.
+__device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dyn_smem, TailSmem& sm, uint32_t part) {
     constexpr uint32_t NW = VAX_SHARD_DRAWS / 8;
     uint32_t* keys = dyn_smem;                 // [VP_HT]
     uint32_t* minj = dyn_smem + VP_HT;         // [VP_HT]
     uint32_t* nib = dyn_smem + 2 * VP_HT;      // [NW]
-    __shared__ uint32_t s_tally[8];
-    const Ctrl* __restrict__ c = v.ctrl;
+    uint32_t* s_tally = sm.tally;   // cleared by the caller
+    const Ctrl* c = &sm.c;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t t = c->t;
     // update_status of step t has already run (previous tail): the programme is active in this step iff vax_some
     const bool vaccinate = c->vax_some != 0 && t != 0u;
-    if (tid < 8) s_tally[tid] = 0;
-    if (vaccinate) for (uint32_t h = tid; h < VP_HT; h += TAIL_THREADS) { keys[h] = HT_EMPTY; minj[h] = 0xFFFFFFFFu; }
-    for (uint32_t h = tid; h < NW; h += TAIL_THREADS) nib[h] = 0;
-    __syncthreads();
-    {
-        uint32_t part = 0;
-        for (uint32_t z = tid; z < n_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
-        part += __shfl_xor_sync(0xffffffffu, part, 8);
-        part += __shfl_xor_sync(0xffffffffu, part, 16);
-        if (lane < 8 && part) atomicAdd(&s_tally[lane], part);
+    if (vaccinate) {
+        for (uint32_t h = tid; h < VP_HT; h += TAIL_THREADS) { keys[h] = HT_EMPTY; minj[h] = 0xFFFFFFFFu; }
+        for (uint32_t h = tid; h < NW; h += TAIL_THREADS) nib[h] = 0;
+        __syncthreads();
     }
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    part += __shfl_xor_sync(0xffffffffu, part, 16);
+    if (lane < 8 && part) atomicAdd(&s_tally[lane], part);
     // the snapshot of a Vaccination event raised for step t is taken by this tail: everybody Susceptible now is eligible, which
     // is what vax_eligible(w, t) says (nobody can have been exposed after step t yet)
     const uint32_t vax_start = c->vax_event ? t : c->vax_start_step;
@@ -1465,14 +1493,13 @@ __device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dy
                 atomicOr(&nib[j >> 3], (8u | cls) << (4u * (j & 7u)));
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
     __shared__ uint32_t s_head[8];
-    if (tid == 0) {
+    if (tid < 8) {   // every one of the eight threads derives the classes itself: no extra barrier
         uint32_t cls[5];
         classes_from_cumulative(s_tally, v.n_pad, v.n, cls);
-        for (int k = 0; k < 5; ++k) s_head[k] = cls[k];
-        s_head[5] = c->new_exp_bldg; s_head[6] = c->new_exp_pt; s_head[7] = 0;
+        s_head[tid] = tid < 5 ? cls[tid] : tid == 5 ? c->new_exp_bldg : tid == 6 ? c->new_exp_pt : 0u;
     }
     __syncthreads();
     // hand the vector to every shard (including this one) as (value, tag) pairs; the nibbles only travel while the
@@ -1481,16 +1508,23 @@ __device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dy
     const uint32_t slot_v = MAIL_LL + 2u * ((t & 1u) * MAX_WORLD + v.rank) * FEXCH_WORDS;
     // The pairs double as "this shard's count pushes for step t + 1 are complete": the previous grid's remote reductions are
     // visible to this grid (it waited for that grid), and the fence makes them precede the pairs for every observer.
-    if (c->pushed_any) __threadfence_system();
+    // One thread fences (it has observed the previous grid's writes; fences are cumulative), the barrier orders the other
+    // threads' stores after it.
+    if (c->pushed_any) {
+        if (tid == 0) __threadfence_system();
+        __syncthreads();
+    }
     for (uint32_t h = tid; h < n_words; h += TAIL_THREADS) {
         const uint32_t value = h < 8u ? s_head[h] : nib[h - 8u];
-        for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(v.peer->mail[p] + slot_v + 2u * h, value, t + 1u);
+        for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(sm.mail[p] + slot_v + 2u * h, value, t + 1u);
     }
     __syncthreads();
+    if (tid < 8) s_tally[tid] = 0;   // tail_phase starts from cleared counters (it fills them from the summed vectors)
 }
 
 // fused pipeline: v.n_update_blocks is the grid of the kernel that left the partial sums (k_step, or k_update in the boot pass)
-__global__ void __launch_bounds__(TAIL_THREADS) k_tail_fused(const DevView v) {
+template <bool P2P>
+__device__ __forceinline__ void tail_fused_body(const DevView& v) {
     KTrace kt; kt.start(v);
     pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
@@ -1498,12 +1532,28 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_tail_fused(const DevView v) {
     if (v.ctrl->finished | v.ctrl->abort_graph) return;
     const uint32_t kt_t = v.ctrl->t;
     kt.begin(v, kt_t, 3);
-    if (v.world > 1) vax_prepare_fused(v, dyn_smem, v.n_update_blocks);
-    tail_phase<TAIL_THREADS, true>(v, dyn_smem, sm, v.n_update_blocks);
+    if (P2P) {
+        // one memory round trip for everything the tail needs before it can send: control block, mailbox pointers, partial sums
+        const uint32_t tid = threadIdx.x;
+        if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + tid);
+        if (tid >= 64 && tid < 64 + MAX_WORLD) sm.mail[tid - 64] = v.peer->mail[tid - 64];
+        uint32_t part = 0;
+        for (uint32_t z = tid; z < v.n_update_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
+        if (tid >= 32 && tid < 40) { sm.tally[tid - 32] = 0; sm.fix[tid - 32] = 0; }
+        __syncthreads();
+        KTrace ks; ks.enter = 0; ks.begin(v, kt_t, 4);   // timeline slot 4: loads done -> vector sent
+        vax_prepare_fused(v, dyn_smem, sm, part);
+        ks.end(v, kt_t, 4);
+        tail_phase<TAIL_THREADS, true, true, true>(v, dyn_smem, sm, v.n_update_blocks);
+    } else {
+        tail_phase<TAIL_THREADS, true, false>(v, dyn_smem, sm, v.n_update_blocks);
+    }
     kt.end(v, kt_t, 3);
 }
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail_fused(const DevView v) { tail_fused_body<false>(v); }
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail_fused_p2p(const DevView v) { tail_fused_body<true>(v); }   // peer-to-peer shards
 
-__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const DevView v) {
+__global__ void __launch_bounds__(TAIL_THREADS, 1) k_tail(const DevView v) {
     pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
@@ -1643,6 +1693,7 @@ int configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vax_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tail_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tail_fused_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     if (const char* env = getenv("ESIM_STEP_TMA")) g_step_tma = env[0] == '1';
     if (const char* env = getenv("ESIM_STEP_BLOCKS")) g_step_blocks_per_sm = atoi(env);
@@ -1707,14 +1758,17 @@ uint32_t step_blocks(uint32_t n_pad) {
     return blocks_for(g_step_tma ? n_pad >> 2 : (n_pad + 7u) >> 3, STEP_THREADS, (uint32_t)sm_count() * (uint32_t)g_step_blocks_per_sm);
 }
 void launch_step_fused(const DevView& v, cudaStream_t s) {
-    if (g_step_tma && !v.p2p) launch_step_kernel(k_step_tma, step_blocks(v.n_pad), STEP_THREADS, sizeof(StepSmem), s, v);
+    if (v.p2p && g_step_occ4) launch_step_kernel(k_step_p2p, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+    else if (v.p2p) launch_step_kernel(k_step_p2p_occ3, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+    else if (g_step_tma) launch_step_kernel(k_step_tma, step_blocks(v.n_pad), STEP_THREADS, sizeof(StepSmem), s, v);
     else if (g_step_occ4) launch_step_kernel(k_step_occ4, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
     else launch_step_kernel(k_step, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
 }
 void launch_tail_fused(const DevView& v, cudaStream_t s) {
     DevView vv = v;
     vv.n_update_blocks = step_blocks(v.n_pad);   // the partial sums come from k_step
-    launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);
+    if (v.p2p) launch_step_kernel(k_tail_fused_p2p, 1, TAIL_THREADS, HT_BYTES, s, vv);
+    else launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);
 }
 void launch_boot_fused(const DevView& v, cudaStream_t s) {
     // Ctrl::t == 0: k_update counts step 1 (class tally, infected occupants, pushes to peers), then the tail runs as "step 0":
@@ -1722,7 +1776,8 @@ void launch_boot_fused(const DevView& v, cudaStream_t s) {
     DevView vv = v;
     vv.boot = 1;
     launch_update(vv, s);
-    launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);   // n_update_blocks = grid of k_update
+    if (v.p2p) launch_step_kernel(k_tail_fused_p2p, 1, TAIL_THREADS, HT_BYTES, s, vv);   // n_update_blocks = grid of k_update
+    else launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);
 }
 void launch_vax_prepare(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_vax_prepare, 1, TAIL_THREADS, VP_SMEM, s, v);

@@ -42,5 +42,26 @@ def raw(path):
         print(",".join(r[i].split('(')[0] for _, i in idx))
 
 
+def traffic(path, out=None):
+    """profiles/traffic.json: DRAM bytes per launch (read + write) and duration of every kernel in a raw export."""
+    import json
+    rows = list(csv.reader(open(path)))
+    H, units = rows[0], rows[1]
+    ki, ri, wi, di = H.index('Kernel Name'), H.index('dram__bytes_read.sum'), H.index('dram__bytes_write.sum'), H.index('gpu__time_duration.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[ki].split('(')[0]
+        b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+        a = acc.setdefault(name, {"launches": 0, "bytes": 0.0, "us": 0.0})
+        a["launches"] += 1; a["bytes"] += b; a["us"] += float(r[di]) * {'us': 1.0, 'ns': 1e-3, 'ms': 1e3}[units[di]]
+    res = {k: {"dram_bytes_per_launch": v["bytes"] / v["launches"], "duration_us_cold_serialised": v["us"] / v["launches"],
+               "launches_captured": v["launches"], "source": path} for k, v in acc.items()}
+    text = json.dumps(res, indent=1)
+    if out:
+        open(out, "w").write(text + "\n")
+    print(text)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -147,9 +147,14 @@ def traffic_from_profile(kernel):
     (profiles/traffic.json, written by scripts/ncu_summary.py traffic); None if no capture of that kernel is committed."""
     p = ROOT / "profiles" / "traffic.json"
     try:
-        return float(json.loads(p.read_text())[kernel]["dram_bytes_per_launch"])
+        table = json.loads(p.read_text())
+        # the capture names the instantiation that ran (k_step_occ4, k_step_p2p, ...)
+        for name in sorted(table, key=len):
+            if name == kernel or name.startswith(kernel + "_"):
+                return float(table[name]["dram_bytes_per_launch"])
     except Exception:
-        return None
+        pass
+    return None
 
 
 def cpu_baseline(pop, cfg_kwargs, seconds, min_steps=8):

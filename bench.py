@@ -125,7 +125,7 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(stats, n_citizens, n_cells):
+def algorithmic_bytes(stats, n_citizens, n_cells, shard_fraction=1.0):
     """Per-step algorithmic bytes of the streaming kernels for the layout in DESIGN.md section 3.
     k_update: 4 B state word per citizen + 8 B (position id + count update) per infected citizen + 4 B per cell (zeroing).
     k_expose: 4 B state word per citizen + 8 B (household + workplace ids) per susceptible citizen + 4 B per cell (every
@@ -134,8 +134,10 @@ def algorithmic_bytes(stats, n_citizens, n_cells):
               4 B per citizen + 8 B per susceptible + 8 B per infected + 8 B per cell (count gathers + zeroing)."""
     from epidemicsimulator_b200 import _abi
     f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
-    s_before = stats[:, f["susceptible"]] + stats[:, f["exposures_building"]] + stats[:, f["exposures_pt"]]
-    infected = stats[:, f["infected"]]
+    # the recorded statistics are global: a shard holds its share of the susceptible / infected citizens (the shards are
+    # balanced by residents and seeded alike, so the share is the shard's fraction of the population)
+    s_before = (stats[:, f["susceptible"]] + stats[:, f["exposures_building"]] + stats[:, f["exposures_pt"]]) * shard_fraction
+    infected = stats[:, f["infected"]] * shard_fraction
     upd = 4.0 * n_citizens + 8.0 * infected + 4.0 * n_cells
     exp = 4.0 * n_citizens + 8.0 * s_before + 4.0 * n_cells
     fused = 4.0 * n_citizens + 8.0 * s_before + 8.0 * infected + 8.0 * n_cells
@@ -322,7 +324,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        upd_b, exp_b, fused_b = algorithmic_bytes(stats, pop.n_citizens, n_cells)
+        upd_b, exp_b, fused_b = algorithmic_bytes(stats, pop.n_citizens, n_cells, pop.n_citizens / n_total)
         f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
         pt_steps = int((stats[:, f["pt_mode"]] != 0).sum())
         if fused:

@@ -292,6 +292,7 @@ void flush_l2(EsimSim* s) {
 void enqueue_step(EsimSim* s, uint32_t parity, bool with_pt = true, bool next_has_pt = true) {
     DevView v = s->v;
     v.next_has_pt = next_has_pt ? 1u : 0u;
+    v.has_pt = (with_pt && v.n_routes) ? 1u : 0u;
     if (s->fused) {
         launch_step_fused(v, s->stream);
         if (with_pt) launch_pt(v, s->stream);
@@ -459,7 +460,7 @@ static void print_ktrace(EsimSim* s) {
     std::vector<unsigned long long> mn(s->ktrace_min.n), mx(s->ktrace_max.n);
     cudaMemcpy(mn.data(), s->ktrace_min.p, s->ktrace_min.bytes(), cudaMemcpyDeviceToHost);
     cudaMemcpy(mx.data(), s->ktrace_max.p, s->ktrace_max.bytes(), cudaMemcpyDeviceToHost);
-    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose/xchg", "pt", "tail", "tail:send", "spare"};
+    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose/xchg", "pt", "tail", "tail:send", "tail:poll"};
     const uint32_t last = s->steps_done, first = last > KTRACE_STEPS - 2 ? last - (KTRACE_STEPS - 2) : 2;
     // everything relative to the end of slot 0 (k_update / k_step) of the same step
     double run[KTRACE_KERNELS] = {}, b_rel[KTRACE_KERNELS] = {}, e_rel[KTRACE_KERNELS] = {}, wait[KTRACE_KERNELS] = {};
@@ -637,6 +638,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.n = N; v.n_pad = n_pad; v.n_bldg = B; v.n_rooms = R; v.n_cells = B + R;
         v.n_routes = n_routes; v.n_riders = n_riders; v.record_buses = rec ? 1u : 0u;
         v.next_has_pt = 1;   // every launch sequence has a public-transport kernel unless a specialised graph says otherwise
+        v.has_pt = 1;        // (conservative default: the fused tail then waits for the grid in front of it)
         v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
         v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt_all.p; v.cnt[1] = s->cnt_all.p + s->cnt_stride; v.cnt[2] = s->cnt_all.p + 2 * s->cnt_stride;
         v.fused = s->fused ? 1u : 0u; v.boot = 0; v.thr = s->thr.p;
@@ -694,7 +696,8 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
             enqueue_step(s, parity, s->h_ctrl->pt_mode != ESIM_PT_NONE, true);
             CK(cudaEventRecord(s->ev[4], s->stream));
         } else if (timed) {
-            const DevView& v = s->v;
+            DevView v = s->v;
+            v.has_pt = (s->h_ctrl->pt_mode != ESIM_PT_NONE && v.n_routes) ? 1u : 0u;
             flush_l2(s);
             CK(cudaEventRecord(s->ev[0], s->stream));
             if (!s->fused) launch_update(v, s->stream);

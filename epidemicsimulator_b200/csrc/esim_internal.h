@@ -95,7 +95,8 @@ struct Ctrl {
     uint32_t new_exp_pt;     // successful public-transport exposures of step t
     uint32_t vaccinated_now;
     uint32_t abort_graph;    // the schedule left the assumptions of the specialised graph being replayed: the rest of it is a no-op
-    uint32_t blocks_done;    // last-block-done counter of k_update in peer-to-peer mode
+    uint32_t blocks_done;    // last-block-done counter of k_update in peer-to-peer mode; fused pipeline: blocks of k_step (or of the
+                             // boot k_update) that have finished their work, polled and reset by the tail
     uint32_t eager_expose;   // more than a quarter of the citizens are susceptible: k_expose loads cell ids eagerly
     uint32_t mask_cur;       // MaskStatus the exposures of step t are evaluated with (= mask_kind except in the fused pipeline,
                              // whose intervention state machine runs one step ahead)
@@ -121,6 +122,8 @@ struct DevView {
     uint32_t n_routes, n_riders;
     uint32_t record_buses;
     uint32_t next_has_pt;  // tail only: the graph slot of the next hour contains a public-transport kernel
+    uint32_t has_pt;       // this step's launch sequence has a public-transport kernel between k_step and the tail
+    uint32_t tail_flag_wait;  // fused tail: poll Ctrl::blocks_done instead of waiting for the k_step grid to drain
     uint32_t* cstate;      // [n_pad]
     const uint32_t* home_cell;   // [n_pad] building id
     const uint32_t* work_cell;   // [n_pad] building id, or n_bldg + room id for school members

@@ -49,6 +49,14 @@ __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// k_step (fused pipeline): the dependent - the tail - may only be launched once the previous tail has completed, because a
+// tail that polls Ctrl::blocks_done (see signal_block_done) reads the control block without a grid dependency of its own: it
+// must find the counter reset and the flags of the finished step.  The tail's block still becomes resident microseconds
+// before k_step ends.
+__device__ __forceinline__ void pdl_prologue_wait_first() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // device-side timeline (ESIM_KTRACE=1): one thread per block stamps %globaltimer around its work
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -135,6 +143,35 @@ __device__ __forceinline__ void wait_for_peers(const DevView& v, uint32_t flag_b
         while (ld_acquire_sys(flag) < t) {
             if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_COMM); break; }
             __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+// ---- k_step -> tail hand-over without a kernel boundary (fused pipeline) --------------------------------------------------
+// With programmatic dependent launch the tail's block is resident long before k_step ends, but griddepcontrol.wait only returns
+// once the whole k_step grid has drained and been flushed: measured 3.6 us from the last k_step block's last instruction to
+// the tail's first (profiles/README.md, device timeline of round 1c) - a fifth of a warm step.  Instead every k_step block
+// announces the end of its work (barrier, fence, one atomic on Ctrl::blocks_done) and the tail polls that counter; the tail
+// resets it when it writes the control block back (no k_step is running then: the next one waits for the tail to complete).
+// Hours with a public-transport kernel between the two keep the grid dependency (DevView::tail_flag_wait == 0).
+__device__ __forceinline__ void signal_block_done(const DevView& v, bool pushed_to_peer) {
+    const int any_pushed = __syncthreads_or(pushed_to_peer);   // every thread of the block has issued its writes
+    if (threadIdx.x == 0) {
+        if (any_pushed) __threadfence_system(); else __threadfence();   // cumulative over the writes observed through the barrier
+        atomicAdd(&v.ctrl->blocks_done, 1u);
+    }
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t x;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+    return x;
+}
+__device__ __forceinline__ void wait_blocks_done(const DevView& v, uint32_t expected) {
+    if (threadIdx.x == 0) {
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(&v.ctrl->blocks_done) < expected) {
+            if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_SIMULATION); break; }   // never hang the GPU
         }
     }
     __syncthreads();
@@ -262,6 +299,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
         if (!v.fused) publish_counts_done(v, pushed, t);
         else if (pushed) v.ctrl->pushed_any = 1u;   // boot pass of the fused pipeline: the tail fences before it sends
     }
+    if (v.fused) signal_block_done(v, pushed);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -270,8 +308,8 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 6) k_update(const DevView v) {
 constexpr int EXPOSE_THREADS = 256;
 
 // Citizen::expose for one susceptible citizen with a household trial threshold and k_w workplace / room trials.
-__device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long long thr_w, uint32_t k_w, uint32_t gid,
-                                        uint32_t t, uint32_t seed_lo, uint32_t seed_hi) {
+__device__ __forceinline__ bool run_trials_body(unsigned long long thr_h, unsigned long long thr_w, uint32_t k_w, uint32_t gid,
+                                                uint32_t t, uint32_t seed_lo, uint32_t seed_hi) {
     Philox4 p = philox4x32_10(gid, t, 0u, DOM_BUILDING, seed_lo, seed_hi);
     if (thr_h && u52_from(p, 0) < thr_h) return true;      // slot 0: Household
     if (k_w && u52_from(p, 1) < thr_w) return true;        // slot 1: Workplace, or first infected room member
@@ -282,6 +320,35 @@ __device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long 
     }
     return false;
 }
+__device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long long thr_w, uint32_t k_w, uint32_t gid,
+                                        uint32_t t, uint32_t seed_lo, uint32_t seed_hi) {
+    return run_trials_body(thr_h, thr_w, k_w, gid, t, seed_lo, seed_hi);
+}
+
+// The whole slow path of one citizen (thresholds, school look-up, trials, state write) behind ONE call, for kernels whose
+// DevView is a __grid_constant__ parameter (its address can be passed on without a local copy): the streaming loop then
+// holds none of the slow path's pointers and constants in registers.  Returns the citizen's new state word.
+__device__ __noinline__ uint32_t trial_citizen(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t i, uint32_t w, uint32_t wc,
+                                               uint32_t n_h, uint32_t n_w, uint32_t t, uint32_t mask_everywhere) {
+    // Citizen::expose (citizen.rs:228-232): a compliant citizen is evaluated with MaskStatus::None, the others
+    // with the global status, and only MaskStatus::Everywhere changes the chance (disease.rs:131-154)
+    const uint32_t mc = (mask_everywhere && !(w & CS_COMPLIANT)) ? 256u : 0u;
+    unsigned long long thr_h = 0, thr_w = 0;
+    uint32_t k_w = 0;
+    if (n_h) thr_h = __ldg(&v.thr[mc + (n_h & 255u)]);  // `exposure_total as u8` (citizen.rs:239)
+    if (n_w) {
+        // a room member gets one trial per infected member of its own room, each with n = infected in the school
+        const uint32_t n_total = wc >= v.n_bldg ? __ldg(&cnt[__ldg(&v.room_parent[wc - v.n_bldg])]) : n_w;
+        thr_w = __ldg(&v.thr[mc + (n_total & 255u)]);
+        k_w = thr_w ? (wc >= v.n_bldg ? n_w : 1u) : 0u;
+    }
+    if (thr_h == 0 && k_w == 0) return w;
+    if (run_trials_body(thr_h, thr_w, k_w, __ldg(&v.global_id[i]), t, v.mp.seed_lo, v.mp.seed_hi)) {
+        w |= t + EXPOSURE_BIAS;                 // DiseaseStatus::Exposed(0) (citizen.rs:244)
+        v.cstate[i] = w;
+    }
+    return w;
+}
 
 // AT_WORK is uniform over the launch.  The simulator.rs:324 filter ("the citizen must currently stand in the building's
 // output area") becomes two bit tests per citizen:
@@ -290,28 +357,39 @@ __device__ __noinline__ bool run_trials(unsigned long long thr_h, unsigned long 
 // CG: read the counts with ld.global.cg (needed inside the persistent kernel, where another SM wrote them during the same
 // launch); the graph kernels use the L1-cached read-only path: neighbours in a quad share their household.
 template <bool AT_WORK, bool CG>
-__device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, uint32_t (&w)[4],
-                                                const uint4 h4, const uint4 k4, uint32_t t, uint32_t mask_everywhere) {
+__device__ __forceinline__ void gather_quad(const uint32_t* __restrict__ cnt, const uint32_t (&w)[4], const uint4 h4, const uint4 k4,
+                                            uint32_t (&n_h)[4], uint32_t (&n_w)[4]) {
     const uint32_t hc[4] = {h4.x, h4.y, h4.z, h4.w};
     const uint32_t wc[4] = {k4.x, k4.y, k4.z, k4.w};
-    const uint32_t n_bldg = v.n_bldg;
     constexpr uint32_t HOME_TEST = AT_WORK ? (CS_LOW16 | CS_SAME_AREA) : CS_LOW16;
     constexpr uint32_t HOME_WANT = AT_WORK ? CS_SAME_AREA : 0u;
     constexpr uint32_t WORK_TEST = AT_WORK ? (CS_LOW16 | CS_HAS_WORK) : (CS_LOW16 | CS_HAS_WORK | CS_SAME_AREA);
     constexpr uint32_t WORK_WANT = AT_WORK ? CS_HAS_WORK : (CS_HAS_WORK | CS_SAME_AREA);
     // gather the counts of all sources first: the household (building.rs:202-204) and the workplace / own room
-    // (building.rs:278-280, 494-522)
-    uint32_t n_h[4], n_w[4];
+    // (building.rs:278-280, 494-522); citizens that are not susceptible gather nothing
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         n_h[k] = (w[k] & HOME_TEST) == HOME_WANT ? (CG ? __ldcg(&cnt[hc[k]]) : __ldg(&cnt[hc[k]])) : 0u;
         n_w[k] = (w[k] & WORK_TEST) == WORK_WANT ? (CG ? __ldcg(&cnt[wc[k]]) : __ldg(&cnt[wc[k]])) : 0u;
     }
-    if (!(n_h[0] | n_h[1] | n_h[2] | n_h[3] | n_w[0] | n_w[1] | n_w[2] | n_w[3])) return 0u;
+}
+
+// the Bernoulli trials of a quad whose gathered counts are not all zero
+template <bool CG, bool SLOWCALL = false>
+__device__ __forceinline__ uint32_t trial_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, uint32_t (&w)[4], const uint4 k4,
+                                               const uint32_t (&n_h)[4], const uint32_t (&n_w)[4], uint32_t t, uint32_t mask_everywhere) {
+    const uint32_t wc[4] = {k4.x, k4.y, k4.z, k4.w};
+    const uint32_t n_bldg = v.n_bldg;
     uint32_t n_exposed = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (!(n_h[k] | n_w[k])) continue;
+        if (SLOWCALL) {   // not with CG: trial_citizen reads the counts through the read-only path
+            const uint32_t nw = trial_citizen(v, cnt, (q << 2) + (uint32_t)k, w[k], wc[k], n_h[k], n_w[k], t, mask_everywhere);
+            n_exposed += nw != w[k];
+            w[k] = nw;
+            continue;
+        }
         // Citizen::expose (citizen.rs:228-232): a compliant citizen is evaluated with MaskStatus::None, the others
         // with the global status, and only MaskStatus::Everywhere changes the chance (disease.rs:131-154)
         const uint32_t mc = (mask_everywhere && !(w[k] & CS_COMPLIANT)) ? 256u : 0u;
@@ -334,6 +412,15 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
         }
     }
     return n_exposed;
+}
+
+template <bool AT_WORK, bool CG, bool SLOWCALL = false>
+__device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t* __restrict__ cnt, uint32_t q, uint32_t (&w)[4],
+                                                const uint4 h4, const uint4 k4, uint32_t t, uint32_t mask_everywhere) {
+    uint32_t n_h[4], n_w[4];
+    gather_quad<AT_WORK, CG>(cnt, w, h4, k4, n_h, n_w);
+    if (!(n_h[0] | n_h[1] | n_h[2] | n_h[3] | n_w[0] | n_w[1] | n_w[2] | n_w[3])) return 0u;
+    return trial_quad<CG, SLOWCALL>(v, cnt, q, w, k4, n_h, n_w, t, mask_everywhere);
 }
 
 __device__ __forceinline__ bool any_susceptible(const uint4 w) {
@@ -398,9 +485,9 @@ __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
 constexpr int STEP_THREADS = 256;
 constexpr uint32_t STEP_PF = 2;   // prefetch distance in iterations
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-__constant__ int g_pf = 1;        // ESIM_STEP_PF=0 switches the L2 prefetches off (experiments)
+__constant__ int g_pf = 0;        // ESIM_STEP_PF=1: L2 prefetches of the streams two iterations ahead (no gain cold, slower warm: profiles/README.md)
 
-template <bool EAGER, bool AT_WORK, bool P2P>
+template <bool EAGER, bool AT_WORK, bool P2P, bool ORDERED = false>
 __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt, bool& pushed) {
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_quads = v.n_pad >> 2;
@@ -433,20 +520,24 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
             if (EAGER) { prefetch_l2(hc4 + qb); prefetch_l2(wc4 + qb); }
         }
     };
-    if (g_pf) {
+    const bool pf = !ORDERED && g_pf != 0;   // ORDERED (k_step_v2): no stream prefetch, see there
+    if (pf) {
 #pragma unroll
         for (uint32_t d = 1; d <= STEP_PF; ++d) prefetch_pair(gtid + d * 2u * T);
         // the infected counts of step t: written by the previous launch, gathered at random below
         for (uint32_t z = gtid; z < ((v.n_cells + 31u) >> 5); z += T) prefetch_l2(cnt + (z << 5));
     }
-    for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
+    // the count buffer of step t + 2 is zeroed here; ORDERED does it after the stream (nothing in this launch reads it), so
+    // that the stores do not stand in front of the first demand loads
+    if (!ORDERED)
+        for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
 
     uint32_t n_exposed = 0;
     uint32_t c_exp = 0, c_inf = 0, c_ei = 0, c_vax = 0;   // #(code != 0), #(code >= i_lo), #(code >= e_lo), #(code >= 0x8000)
     for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
         const uint32_t q1 = q0 + T;
         const bool have1 = q1 < n_quads;
-        if (g_pf) prefetch_pair(q0 + (STEP_PF + 1u) * 2u * T);
+        if (pf) prefetch_pair(q0 + (STEP_PF + 1u) * 2u * T);
         const uint4 wa = cs4[q0];
         const uint4 wb = have1 ? cs4[q1] : pad4;
         uint4 ha, ka, hb, kb;
@@ -514,6 +605,57 @@ __device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __
     if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
     return n_exposed;
 }
+
+// ---- k_step_v2: the same stream with the memory requests of a cold step ordered by need -----------------------------------
+// A cold step is a burst: everything a block will ever read is requested within the first microseconds, and the memory system
+// serves requests roughly in arrival order.  Measured on B200 (profiles/README.md, round 1c): L2 prefetches of later iterations
+// issued before the first demand loads make those wait for half of the whole transfer (k_step 20.1 us -> 19.0 us without),
+// and any stream prefetch costs ~1 us per step once the working set is L2-resident.  So this build has no stream prefetch;
+// the state words of the first iteration are requested before the control block is read (their addresses only depend on
+// the launch geometry), and the zeroing stores of the count buffer of step t + 2 leave after the stream instead of before it.
+#ifndef ESIM_EARLY_STATE_PREFETCH
+#define ESIM_EARLY_STATE_PREFETCH 1
+#endif
+template <bool P2P>
+__device__ __forceinline__ void k_step_body2(const DevView& v) {
+    KTrace kt; kt.start(v);
+    pdl_prologue_wait_first();
+    __shared__ uint32_t s_cnt[4];
+#if ESIM_EARLY_STATE_PREFETCH
+    // the state words of the first iteration: their addresses only depend on the launch geometry, so the requests (L2
+    // prefetches: no register is held) leave before the control block has been read
+    {
+        const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x, n_quads = v.n_pad >> 2;
+        const uint4* cs4 = reinterpret_cast<const uint4*>(v.cstate);
+        if ((threadIdx.x & 7u) == 0u) {
+            if (gtid < n_quads) prefetch_l2(cs4 + gtid);
+            if (gtid + T < n_quads) prefetch_l2(cs4 + gtid + T);
+        }
+    }
+#endif
+    const Ctrl* __restrict__ c = v.ctrl;
+    if (c->finished | c->abort_graph) return;
+    const uint32_t kt_t = c->t;
+    // peer-to-peer shards: see k_step_body
+    if (P2P && (v.n_shared_b | v.n_shared_r) && c->vax_some) wait_for_peers(v, MAIL_FLAG_C, kt_t);
+    kt.begin(v, kt_t, 0);
+    const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
+    bool pushed = false;
+    const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true, P2P, true>(v, c, s_cnt, pushed) : step_stream<true, false, P2P, true>(v, c, s_cnt, pushed))
+                                     : (at_work ? step_stream<false, true, P2P, true>(v, c, s_cnt, pushed) : step_stream<false, false, P2P, true>(v, c, s_cnt, pushed));
+    const uint32_t s = warp_sum(n_exposed);
+    if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+    if (P2P && pushed) v.ctrl->pushed_any = 1u;   // the tail fences system-wide before it sends its vector
+    {   // the count buffer of step t + 2: nothing in this launch reads it
+        uint4* __restrict__ cnt_zero = reinterpret_cast<uint4*>(v.cnt[cnt_slot(1u, kt_t + 2u)]);
+        const uint32_t T = gridDim.x * blockDim.x;
+        for (uint32_t z = blockIdx.x * blockDim.x + threadIdx.x; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    signal_block_done(v, P2P && pushed);
+    kt.end(v, kt_t, 0);
+}
+__global__ void __launch_bounds__(STEP_THREADS, 4) k_step_v2(const __grid_constant__ DevView v) { k_step_body2<false>(v); }
+__global__ void __launch_bounds__(STEP_THREADS, 4) k_step_p2p_v2(const __grid_constant__ DevView v) { k_step_body2<true>(v); }
 
 // ---- k_step_tma: the same pass with the streaming reads staged through shared memory by bulk asynchronous copies ------------
 // Every block owns a contiguous range of quads and walks it in tiles of STEP_TILE quads.  One elected thread keeps
@@ -647,7 +789,7 @@ __device__ __forceinline__ uint32_t step_stream_tma(const DevView& v, const Ctrl
 
 __global__ void __launch_bounds__(STEP_THREADS, 4) k_step_tma(const DevView v) {
     KTrace kt; kt.start(v);
-    pdl_prologue();
+    pdl_prologue_wait_first();
     extern __shared__ __align__(128) unsigned char step_smem_raw[];
     StepSmem& sm = *reinterpret_cast<StepSmem*>(step_smem_raw);
     __shared__ uint32_t s_cnt[4];
@@ -660,13 +802,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) k_step_tma(const DevView v) {
                                      : (at_work ? step_stream_tma<false, true>(v, c, sm, s_cnt) : step_stream_tma<false, false>(v, c, sm, s_cnt));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+    signal_block_done(v, false);
     kt.end(v, kt_t, 0);
 }
 
 template <int OCC, bool P2P>
 __device__ __forceinline__ void k_step_body(const DevView& v) {
     KTrace kt; kt.start(v);
-    pdl_prologue();
+    pdl_prologue_wait_first();
     __shared__ uint32_t s_cnt[4];
     const Ctrl* __restrict__ c = v.ctrl;
     if (c->finished | c->abort_graph) return;
@@ -683,6 +826,7 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
     if (P2P && pushed) v.ctrl->pushed_any = 1u;   // the tail fences system-wide before it sends its vector
+    signal_block_done(v, P2P && pushed);
     kt.end(v, kt_t, 0);
 }
 __global__ void __launch_bounds__(STEP_THREADS, 3) k_step(const DevView v) { k_step_body<3, false>(v); }
@@ -1294,6 +1438,7 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         }
         c->t = nt;
         c->pushed_any = 0;
+        if (FUSED) c->blocks_done = 0;   // see signal_block_done: no producer is running now
         c->new_exp_bldg = 0; c->new_exp_pt = 0;
         c->vaccinated_now = sm.accepted;
         // a specialised day graph has no public-transport kernel in most slots: if the next hour needs one after all (lockdown
@@ -1526,10 +1671,20 @@ __device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dy
 template <bool P2P>
 __device__ __forceinline__ void tail_fused_body(const DevView& v) {
     KTrace kt; kt.start(v);
-    pdl_prologue();
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
-    if (v.ctrl->finished | v.ctrl->abort_graph) return;
+    if (v.tail_flag_wait) {
+        // finished / abort_graph / t are only ever written by a tail: stable since the previous one completed
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (v.ctrl->finished | v.ctrl->abort_graph) return;    // k_step left without announcing anything either
+        KTrace kp; kp.enter = 0;
+        if (v.ktrace_min && threadIdx.x == 0) kp.enter = global_ns();   // timeline slot 5: control block read -> counter complete
+        wait_blocks_done(v, v.n_update_blocks);                  // see signal_block_done
+        if (v.ktrace_min) { kp.begin(v, v.ctrl->t, 5); kp.end(v, v.ctrl->t, 5); }
+    } else {
+        pdl_prologue();
+        if (v.ctrl->finished | v.ctrl->abort_graph) return;
+    }
     const uint32_t kt_t = v.ctrl->t;
     kt.begin(v, kt_t, 3);
     if (P2P) {
@@ -1688,6 +1843,8 @@ int sm_count() {
 static bool g_step_tma = false;         // ESIM_STEP_TMA=1 selects the bulk-copy staged k_step_tma (measured slower)
 static bool g_step_occ4 = true;         // ESIM_STEP_OCC4=0: the 80-register build of k_step (3 resident blocks per SM)
 static int g_step_blocks_per_sm = 4;    // k_step blocks per SM in the grid (3 are resident; more = several waves)
+static bool g_tail_flag_wait = true;    // ESIM_TAIL_FLAGWAIT=0: the tail waits for the k_step grid to drain (griddepcontrol.wait)
+static int g_step_variant = 2;          // ESIM_STEP_V=1: the first fused build (stream prefetch switchable, zeroing in front of the stream)
 
 int configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
@@ -1697,6 +1854,8 @@ int configure_kernels() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem));
     if (const char* env = getenv("ESIM_STEP_TMA")) g_step_tma = env[0] == '1';
     if (const char* env = getenv("ESIM_STEP_BLOCKS")) g_step_blocks_per_sm = atoi(env);
+    if (const char* env = getenv("ESIM_STEP_V")) g_step_variant = atoi(env);
+    if (const char* env = getenv("ESIM_TAIL_FLAGWAIT")) g_tail_flag_wait = env[0] != '0';
     if (const char* env = getenv("ESIM_STEP_PF")) { const int on = env[0] != '0'; if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_pf, &on, sizeof(on)); }
     if (const char* env = getenv("ESIM_STEP_OCC4")) { g_step_occ4 = env[0] == '1'; if (!g_step_occ4 && !getenv("ESIM_STEP_BLOCKS")) g_step_blocks_per_sm = 3; }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);
@@ -1758,7 +1917,11 @@ uint32_t step_blocks(uint32_t n_pad) {
     return blocks_for(g_step_tma ? n_pad >> 2 : (n_pad + 7u) >> 3, STEP_THREADS, (uint32_t)sm_count() * (uint32_t)g_step_blocks_per_sm);
 }
 void launch_step_fused(const DevView& v, cudaStream_t s) {
-    if (v.p2p && g_step_occ4) launch_step_kernel(k_step_p2p, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+    if (g_step_variant >= 2 && !g_step_tma) {
+        if (v.p2p) launch_step_kernel(k_step_p2p_v2, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+        else launch_step_kernel(k_step_v2, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
+    }
+    else if (v.p2p && g_step_occ4) launch_step_kernel(k_step_p2p, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
     else if (v.p2p) launch_step_kernel(k_step_p2p_occ3, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
     else if (g_step_tma) launch_step_kernel(k_step_tma, step_blocks(v.n_pad), STEP_THREADS, sizeof(StepSmem), s, v);
     else if (g_step_occ4) launch_step_kernel(k_step_occ4, step_blocks(v.n_pad), STEP_THREADS, 0, s, v);
@@ -1767,6 +1930,7 @@ void launch_step_fused(const DevView& v, cudaStream_t s) {
 void launch_tail_fused(const DevView& v, cudaStream_t s) {
     DevView vv = v;
     vv.n_update_blocks = step_blocks(v.n_pad);   // the partial sums come from k_step
+    vv.tail_flag_wait = (g_tail_flag_wait && !v.has_pt) ? 1u : 0u;   // a public-transport kernel in between: keep the grid dependency
     if (v.p2p) launch_step_kernel(k_tail_fused_p2p, 1, TAIL_THREADS, HT_BYTES, s, vv);
     else launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);
 }
@@ -1775,6 +1939,8 @@ void launch_boot_fused(const DevView& v, cudaStream_t s) {
     // it records nothing, turns the partial sums into Ctrl::tally, runs update_status of step 1 and lays out the schedule
     DevView vv = v;
     vv.boot = 1;
+    vv.has_pt = 0;
+    vv.tail_flag_wait = 0;   // once per run: keep the grid dependency
     launch_update(vv, s);
     if (v.p2p) launch_step_kernel(k_tail_fused_p2p, 1, TAIL_THREADS, HT_BYTES, s, vv);   // n_update_blocks = grid of k_update
     else launch_step_kernel(k_tail_fused, 1, TAIL_THREADS, HT_BYTES, s, vv);

@@ -8,7 +8,8 @@ synthetic census-shaped population (11 300 output areas, pop_seed 20110327), 500
 infections with the reference's constants.  Prints ONE JSON line (see README / DESIGN.md for the keys).
 
   value        citizen-timesteps/s with the population resident in HBM: sum over the K steps of the CUDA-event time of each
-               step (events recorded by the library on its own stream around the kernels), L2 flushed before every step.
+               step (events recorded by the library on its own stream around the kernels, esim_run_timed), L2 flushed
+               before every step.
   e2e          the same metric through the public API with host buffers: esim_import_population (host -> device) +
                esim_run(K) + esim_read_stats + esim_read_state (device -> host), wall clock between synchronisations.
   roofline     dominant kernel (k_expose): algorithmic bytes of its launches / its CUDA-event time, against the measured
@@ -261,6 +262,7 @@ def main():
     sim = make_sim(_abi.CFG_FLUSH_L2)
     for _ in range(w):
         sim.step(timed=True)
+    sim.run_timed(w)
     sim.run(w)
     sim.close()
 
@@ -271,12 +273,7 @@ def main():
     sim = make_sim(_abi.CFG_FLUSH_L2)
     fused = sim.fused
     barrier()
-    steps_run = 0
-    for _ in range(args.steps):
-        alive = sim.step(timed=True)
-        steps_run += 1
-        if not alive:
-            break
+    steps_run = sim.run_timed(args.steps)   # CUDA events around every step; step k + 1 is queued before step k is read back
     barrier()
     stats = sim.statistics()
     n_cells = pop.n_buildings + pop.n_rooms

@@ -43,6 +43,15 @@ def host_lib() -> C.CDLL:
     lib.esim_shard_room_global.restype = _abi.u32p
     lib.esim_shard_destroy.argtypes = [vp]
     lib.esim_shard_destroy.restype = None
+    lib.esim_population_save.argtypes = [C.POINTER(_abi.EsimPopulationSoA), _abi.u32p, C.POINTER(C.c_char_p), C.c_char_p]
+    lib.esim_population_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.esim_population_file_view.argtypes = [vp, C.POINTER(_abi.EsimPopulationSoA)]
+    lib.esim_population_file_area_offsets.argtypes = [vp]
+    lib.esim_population_file_area_offsets.restype = _abi.u32p
+    lib.esim_population_file_area_code.argtypes = [vp, C.c_uint32]
+    lib.esim_population_file_area_code.restype = C.c_char_p
+    lib.esim_population_file_destroy.argtypes = [vp]
+    lib.esim_population_file_destroy.restype = None
     return lib
 
 
@@ -60,6 +69,7 @@ def cuda_lib() -> C.CDLL:
     lib.esim_step.argtypes = [vp, C.POINTER(_abi.EsimStepStats)]
     lib.esim_step_timed.argtypes = [vp, C.POINTER(_abi.EsimStepStats)]
     lib.esim_run.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.esim_run_timed.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.esim_read_stats.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(_abi.EsimStepStats)]
     lib.esim_steps_done.argtypes = [vp]
     lib.esim_is_fused.argtypes = [vp]

@@ -22,7 +22,7 @@ CUDA_LIB = PKG / "libesim_b200.so"
 HOST_LIB = PKG / "libesim_host.so"
 
 CUDA_SOURCES = ["esim_kernels.cu", "esim_import.cu", "esim_api.cu"]
-HOST_SOURCES = ["popgen.cpp"]
+HOST_SOURCES = ["popgen.cpp", "population_io.cpp"]
 
 
 def _newer(target: Path, deps) -> bool:

@@ -753,6 +753,84 @@ static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
 int esim_step(EsimSim* s, EsimStepStats* out) { return step_common(s, out, false); }
 int esim_step_timed(EsimSim* s, EsimStepStats* out) { return step_common(s, out, true); }
 
+// Whole-step timing of many steps without a host round trip between them.  esim_step_timed synchronises after every step
+// (the host needs the control block to know whether the next hour has riders), so between two steps the GPU idles for the
+// host's turnaround - harmless on one GPU (the events only bracket the step), but with one process per GPU the shards drift
+// out of phase by their hosts' jitter and every step's exchange waits for the slowest host.  The fused tail lays out the
+// schedule one hour ahead (Ctrl::next_pt_mode), so step k + 1 can be enqueued before step k has been read back: the GPU
+// always has the next flush + step queued and the shards are paced by the devices alone.
+int esim_run_timed(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
+    if (steps_done) *steps_done = 0;
+    return guarded(s, [&]() -> int {
+        require_ready(s);
+        if (s->world > 1 && !s->comm && !s->v.p2p)
+            throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
+        const uint32_t start = s->steps_done;
+        const uint32_t budget = std::min<uint32_t>(max_steps, s->cfg.max_time_step - std::min(s->cfg.max_time_step, start));
+        if (!s->fused || (s->cfg.flags & ESIM_CFG_TIME_KERNELS)) {
+            // no look-ahead in the three-kernel pipeline / with per-kernel events: one synchronised step at a time
+            for (uint32_t k = 0; k < budget && !s->finished; ++k) {
+                const int rc = step_common(s, nullptr, true);
+                if (rc < 0) return rc;
+            }
+            if (steps_done) *steps_done = s->steps_done - start;
+            return s->finished ? 0 : 1;
+        }
+        struct Slot { cudaEvent_t begin = nullptr, end = nullptr, copied = nullptr; Ctrl* ctrl = nullptr; };
+        Slot slot[2];
+        Ctrl* pinned = nullptr;
+        CK(cudaMallocHost(&pinned, 2 * sizeof(Ctrl)));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreate(&slot[i].begin)); CK(cudaEventCreate(&slot[i].end));
+            CK(cudaEventCreateWithFlags(&slot[i].copied, cudaEventDisableTiming));
+            slot[i].ctrl = pinned + i;
+        }
+        auto cleanup = [&]() {
+            cudaStreamSynchronize(s->stream);
+            for (int i = 0; i < 2; ++i) { cudaEventDestroy(slot[i].begin); cudaEventDestroy(slot[i].end); cudaEventDestroy(slot[i].copied); }
+            cudaFreeHost(pinned);
+        };
+        try {
+            auto enqueue = [&](uint32_t k, uint32_t pt_mode) {
+                Slot& sl = slot[k & 1u];
+                flush_l2(s);
+                CK(cudaEventRecord(sl.begin, s->stream));
+                enqueue_step(s, (start + k + 1u) & 1u, pt_mode != ESIM_PT_NONE, true);
+                CK(cudaEventRecord(sl.end, s->stream));
+                CK(cudaMemcpyAsync(sl.ctrl, s->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+                CK(cudaEventRecord(sl.copied, s->stream));
+            };
+            // h_ctrl is current: pt_mode is the schedule of the first step, next_pt_mode that of the second
+            uint32_t pt_after_next = s->h_ctrl->next_pt_mode;
+            if (budget > 0 && !s->finished) enqueue(0, s->h_ctrl->pt_mode);
+            for (uint32_t k = 0; k < budget && !s->finished; ++k) {
+                if (k + 1 < budget) enqueue(k + 1, pt_after_next);
+                Slot& sl = slot[k & 1u];
+                CK(cudaEventSynchronize(sl.copied));
+                const uint32_t before = s->steps_done;
+                *s->h_ctrl = *sl.ctrl;                      // the control block after step k
+                pt_after_next = sl.ctrl->next_pt_mode;      // schedule of step k + 2
+                const int rc = after_steps(s);
+                if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
+                if (s->steps_done > before) {
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, sl.begin, sl.end));
+                    s->timings.total += ms * 1e-3;
+                    s->timings.steps += 1;
+                    s->step_total_ms[before] = ms;
+                }
+            }
+            CK(cudaStreamSynchronize(s->stream));   // a step enqueued past the end of the epidemic is a no-op on the device
+            fetch_ctrl(s);
+            const int rc = after_steps(s);
+            if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+        if (steps_done) *steps_done = s->steps_done - start;
+        return s->finished ? 0 : 1;
+    });
+}
+
 int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
     if (steps_done) *steps_done = 0;
     return guarded(s, [&]() -> int {

@@ -167,6 +167,38 @@ def shard_population(pop: Population, rank: int, world: int) -> Population:
         lib.esim_shard_destroy(h)
 
 
+def save_population(pop: Population, path: str, area_codes=None) -> None:
+    """Writes the binary population file (format: csrc/population_io.cpp) - what a Rust exporter of the reference's
+    SimulatorBuilder writes, and what the drivers load."""
+    lib = host_lib()
+    s = pop.as_soa()
+    off = pop.area_offsets.ctypes.data_as(_abi.u32p) if pop.area_offsets is not None else None
+    codes = None
+    if area_codes is not None:
+        if len(area_codes) != pop.n_areas:
+            raise ValueError("one code per output area")
+        codes = (C.c_char_p * pop.n_areas)(*[str(c).encode() for c in area_codes])
+    _check(lib.esim_population_save(C.byref(s), off, codes, str(path).encode()))
+
+
+def load_population(path: str):
+    """Reads a binary population file; returns (Population, area codes or None).  Corrupt files raise SimError."""
+    lib = host_lib()
+    h = C.c_void_p()
+    _check(lib.esim_population_load(str(path).encode(), C.byref(h)))
+    try:
+        v = _abi.EsimPopulationSoA()
+        _check(lib.esim_population_file_view(h, C.byref(v)))
+        p_off = lib.esim_population_file_area_offsets(h)
+        off = np.ctypeslib.as_array(p_off, shape=(v.n_areas + 1,)).copy() if p_off else None
+        codes = None
+        if v.n_areas and lib.esim_population_file_area_code(h, 0) is not None:
+            codes = [lib.esim_population_file_area_code(h, a).decode() for a in range(v.n_areas)]
+        return _from_soa(v, area_offsets=off), codes
+    finally:
+        lib.esim_population_file_destroy(h)
+
+
 def _check(code: int):
     if code < 0:
         raise _abi.SimError(code, "host library call failed")

@@ -152,6 +152,13 @@ class Simulator:
         self._check(self._lib.esim_run(self._h, int(max_steps), C.byref(n)))
         return int(n.value)
 
+    def run_timed(self, max_steps: int) -> int:
+        """Like `max_steps` calls of step(timed=True) (whole-step CUDA events, L2 flush if configured) without a host round
+        trip between the steps; returns the number of steps executed."""
+        n = C.c_uint32(0)
+        self._check(self._lib.esim_run_timed(self._h, int(max_steps), C.byref(n)))
+        return int(n.value)
+
     def simulate(self, output_name: Optional[str] = None, area_codes=None, verbose: bool = True) -> None:
         """Simulator::simulate (simulator.rs:108-127): until the disease is eradicated or max_time_step, then dump."""
         start = time.time()

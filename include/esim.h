@@ -212,6 +212,11 @@ int esim_step(EsimSim* sim, EsimStepStats* out /* nullable */);
  * ESIM_CFG_TIME_KERNELS, around each phase (the reference's record_function_time, statistics.rs:173-175);
  * accumulates into EsimTimings. */
 int esim_step_timed(EsimSim* sim, EsimStepStats* out /* nullable */);
+/* Up to max_steps timed steps (whole-step events, accumulated like esim_step_timed) without a host round trip between them:
+ * step k + 1 is enqueued before step k has been read back, so that one-process-per-GPU shards are paced by the devices and
+ * not by their hosts.  Falls back to one synchronised esim_step_timed per step in the three-kernel pipeline or with
+ * ESIM_CFG_TIME_KERNELS. */
+int esim_run_timed(EsimSim* sim, uint32_t max_steps, uint32_t* steps_done /* nullable */);
 /* Simulator::simulate (simulator.rs:108-127) without the dump: up to max_steps steps, device-resident
  * (no host synchronisation per step), stops after the step in which the disease disappears.
  * steps_done receives the number of steps executed by this call. */

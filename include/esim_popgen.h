@@ -1,5 +1,5 @@
 /*
- * esim_popgen.h — host-side synthetic census-shaped population generator and output-area sharding
+ * esim_popgen.h — host-side synthetic census-shaped population generator, output-area sharding and the population file
  * (libesim_host.so, no CUDA dependency).
  *
  * The reference builds its population from NOMIS census tables and OSM buildings
@@ -68,6 +68,22 @@ int  esim_shard_view(const EsimShard* s, EsimPopulationSoA* pop);
 const uint32_t* esim_shard_bldg_global(const EsimShard* s);
 const uint32_t* esim_shard_room_global(const EsimShard* s);
 void esim_shard_destroy(EsimShard* s);
+
+/*
+ * Binary population file (format in epidemicsimulator_b200/csrc/population_io.cpp): what a Rust exporter of the
+ * reference's `SimulatorBuilder` (sim/src/simulator_builder.rs:58-69, the state `Simulator::from` consumes at
+ * sim/src/simulator.rs:601-644) writes once, and what the drivers here load.  `area_first_citizen` (n_areas + 1 entries,
+ * needed for sharding) and `area_codes` (n_areas C strings = OutputAreaID::code, output_area.rs:42-45, the keys of
+ * exposures.json) are optional.  esim_population_load verifies magic, size, checksum and every index.
+ */
+typedef struct EsimPopulationFile EsimPopulationFile; /* opaque: owns the loaded arrays */
+int  esim_population_save(const EsimPopulationSoA* pop, const uint32_t* area_first_citizen /* nullable */,
+                          const char* const* area_codes /* nullable */, const char* path);
+int  esim_population_load(const char* path, EsimPopulationFile** out);
+int  esim_population_file_view(const EsimPopulationFile* f, EsimPopulationSoA* pop);
+const uint32_t* esim_population_file_area_offsets(const EsimPopulationFile* f);           /* NULL if not stored */
+const char*     esim_population_file_area_code(const EsimPopulationFile* f, uint32_t area); /* NULL if not stored */
+void esim_population_file_destroy(EsimPopulationFile* f);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,24 @@ def test_lockstep_reference_constants():
     assert seen["bld_exp"]
 
 
+def test_run_timed_matches_oracle_stats():
+    """esim_run_timed enqueues step k + 1 before step k has been read back (the schedule is known one hour ahead): lockdown
+    with frozen riders, vaccination, the end of the epidemic inside the call, and a second call after it."""
+    pop = synthetic_population(n_areas=60, areas_per_school=12, cross_area_fraction=0.5)
+    cfg = dict(exposure_chance=0.02, vaccination_rate=150, seed=5)
+    sim = _sim(pop, flags=_abi.CFG_FLUSH_L2, **cfg)
+    orc = Oracle(pop, default_config(**cfg))
+    n = sim.run_timed(37) + sim.run_timed(1) + sim.run_timed(1400)
+    m = orc.run(1438)
+    assert n == m
+    assert np.array_equal(sim.statistics(), orc.stats())
+    _compare_state(sim, orc, n)
+    t = sim.timings()
+    assert t["steps"] == n and t["total"] > 0
+    assert sim.run_timed(5) == orc.run(5)
+    sim.close(); orc.close()
+
+
 def test_run_matches_oracle_stats():
     pop = synthetic_population(n_areas=80, areas_per_school=16, cross_area_fraction=0.5)
     cfg = dict(exposure_chance=0.01, vaccination_rate=200, seed=11)

@@ -1,0 +1,102 @@
+// esim_run - C++ stand-in for the reference's `run --simulate` mode (run/src/main.rs:290-313) over the C ABI.
+//
+//   esim_run <population.esimpop> [--output_name=<dir/>] [--steps=<n>] [--seed=<u64>] [--device=<ordinal>] [--synthetic=<areas>]
+//
+// The reference loads census / OSM data, builds the population in-process and calls `Simulator::simulate(output_name)`
+// (sim/src/simulator.rs:108-127).  Here the population arrives as the binary file a Rust exporter of `SimulatorBuilder`
+// writes (include/esim_popgen.h) - or, with --synthetic, from the deterministic generator - and
+// the loop below is `simulate`: steps in chunks of DEBUG_ITERATION_PRINT (sim/src/config.rs:34) with the reference's
+// progress line, then `dump_to_file`.  Everything per time step runs in libesim_b200.so; there is no CPU path.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "esim.h"
+#include "esim_popgen.h"
+
+static int fail(const char* what, int code, EsimSim* sim) {
+    fprintf(stderr, "esim_run: %s failed (%d): %s\n", what, code, esim_last_error(sim) ? esim_last_error(sim) : "");
+    return 1;
+}
+
+int main(int argc, char** argv) {
+    std::string path, output = "statistics_output/v1.7/";   // the reference's default (run/src/main.rs:183)
+    uint32_t steps = 0, synthetic = 0;
+    uint64_t seed = 0;
+    int device = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a.rfind("--output_name=", 0) == 0) output = a.substr(14);
+        else if (a.rfind("--steps=", 0) == 0) steps = (uint32_t)strtoul(a.c_str() + 8, nullptr, 10);
+        else if (a.rfind("--seed=", 0) == 0) seed = strtoull(a.c_str() + 7, nullptr, 10);
+        else if (a.rfind("--device=", 0) == 0) device = atoi(a.c_str() + 9);
+        else if (a.rfind("--synthetic=", 0) == 0) synthetic = (uint32_t)strtoul(a.c_str() + 12, nullptr, 10);
+        else if (a[0] != '-') path = a;
+        else { fprintf(stderr, "esim_run: unknown option %s\n", a.c_str()); return 2; }
+    }
+    if (path.empty() && !synthetic) {
+        fprintf(stderr, "usage: esim_run <population.esimpop> [--output_name=<dir/>] [--steps=<n>] [--seed=<u64>] [--device=<n>] [--synthetic=<areas>]\n");
+        return 2;
+    }
+    const auto t_total = std::chrono::steady_clock::now();
+    EsimPopulationFile* file = nullptr;
+    EsimPopgen* gen = nullptr;
+    EsimPopulationSoA pop;
+    std::vector<const char*> codes;
+    if (synthetic) {
+        EsimPopgenParams pp;
+        esim_popgen_default_params(&pp);
+        pp.n_areas = synthetic;
+        int rc = esim_popgen_create(&pp, &gen);
+        if (rc < 0) return fail("esim_popgen_create", rc, nullptr);
+        esim_popgen_view(gen, &pop);
+    } else {
+        int rc = esim_population_load(path.c_str(), &file);
+        if (rc < 0) { fprintf(stderr, "esim_run: cannot load %s (%d)\n", path.c_str(), rc); return 1; }
+        esim_population_file_view(file, &pop);
+        if (esim_population_file_area_code(file, 0))
+            for (uint32_t a = 0; a < pop.n_areas; ++a) codes.push_back(esim_population_file_area_code(file, a));
+    }
+    EsimConfig cfg;
+    esim_default_config(&cfg);
+    cfg.seed = seed; cfg.device = device;
+    if (steps) cfg.max_time_step = steps;
+    EsimSim* sim = nullptr;
+    int rc = esim_create(&cfg, &sim);
+    if (rc < 0) return fail("esim_create", rc, nullptr);
+    rc = esim_import_population(sim, &pop);
+    if (rc < 0) return fail("esim_import_population", rc, sim);
+    printf("Finished loading data and Initialising  simulator in %.2f\n",
+           std::chrono::duration<double>(std::chrono::steady_clock::now() - t_total).count());
+    printf("Starting simulation with %u areas\n", pop.n_areas);
+
+    // Simulator::simulate: the progress line every DEBUG_ITERATION_PRINT steps (simulator.rs:118-121)
+    constexpr uint32_t DEBUG_ITERATION_PRINT = 50;
+    auto t_chunk = std::chrono::steady_clock::now();
+    uint32_t done = 0;
+    int alive = 1;
+    while (alive == 1 && done < cfg.max_time_step) {
+        uint32_t n = 0;
+        alive = esim_run(sim, DEBUG_ITERATION_PRINT, &n);
+        if (alive < 0) return fail("esim_run", alive, sim);
+        done += n;
+        if (n == 0) break;
+        EsimStepStats st;
+        if (esim_read_stats(sim, done - 1, 1, &st) == 1) {
+            const auto now = std::chrono::steady_clock::now();
+            printf("Completed %3u time steps, in: %6.2f seconds  Statistics: Hour: %u, Susceptible: %u, Exposed: %u, Infected: %u, Recovered: %u, Vaccinated: %u\n",
+                   n, std::chrono::duration<double>(now - t_chunk).count(), st.time_step, st.susceptible, st.exposed, st.infected, st.recovered, st.vaccinated);
+            t_chunk = now;
+        }
+    }
+    rc = esim_dump_statistics(sim, output.c_str(), codes.empty() ? nullptr : codes.data());
+    if (rc < 0) return fail("esim_dump_statistics", rc, sim);
+    esim_destroy(sim);
+    if (file) esim_population_file_destroy(file);
+    if (gen) esim_popgen_destroy(gen);
+    printf("Finished in %.3fs (%u time steps)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_total).count(), done);
+    return 0;
+}

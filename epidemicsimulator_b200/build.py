@@ -81,8 +81,23 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     return CUDA_LIB
 
 
+DRIVER = ROOT / "drivers" / "esim_run"
+
+
+def build_driver(force: bool = False) -> Path:
+    """drivers/esim_run: the C++ stand-in for the reference's `run --simulate` binary, linked against both libraries."""
+    src = ROOT / "drivers" / "esim_run.cpp"
+    deps = [src, INCLUDE / "esim.h", INCLUDE / "esim_popgen.h", CUDA_LIB, HOST_LIB]
+    if not force and _newer(DRIVER, deps):
+        return DRIVER
+    _run([host_compiler(), "-O2", "-std=c++17", "-Wall", "-I", str(INCLUDE), str(src), "-o", str(DRIVER),
+          "-L", str(PKG), "-lesim_b200", "-lesim_host", "-Wl,-rpath,$ORIGIN/../epidemicsimulator_b200",
+          "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-Wl,--allow-shlib-undefined"])
+    return DRIVER
+
+
 def build_all(force: bool = False, verbose: bool = False):
-    return build_host(force), build_cuda(force, verbose)
+    return build_host(force), build_cuda(force, verbose), build_driver(force)
 
 
 if __name__ == "__main__":

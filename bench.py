@@ -226,6 +226,9 @@ def main():
         run_reference(args, wl, rank, world)
         return
 
+    # rank 0 prints ONE line: keep NCCL's own version banner (NCCL_DEBUG=VERSION) off stdout
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     from epidemicsimulator_b200 import _abi, build, synthetic_population, shard_population

@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) k_step_p2p_occ3(const DevView
 //   pop from the end (:364-388)     = bus b holds ranks [n - cap(b+1), n - cap b)
 constexpr int PT_MAX_FAST = 128;            // riders of a route handled in registers + shared memory
 constexpr int PT_PER_LANE = PT_MAX_FAST / 32;
-struct PtWarpSmem {
+struct __align__(16) PtWarpSmem {
     uint32_t key[PT_MAX_FAST];
     uint32_t buscnt[PT_MAX_FAST];
 };
@@ -895,72 +895,150 @@ __device__ __noinline__ uint32_t pt_route_slow(const DevView& v, uint32_t off, u
 }
 
 // All routes, grid-stride by warp.  `ws` is this warp's shared-memory staging area.
+//
+// A route costs three dependent memory round trips (route offsets -> rider indices -> state words and global ids) and a warp
+// walks several routes, so the loads are software-pipelined over the warp's routes: while route r is being ranked, the state
+// words of route r + 1, the rider indices of route r + 2 and the offsets of route r + 3 are in flight.
+// Rank of the lane's riders in the order (key, position): #{m : (key[m], m) < (key[j], j)} as one 64-bit comparison per pair.
+// All NS slots of a lane share the walk over the route's keys (one 128-bit shared-memory load per four keys).  `skey` holds
+// the n keys; entries n .. PT_MAX_FAST-1 are never compared because their m >= n.
+template <int NS>
+__device__ __forceinline__ void pt_rank(const uint32_t* skey, uint32_t n, uint32_t lane, const uint32_t (&key)[PT_PER_LANE], uint32_t (&rank)[PT_PER_LANE]) {
+    unsigned long long mine[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { mine[s] = ((unsigned long long)key[s] << 32) | (lane + 32u * s); rank[s] = 0; }
+#pragma unroll
+    for (int s = NS; s < PT_PER_LANE; ++s) rank[s] = 0;
+    const uint4* skey4 = reinterpret_cast<const uint4*>(skey);
+    const uint32_t n4 = n >> 2;
+    constexpr int P = NS == 1 ? 4 : (NS == 2 ? 2 : 1);   // independent counters per slot: the additions do not form one dependent chain
+    uint32_t part[NS][P];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int e = 0; e < P; ++e) part[s][e] = 0;
+    for (uint32_t q = 0; q < n4; ++q) {
+        const uint4 k4 = skey4[q];
+        const uint32_t km[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned long long other = ((unsigned long long)km[e] << 32) | (4u * q + (uint32_t)e);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) part[s][e % P] += other < mine[s];
+        }
+    }
+    for (uint32_t m = n4 << 2; m < n; ++m) {
+        const unsigned long long other = ((unsigned long long)skey[m] << 32) | m;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) part[s][0] += other < mine[s];
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int e = 0; e < P; ++e) sum += part[s][e];
+        rank[s] = sum;
+    }
+}
+
+struct PtRoute {
+    uint32_t off, n;
+};
+__device__ __forceinline__ PtRoute pt_load_route(const DevView& v, uint32_t r) {
+    PtRoute x; x.off = 0; x.n = 0;
+    if (r < v.n_routes) { x.off = __ldg(&v.route_off[r]); x.n = __ldg(&v.route_off[r + 1]) - x.off; }
+    return x;
+}
+__device__ __forceinline__ void pt_load_idx(const DevView& v, const PtRoute& x, uint32_t lane, uint32_t (&idx)[PT_PER_LANE]) {
+#pragma unroll
+    for (int s = 0; s < PT_PER_LANE; ++s) {
+        const uint32_t j = lane + 32u * s;
+        idx[s] = (j < x.n && x.n <= PT_MAX_FAST) ? __ldg(&v.riders[x.off + j]) : 0xFFFFFFFFu;
+    }
+}
+__device__ __forceinline__ void pt_load_riders(const DevView& v, const uint32_t (&idx)[PT_PER_LANE], uint32_t (&w)[PT_PER_LANE], uint32_t (&gid)[PT_PER_LANE]) {
+#pragma unroll
+    for (int s = 0; s < PT_PER_LANE; ++s) {
+        w[s] = idx[s] != 0xFFFFFFFFu ? __ldcg(&v.cstate[idx[s]]) : CS_PADDING;
+        gid[s] = idx[s] != 0xFFFFFFFFu ? __ldg(&v.global_id[idx[s]]) : 0u;
+    }
+}
+
 __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint32_t t, uint32_t mask_everywhere) {
     const uint32_t te = v.mp.exposed_time, ti = v.mp.infected_time, cap = v.mp.bus_capacity;
     const uint32_t lane = lane_id();
     const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t stride = gridDim.x * warps_per_block;
     uint32_t n_exposed = 0;
-    for (uint32_t r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < v.n_routes; r += gridDim.x * warps_per_block) {
-        const uint32_t off = __ldg(&v.route_off[r]), n = __ldg(&v.route_off[r + 1]) - off;
-        if (n > PT_MAX_FAST) { n_exposed += pt_route_slow(v, off, n, t, mask_everywhere); continue; }
-        // pass 1: everything a rider needs, all loads of the lane's riders in flight together
-        uint32_t idx[PT_PER_LANE], w[PT_PER_LANE], gid[PT_PER_LANE];
+    uint32_t r = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    // fill the pipeline: offsets of three routes, rider indices of two, riders of one
+    PtRoute cur = pt_load_route(v, r), nxt = pt_load_route(v, r + stride), nn = pt_load_route(v, r + 2u * stride);
+    uint32_t idx[PT_PER_LANE], w[PT_PER_LANE], gid[PT_PER_LANE], idx_n[PT_PER_LANE];
+    pt_load_idx(v, cur, lane, idx);
+    pt_load_idx(v, nxt, lane, idx_n);
+    pt_load_riders(v, idx, w, gid);
+    for (; r < v.n_routes; r += stride) {
+        // requests of the routes behind this one
+        uint32_t w_n[PT_PER_LANE], gid_n[PT_PER_LANE], idx_nn[PT_PER_LANE];
+        pt_load_riders(v, idx_n, w_n, gid_n);
+        pt_load_idx(v, nn, lane, idx_nn);
+        const PtRoute nnn = pt_load_route(v, r + 3u * stride);
+        const uint32_t n = cur.n;
+        if (n > PT_MAX_FAST) {
+            n_exposed += pt_route_slow(v, cur.off, n, t, mask_everywhere);
+        } else {
+            // pass 1: shuffle keys and trial words of the lane's riders
+            uint32_t key[PT_PER_LANE], u_lo[PT_PER_LANE], u_hi[PT_PER_LANE];
 #pragma unroll
-        for (int s = 0; s < PT_PER_LANE; ++s) {
-            const uint32_t j = lane + 32u * s;
-            idx[s] = j < n ? __ldg(&v.riders[off + j]) : 0xFFFFFFFFu;
-        }
-#pragma unroll
-        for (int s = 0; s < PT_PER_LANE; ++s) {
-            w[s] = idx[s] != 0xFFFFFFFFu ? __ldcg(&v.cstate[idx[s]]) : CS_PADDING;
-            gid[s] = idx[s] != 0xFFFFFFFFu ? __ldg(&v.global_id[idx[s]]) : 0u;
-        }
-        uint32_t key[PT_PER_LANE], u_lo[PT_PER_LANE], u_hi[PT_PER_LANE];
-#pragma unroll
-        for (int s = 0; s < PT_PER_LANE; ++s) {
-            const uint32_t j = lane + 32u * s;
-            if (j < n) {
-                const Philox4 p = philox4x32_10(gid[s], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
-                key[s] = p.v[0]; u_lo[s] = p.v[2]; u_hi[s] = p.v[3];
-                ws->key[j] = key[s];
-            }
-            ws->buscnt[j] = 0;
-        }
-        __syncwarp();
-        // pass 2: rank in the shuffled order -> bus; infected riders per bus (PublicTransport::exposure_count)
-        uint32_t bus[PT_PER_LANE];
-#pragma unroll
-        for (int s = 0; s < PT_PER_LANE; ++s) {
-            const uint32_t j = lane + 32u * s;
-            bus[s] = 0;
-            if (j < n) {
-                uint32_t rank = 0;
-                for (uint32_t m = 0; m < n; ++m) {
-                    const uint32_t km = ws->key[m];
-                    rank += (km < key[s]) || (km == key[s] && m < j);
+            for (int s = 0; s < PT_PER_LANE; ++s) {
+                const uint32_t j = lane + 32u * s;
+                key[s] = u_lo[s] = u_hi[s] = 0u;
+                if (j < n) {
+                    const Philox4 p = philox4x32_10(gid[s], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
+                    key[s] = p.v[0]; u_lo[s] = p.v[2]; u_hi[s] = p.v[3];
+                    ws->key[j] = key[s];
                 }
-                bus[s] = (n - 1 - rank) / cap;
-                if (status_at(w[s], t, te, ti) == ST_I) atomicAdd(&ws->buscnt[bus[s]], 1u);
+                ws->buscnt[j] = 0;
             }
-        }
-        __syncwarp();
-        // pass 3: every susceptible rider of a bus with infected riders is exposed with n = infected on that bus
+            __syncwarp();
+            // pass 2: rank in the shuffled order -> bus; infected riders per bus (PublicTransport::exposure_count)
+            uint32_t rank[PT_PER_LANE];
+            if (n <= 32u) pt_rank<1>(ws->key, n, lane, key, rank);
+            else if (n <= 64u) pt_rank<2>(ws->key, n, lane, key, rank);
+            else pt_rank<PT_PER_LANE>(ws->key, n, lane, key, rank);
+            uint32_t bus[PT_PER_LANE];
 #pragma unroll
-        for (int s = 0; s < PT_PER_LANE; ++s) {
-            const uint32_t j = lane + 32u * s;
-            if (j >= n) continue;
-            const uint32_t n_b = ws->buscnt[bus[s]];
-            if (v.record_buses) { v.rec_bus[idx[s]] = bus[s]; v.rec_businf[idx[s]] = n_b; }
-            if (n_b == 0 || !is_susceptible(w[s])) continue;
-            const uint32_t mc = (mask_everywhere && !(w[s] & CS_COMPLIANT)) ? 256u : 0u;
-            const unsigned long long thr = __ldg(&v.thr[mc + (n_b & 255u)]);
-            const uint64_t m52 = (((uint64_t)u_hi[s] << 32) | (uint64_t)u_lo[s]) >> 12;
-            if (m52 < thr) {
-                v.cstate[idx[s]] = w[s] | (t + EXPOSURE_BIAS) | CS_VIA_PT;
-                ++n_exposed;
+            for (int s = 0; s < PT_PER_LANE; ++s) {
+                const uint32_t j = lane + 32u * s;
+                bus[s] = 0;
+                if (j < n) {
+                    bus[s] = (n - 1 - rank[s]) / cap;
+                    if (status_at(w[s], t, te, ti) == ST_I) atomicAdd(&ws->buscnt[bus[s]], 1u);
+                }
             }
+            __syncwarp();
+            // pass 3: every susceptible rider of a bus with infected riders is exposed with n = infected on that bus
+#pragma unroll
+            for (int s = 0; s < PT_PER_LANE; ++s) {
+                const uint32_t j = lane + 32u * s;
+                if (j >= n) continue;
+                const uint32_t n_b = ws->buscnt[bus[s]];
+                if (v.record_buses) { v.rec_bus[idx[s]] = bus[s]; v.rec_businf[idx[s]] = n_b; }
+                if (n_b == 0 || !is_susceptible(w[s])) continue;
+                const uint32_t mc = (mask_everywhere && !(w[s] & CS_COMPLIANT)) ? 256u : 0u;
+                const unsigned long long thr = __ldg(&v.thr[mc + (n_b & 255u)]);
+                const uint64_t m52 = (((uint64_t)u_hi[s] << 32) | (uint64_t)u_lo[s]) >> 12;
+                if (m52 < thr) {
+                    v.cstate[idx[s]] = w[s] | (t + EXPOSURE_BIAS) | CS_VIA_PT;
+                    ++n_exposed;
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        // advance the pipeline
+        cur = nxt; nxt = nn; nn = nnn;
+#pragma unroll
+        for (int s = 0; s < PT_PER_LANE; ++s) { idx[s] = idx_n[s]; w[s] = w_n[s]; gid[s] = gid_n[s]; idx_n[s] = idx_nn[s]; }
     }
     const uint32_t s = warp_sum(n_exposed);
     if (lane == 0 && s) atomicAdd(&v.ctrl->new_exp_pt, s);
@@ -1905,8 +1983,14 @@ void launch_expose(const DevView& v, cudaStream_t s) {
 }
 void launch_pt(const DevView& v, cudaStream_t s) {
     if (v.n_routes == 0) return;
-    // one warp per route, grid-stride; at most 8 resident blocks per SM
-    launch_step_kernel(k_pt, blocks_for(v.n_routes, PT_THREADS / 32, (uint32_t)sm_count() * 8u), PT_THREADS, 0, s, v);
+    // one warp per route, grid-stride over one resident wave: the warps pipeline their loads over the routes they walk
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (const char* env = getenv("ESIM_PT_BLOCKS")) per_sm = atoi(env);
+        if (per_sm <= 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt, PT_THREADS, 0) != cudaSuccess) per_sm = 0;
+        if (per_sm <= 0) per_sm = 4;
+    }
+    launch_step_kernel(k_pt, blocks_for(v.n_routes, PT_THREADS / 32, (uint32_t)sm_count() * (uint32_t)per_sm), PT_THREADS, 0, s, v);
 }
 void launch_tail(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_tail, 1, TAIL_THREADS, HT_BYTES, s, v);

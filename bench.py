@@ -361,7 +361,9 @@ def main():
             "kernel_seconds_note": "second pass over the same steps with a CUDA event between every two kernels (each event "
                                    "adds ~2.5 us and ends the programmatic overlap of consecutive kernels)",
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic_from_profile(dominant), "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         # the committed ncu capture is of the BASELINE per-GPU workload: no figure for other sizes
+                         "traffic": traffic_from_profile(dominant) if not args.areas else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes / max(steps_run, 1),
                          "avg_launch_us": dom_s / max(steps_run, 1) * 1e6},
             "clocks": clock_info,

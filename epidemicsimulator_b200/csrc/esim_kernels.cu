@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
 constexpr int STEP_THREADS = 256;
 constexpr uint32_t STEP_PF = 2;   // prefetch distance in iterations
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__constant__ int g_tail_fence = 0;   // ESIM_TAIL_FENCE=1: the peer-to-peer tail's conservative fences (see vax_prepare_fused, tail_phase)
 __constant__ int g_pf = 0;        // ESIM_STEP_PF=1: L2 prefetches of the streams two iterations ahead (no gain cold, slower warm: profiles/README.md)
 
 template <bool EAGER, bool AT_WORK, bool P2P, bool ORDERED = false>
@@ -1462,7 +1463,12 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         __syncthreads();                                   // every thread's corrections are issued
         if (tid == 0 && sm.fix[7]) __threadfence_system();   // cumulative: covers the other threads' reductions observed through the barrier
         __syncthreads();
-        if (tid < v.world && tid != v.rank) st_release_sys(sm.mail[tid] + MAIL_FLAG_C + v.rank, sm.c.t + 1u);
+        // The flag orders nothing but those corrections (fenced above when there are any): a release store would also wait for
+        // this thread's earlier pair stores to be acknowledged over NVLink - a round trip on the tail's critical path.
+        if (tid < v.world && tid != v.rank) {
+            if (g_tail_fence || sm.fix[7]) st_release_sys(sm.mail[tid] + MAIL_FLAG_C + v.rank, sm.c.t + 1u);
+            else asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(sm.mail[tid] + MAIL_FLAG_C + v.rank), "r"(sm.c.t + 1u) : "memory");
+        }
     }
 
     if (tid == 0) {
@@ -1733,7 +1739,10 @@ __device__ __forceinline__ void vax_prepare_fused(const DevView& v, uint32_t* dy
     // visible to this grid (it waited for that grid), and the fence makes them precede the pairs for every observer.
     // One thread fences (it has observed the previous grid's writes; fences are cumulative), the barrier orders the other
     // threads' stores after it.
-    if (c->pushed_any) {
+    // Every producer block that pushed has already fenced system-wide before it announced itself (signal_block_done), and this
+    // block has observed all announcements (wait_blocks_done) or the completion of the grid: the extra fence is only needed
+    // when that hand-over is switched off for experiments.
+    if (c->pushed_any && g_tail_fence) {
         if (tid == 0) __threadfence_system();
         __syncthreads();
     }
@@ -1934,6 +1943,7 @@ int configure_kernels() {
     if (const char* env = getenv("ESIM_STEP_BLOCKS")) g_step_blocks_per_sm = atoi(env);
     if (const char* env = getenv("ESIM_STEP_V")) g_step_variant = atoi(env);
     if (const char* env = getenv("ESIM_TAIL_FLAGWAIT")) g_tail_flag_wait = env[0] != '0';
+    if (const char* env = getenv("ESIM_TAIL_FENCE")) { const int on = env[0] != '0'; if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tail_fence, &on, sizeof(on)); }
     if (const char* env = getenv("ESIM_STEP_PF")) { const int on = env[0] != '0'; if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_pf, &on, sizeof(on)); }
     if (const char* env = getenv("ESIM_STEP_OCC4")) { g_step_occ4 = env[0] == '1'; if (!g_step_occ4 && !getenv("ESIM_STEP_BLOCKS")) g_step_blocks_per_sm = 3; }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_BYTES);

@@ -1,0 +1,80 @@
+//! Drop-in body for sim/src/simulator.rs: the public API (`From<SimulatorBuilder>`, `step`, `simulate`, the pub fields
+//! `visualisation` reads) stays, everything per time step runs in libesim_b200.so.  Not compiled in this repository.
+use std::ffi::{CStr, CString};
+use anyhow::Context;
+use sim_b200_sys as ffi;
+
+pub struct Simulator {
+    handle: *mut ffi::EsimSim,
+    pub area_code: String,                                   // simulator.rs:88
+    pub output_area_lookup: HashMap<String, u32>,            // simulator.rs:90
+    area_codes: Vec<CString>,                                // OutputAreaID::code per area index, for exposures.json
+    max_time_step: u32,
+    n_citizens: usize,
+}
+
+fn check(sim: *mut ffi::EsimSim, rc: i32) -> anyhow::Result<i32> {
+    if rc >= 0 { return Ok(rc); }
+    let msg = unsafe { CStr::from_ptr(ffi::esim_last_error(sim)) }.to_string_lossy().into_owned();
+    // ESIM_ERR_* are numbered after the SimError variants (sim/src/error.rs:24-52)
+    Err(SimError::from_code(rc, msg).into())
+}
+
+impl From<SimulatorBuilder> for Simulator {                 // replaces simulator.rs:601-644
+    fn from(builder: SimulatorBuilder) -> Self {
+        let soa = export_b200::to_soa(&builder);            // the arrays of export_b200.rs, kept alive for the call below
+        let mut cfg: ffi::EsimConfig = unsafe { std::mem::zeroed() };
+        unsafe { ffi::esim_default_config(&mut cfg) };
+        let d = &builder.disease_model;                      // disease.rs:97-109
+        cfg.exposure_chance = d.exposure_chance; cfg.exposed_time = d.exposed_time as u32; cfg.infected_time = d.infected_time as u32;
+        cfg.max_time_step = d.max_time_step as u32; cfg.vaccination_rate = d.vaccination_rate as u32;
+        cfg.mask_effectiveness = d.mask_percentage;
+        let mut handle = std::ptr::null_mut();
+        check(std::ptr::null_mut(), unsafe { ffi::esim_create(&cfg, &mut handle) }).expect("no B200: there is no CPU fallback");
+        check(handle, unsafe { ffi::esim_import_population(handle, &soa.view()) }).expect("population rejected");
+        Simulator { handle, area_code: builder.area_code, output_area_lookup: builder.output_area_lookup,
+                    area_codes: soa.area_codes, max_time_step: cfg.max_time_step, n_citizens: soa.home.len() }
+    }
+}
+
+impl Simulator {
+    /// simulator.rs:131-152
+    pub fn step(&mut self) -> anyhow::Result<bool> {
+        let mut s = ffi::EsimStepStats::default();
+        Ok(check(self.handle, unsafe { ffi::esim_step(self.handle, &mut s) })? == 1)
+    }
+
+    /// simulator.rs:108-127: the loop stays on the device between two progress lines
+    pub fn simulate(&mut self, output_name: String) -> anyhow::Result<()> {
+        let mut start_time = Instant::now();
+        let mut done = 0u32;
+        while done < self.max_time_step {
+            let mut n = 0u32;
+            let alive = check(self.handle, unsafe { ffi::esim_run(self.handle, DEBUG_ITERATION_PRINT as u32, &mut n) })?;
+            done += n;
+            if n > 0 {
+                let mut last = ffi::EsimStepStats::default();
+                check(self.handle, unsafe { ffi::esim_read_stats(self.handle, done - 1, 1, &mut last) })?;
+                println!("Completed {: >3} time steps, in: {: >6} seconds  Statistics: {:?},   Memory usage: {}",
+                         n, format!("{:.2}", start_time.elapsed().as_secs_f64()), last, get_memory_usage()?);
+                start_time = Instant::now();
+            }
+            if alive == 0 || n == 0 { break; }
+        }
+        let dir = CString::new(output_name).context("output name")?;
+        let codes: Vec<*const c_char> = self.area_codes.iter().map(|c| c.as_ptr()).collect();
+        check(self.handle, unsafe { ffi::esim_dump_statistics(self.handle, dir.as_ptr(), codes.as_ptr()) })?;   // statistics.rs:113-150
+        Ok(())
+    }
+
+    /// What `visualisation` reads from `output_areas[*].citizens` (citizen_connections.rs:37-60): refreshed on demand
+    pub fn citizen_states(&mut self) -> anyhow::Result<(Vec<u8>, Vec<u16>, Vec<u32>)> {
+        let (mut status, mut timer, mut cur) = (vec![0u8; self.n_citizens], vec![0u16; self.n_citizens], vec![0u32; self.n_citizens]);
+        let mut view = ffi::EsimStateView { status: status.as_mut_ptr(), timer: timer.as_mut_ptr(), current_bldg: cur.as_mut_ptr(),
+                                            on_pt: std::ptr::null_mut(), vax_eligible: std::ptr::null_mut() };
+        check(self.handle, unsafe { ffi::esim_read_state(self.handle, &mut view) })?;
+        Ok((status, timer, cur))
+    }
+}
+
+impl Drop for Simulator { fn drop(&mut self) { unsafe { ffi::esim_destroy(self.handle) } } }

@@ -90,3 +90,32 @@ def test_missing_file_is_an_io_error(tmp_path):
     with pytest.raises(SimError) as e:
         load_population(tmp_path / "nope.esimpop")
     assert e.value.code == -11
+
+
+def test_file_from_an_independent_writer_loads(pop, tmp_path):
+    """The layout as documented (and as integration/rust/export_b200.rs writes it: status + timer + area offsets + area codes,
+    no age / occupation / global ids), produced here without the library's writer."""
+    def padded(a):
+        b = np.ascontiguousarray(a).tobytes()
+        return b + b"\0" * ((64 - len(b) % 64) % 64)
+    codes = ["E%05d" % a for a in range(pop.n_areas)]
+    blob = "".join(codes).encode()
+    code_off = np.cumsum([0] + [len(c) for c in codes]).astype(np.uint32)
+    arrays = [pop.home_bldg, pop.work_bldg, pop.room, pop.flags, pop.status, pop.timer, pop.bldg_area, pop.bldg_type,
+              pop.room_bldg, pop.area_offsets.astype(np.uint32), code_off, np.frombuffer(blob, np.uint8)]
+    payload = b"".join(padded(a) for a in arrays)
+    header = b"ESIMPOP\x01" + np.array([1, 128, pop.n_citizens, pop.n_areas, pop.n_buildings, pop.n_rooms, 0, 0, 0, 0,
+                                         4 | 8 | 32 | 64, len(blob)], np.uint32).tobytes() + np.uint64(len(payload)).tobytes()
+    header += b"\0" * (128 - len(header))
+    body = header + payload
+    h = 14695981039346656037
+    for chunk in (body,):
+        for byte in chunk:
+            h = ((h ^ byte) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    path = tmp_path / "independent.esimpop"
+    path.write_bytes(body + h.to_bytes(8, "little"))
+    back, got = load_population(path)
+    for name in ("home_bldg", "work_bldg", "room", "flags", "status", "timer", "bldg_area", "bldg_type", "room_bldg"):
+        assert np.array_equal(getattr(back, name), getattr(pop, name)), name
+    assert got == codes and np.array_equal(back.area_offsets, pop.area_offsets)
+    assert back.age.max() == 0 and back.global_id is None      # optional arrays that were not stored

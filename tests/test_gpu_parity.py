@@ -221,6 +221,37 @@ def test_full_size_run_properties():
     sim.close(); again.close(); other.close()
 
 
+def test_yorkshire_and_humber_size_with_interventions():
+    """BASELINE configs[2]: ~5.3 M citizens (17 246 output areas, `simulation_analysis` logs), lockdown, masks and the
+    vaccination rollout enabled (reference constants).  Too big for the oracle in a test: size-independent properties."""
+    pop = synthetic_population(n_areas=17246, areas_per_school=103)
+    assert 5.0e6 < pop.n_citizens < 5.6e6
+    sim = _sim(pop, seed=7, exposure_chance=0.002)     # a faster epidemic so that every intervention fires within the run
+    n = sim.run(3000)
+    st = sim.statistics()
+    f = {name: i for i, name in enumerate(_abi.STATS_FIELDS)}
+    assert n == st.shape[0] and (st[:, 1:6].sum(1) == pop.n_citizens).all()
+    total = float(pop.n_citizens)
+    share = st[:, f["infected"]] / total
+    lock = st[:, f["lockdown_hours"]] != _abi.NONE_U32
+    vax = st[:, f["vaccination_hours"]] != _abi.NONE_U32
+    assert lock.any() and vax.any() and (st[:, f["mask_status"]] == _abi.MASK_EVERYWHERE).any()
+    # InterventionStatus::update_status (interventions.rs:110-184): strict thresholds on the infected share of the same step
+    assert np.array_equal(lock, share > 0.0034)
+    first = int(np.argmax(share > 0.005))
+    assert not vax[:first].any() and vax[first:].all()                 # the vaccination programme latches on
+    # choose_multiple(85 * 18) per hour from the hour after the event while more than that many are eligible
+    picks = st[:, f["vaccinated_now"]]
+    assert picks[:first].sum() == 0 and (picks[first:][st[first:, f["vaccine_eligible"]] > 1530] == 1530).all()
+    assert (np.diff(st[first:, f["vaccine_eligible"]]) <= 0).all()      # the eligible set only shrinks (PT exposures)
+    # while locked down nobody moves: at_work / pt_mode keep the value of the hour the lockdown started
+    moves = (np.diff(st[:, f["at_work"]]) != 0) | (np.diff(st[:, f["pt_mode"]]) != 0)
+    assert not moves[lock[:-1]].any()
+    s = sim.state()
+    assert np.bincount(s["status"], minlength=5).tolist() == st[-1, 1:6].tolist()
+    sim.close()
+
+
 def test_error_paths():
     from epidemicsimulator_b200.simulator import Simulator
     sim = Simulator()

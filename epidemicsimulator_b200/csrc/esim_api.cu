@@ -133,6 +133,8 @@ struct EsimSim {
     DevBuf<uint32_t> cstate, home_cell, work_cell, gid, room_parent, cnt_all, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
         rec_bus, rec_businf;
     DevBuf<unsigned long long> thr;
+    DevBuf<uint4> pt_span;              // public transport: whole routes packed into spans of <= 128 riders (see pt_phase)
+    DevBuf<uint16_t> pt_seg;            // per rider: start of its route inside the span | riders of the route << 8
     DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
     DevBuf<uint32_t> exch, vax_cand;    // sharded runs
     DevBuf<uint32_t> peer_mail;         // peer-to-peer exchange (sharded runs): this shard's mailbox in HBM
@@ -195,6 +197,7 @@ struct EsimSim {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt_all.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
+        pt_span.release(); pt_seg.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
         if (stream) cudaStreamSynchronize(stream);
         ktrace_min.release(); ktrace_max.release();
@@ -585,6 +588,38 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         }
         CK(cudaMemcpyAsync(s->route_off.p + n_routes, &n_riders, 4, cudaMemcpyHostToDevice, st));  // closing offset
         tr.mark("routes (select, sort, heads)", st);
+        // ---- spans: consecutive whole routes packed greedily into groups of at most ESIM_PT_SPAN_RIDERS riders, one warp of the
+        // public-transport kernel per span (a route per warp wastes the warp when a route has one or two riders: cross-area
+        // workplaces give (home area, work area) routes of a handful of citizens each).  A longer route is a span of its own.
+        uint32_t n_spans = 0;
+        if (n_routes) {
+            std::vector<uint32_t> h_off((size_t)n_routes + 1);
+            CK(cudaMemcpyAsync(h_off.data(), s->route_off.p, h_off.size() * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::vector<uint4> spans;
+            std::vector<uint16_t> seg(n_riders, 0);
+            spans.reserve(n_routes / 2 + 1);
+            uint32_t r = 0;
+            while (r < n_routes) {
+                const uint32_t first = r, span_off = h_off[r];
+                uint32_t total = h_off[r + 1] - h_off[r];
+                ++r;
+                if (total <= ESIM_PT_SPAN_RIDERS)
+                    while (r < n_routes && total + (h_off[r + 1] - h_off[r]) <= ESIM_PT_SPAN_RIDERS) { total += h_off[r + 1] - h_off[r]; ++r; }
+                spans.push_back(make_uint4(span_off, total, first, r - first));
+                if (total <= ESIM_PT_SPAN_RIDERS)
+                    for (uint32_t q = first; q < r; ++q) {
+                        const uint32_t start = h_off[q] - span_off, len = h_off[q + 1] - h_off[q];
+                        for (uint32_t j = h_off[q]; j < h_off[q + 1]; ++j) seg[j] = (uint16_t)(start | (len << 8));
+                    }
+            }
+            n_spans = (uint32_t)spans.size();
+            s->pt_span.alloc(n_spans); s->pt_seg.alloc(std::max<uint32_t>(n_riders, 1));
+            CK(cudaMemcpyAsync(s->pt_span.p, spans.data(), spans.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s->pt_seg.p, seg.data(), seg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));   // the staging vectors go out of scope
+        }
+        tr.mark("public-transport spans", st);
 
         unsigned long long thr[512];
         build_thresholds(s->cfg, thr);
@@ -642,6 +677,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.global_id = s->gid.p;
         v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt_all.p; v.cnt[1] = s->cnt_all.p + s->cnt_stride; v.cnt[2] = s->cnt_all.p + 2 * s->cnt_stride;
         v.fused = s->fused ? 1u : 0u; v.boot = 0; v.thr = s->thr.p;
+        v.n_spans = n_spans; v.pt_span = s->pt_span.p; v.pt_seg = s->pt_seg.p;
         v.route_off = s->route_off.p; v.riders = s->riders.p; v.pt_key = s->pt_key.p; v.pt_bus = s->pt_bus.p;
         v.pt_buscnt = s->pt_buscnt.p; v.rec_bus = s->rec_bus.p; v.rec_businf = s->rec_businf.p;
         v.world = s->world; v.exch = s->exch.p; v.vax_cand = s->vax_cand.p;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #define ESIM_VAX_SHARD_DRAWS 4096u   // vaccination candidate draws a sharded run examines per step
+#define ESIM_PT_SPAN_RIDERS 128u     // riders of the routes one warp of the public-transport kernel handles together
 
 #include "esim.h"
 
@@ -138,6 +139,9 @@ struct DevView {
     // public transport
     const uint32_t* route_off;   // [n_routes + 1]
     const uint32_t* riders;      // [n_riders] citizen index, grouped by route, ascending inside a route
+    uint32_t n_spans;            // whole routes packed into spans of <= ESIM_PT_SPAN_RIDERS riders (a longer route: its own span)
+    const uint4* pt_span;        // [n_spans] x = first rider (index into riders), y = riders, z = first route, w = routes
+    const uint16_t* pt_seg;      // [n_riders] start of the rider's route inside its span | riders of that route << 8
     uint32_t* pt_key;      // [n_riders] scratch: shuffle keys
     uint32_t* pt_bus;      // [n_riders] scratch: bus of each rider
     uint32_t* pt_buscnt;   // [n_riders] scratch: infected riders per bus (route_off[r] + bus)

@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 3) k_step_p2p_occ3(const DevView
 // the same hours (citizen.rs:179-195), so the riders of a route are static and stored as a CSR built at import.
 //   shuffle (simulator.rs:362)      = ascending order of (Philox key, position in the route list)
 //   pop from the end (:364-388)     = bus b holds ranks [n - cap(b+1), n - cap b)
-constexpr int PT_MAX_FAST = 128;            // riders of a route handled in registers + shared memory
+constexpr int PT_MAX_FAST = ESIM_PT_SPAN_RIDERS;   // riders of a span (whole routes) handled in registers + shared memory
 constexpr int PT_PER_LANE = PT_MAX_FAST / 32;
 struct __align__(16) PtWarpSmem {
     uint32_t key[PT_MAX_FAST];
@@ -895,11 +895,13 @@ __device__ __noinline__ uint32_t pt_route_slow(const DevView& v, uint32_t off, u
     return n_exposed;
 }
 
-// All routes, grid-stride by warp.  `ws` is this warp's shared-memory staging area.
+// All routes, grid-stride by warp over SPANS: whole consecutive routes packed at import into groups of at most PT_MAX_FAST
+// riders (DevView::pt_span, DevView::pt_seg), so that a warp is full whether the routes have fifty riders or two (cross-area
+// workplaces give (home area, work area) routes of a handful of citizens each).  `ws` is this warp's shared-memory staging area.
 //
-// A route costs three dependent memory round trips (route offsets -> rider indices -> state words and global ids) and a warp
-// walks several routes, so the loads are software-pipelined over the warp's routes: while route r is being ranked, the state
-// words of route r + 1, the rider indices of route r + 2 and the offsets of route r + 3 are in flight.
+// A span costs three dependent memory round trips (span record -> rider indices and segments -> state words and global ids)
+// and a warp walks several spans, so the loads are software-pipelined: while span k is being ranked, the state words of span
+// k + 1, the rider indices of span k + 2 and the record of span k + 3 are in flight.
 // Rank of the lane's riders in the order (key, position): #{m : (key[m], m) < (key[j], j)} as one 64-bit comparison per pair.
 // All NS slots of a lane share the walk over the route's keys (one 128-bit shared-memory load per four keys).  `skey` holds
 // the n keys; entries n .. PT_MAX_FAST-1 are never compared because their m >= n.
@@ -942,26 +944,30 @@ __device__ __forceinline__ void pt_rank(const uint32_t* skey, uint32_t n, uint32
     }
 }
 
-struct PtRoute {
-    uint32_t off, n;
+struct PtSpan {
+    uint32_t off, n, n_routes;
 };
-__device__ __forceinline__ PtRoute pt_load_route(const DevView& v, uint32_t r) {
-    PtRoute x; x.off = 0; x.n = 0;
-    if (r < v.n_routes) { x.off = __ldg(&v.route_off[r]); x.n = __ldg(&v.route_off[r + 1]) - x.off; }
+__device__ __forceinline__ PtSpan pt_load_span(const DevView& v, uint32_t k) {
+    PtSpan x; x.off = 0; x.n = 0; x.n_routes = 0;
+    if (k < v.n_spans) { const uint4 r = __ldg(&v.pt_span[k]); x.off = r.x; x.n = r.y; x.n_routes = r.w; }
     return x;
 }
-__device__ __forceinline__ void pt_load_idx(const DevView& v, const PtRoute& x, uint32_t lane, uint32_t (&idx)[PT_PER_LANE]) {
+__device__ __forceinline__ void pt_load_idx(const DevView& v, const PtSpan& x, uint32_t lane, uint32_t (&idx)[PT_PER_LANE]) {
 #pragma unroll
     for (int s = 0; s < PT_PER_LANE; ++s) {
         const uint32_t j = lane + 32u * s;
         idx[s] = (j < x.n && x.n <= PT_MAX_FAST) ? __ldg(&v.riders[x.off + j]) : 0xFFFFFFFFu;
     }
 }
-__device__ __forceinline__ void pt_load_riders(const DevView& v, const uint32_t (&idx)[PT_PER_LANE], uint32_t (&w)[PT_PER_LANE], uint32_t (&gid)[PT_PER_LANE]) {
+// state words, global ids and route segments of a span's riders (the segments only need the span record)
+__device__ __forceinline__ void pt_load_riders(const DevView& v, const PtSpan& x, uint32_t lane, const uint32_t (&idx)[PT_PER_LANE],
+                                               uint32_t (&w)[PT_PER_LANE], uint32_t (&gid)[PT_PER_LANE], uint32_t (&seg)[PT_PER_LANE]) {
 #pragma unroll
     for (int s = 0; s < PT_PER_LANE; ++s) {
-        w[s] = idx[s] != 0xFFFFFFFFu ? __ldcg(&v.cstate[idx[s]]) : CS_PADDING;
-        gid[s] = idx[s] != 0xFFFFFFFFu ? __ldg(&v.global_id[idx[s]]) : 0u;
+        const bool have = idx[s] != 0xFFFFFFFFu;
+        w[s] = have ? __ldcg(&v.cstate[idx[s]]) : CS_PADDING;
+        gid[s] = have ? __ldg(&v.global_id[idx[s]]) : 0u;
+        seg[s] = have ? (uint32_t)__ldg(&v.pt_seg[x.off + lane + 32u * s]) : 0u;
     }
 }
 
@@ -971,22 +977,22 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t stride = gridDim.x * warps_per_block;
     uint32_t n_exposed = 0;
-    uint32_t r = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    // fill the pipeline: offsets of three routes, rider indices of two, riders of one
-    PtRoute cur = pt_load_route(v, r), nxt = pt_load_route(v, r + stride), nn = pt_load_route(v, r + 2u * stride);
-    uint32_t idx[PT_PER_LANE], w[PT_PER_LANE], gid[PT_PER_LANE], idx_n[PT_PER_LANE];
+    uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    // fill the pipeline: records of three spans, rider indices of two, riders of one
+    PtSpan cur = pt_load_span(v, k), nxt = pt_load_span(v, k + stride), nn = pt_load_span(v, k + 2u * stride);
+    uint32_t idx[PT_PER_LANE], seg[PT_PER_LANE], w[PT_PER_LANE], gid[PT_PER_LANE], idx_n[PT_PER_LANE];
     pt_load_idx(v, cur, lane, idx);
     pt_load_idx(v, nxt, lane, idx_n);
-    pt_load_riders(v, idx, w, gid);
-    for (; r < v.n_routes; r += stride) {
-        // requests of the routes behind this one
-        uint32_t w_n[PT_PER_LANE], gid_n[PT_PER_LANE], idx_nn[PT_PER_LANE];
-        pt_load_riders(v, idx_n, w_n, gid_n);
+    pt_load_riders(v, cur, lane, idx, w, gid, seg);
+    for (; k < v.n_spans; k += stride) {
+        // requests of the spans behind this one
+        uint32_t w_n[PT_PER_LANE], gid_n[PT_PER_LANE], seg_n[PT_PER_LANE], idx_nn[PT_PER_LANE];
+        pt_load_riders(v, nxt, lane, idx_n, w_n, gid_n, seg_n);
         pt_load_idx(v, nn, lane, idx_nn);
-        const PtRoute nnn = pt_load_route(v, r + 3u * stride);
+        const PtSpan nnn = pt_load_span(v, k + 3u * stride);
         const uint32_t n = cur.n;
         if (n > PT_MAX_FAST) {
-            n_exposed += pt_route_slow(v, cur.off, n, t, mask_everywhere);
+            n_exposed += pt_route_slow(v, cur.off, n, t, mask_everywhere);   // a single long route
         } else {
             // pass 1: shuffle keys and trial words of the lane's riders
             uint32_t key[PT_PER_LANE], u_lo[PT_PER_LANE], u_hi[PT_PER_LANE];
@@ -1002,19 +1008,34 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
                 ws->buscnt[j] = 0;
             }
             __syncwarp();
-            // pass 2: rank in the shuffled order -> bus; infected riders per bus (PublicTransport::exposure_count)
+            // pass 2: rank in the shuffled order of the rider's own route -> bus; infected riders per bus
+            // (PublicTransport::exposure_count).  Counter of bus b of a route = slot (route start + b): b < riders of the route.
             uint32_t rank[PT_PER_LANE];
-            if (n <= 32u) pt_rank<1>(ws->key, n, lane, key, rank);
-            else if (n <= 64u) pt_rank<2>(ws->key, n, lane, key, rank);
-            else pt_rank<PT_PER_LANE>(ws->key, n, lane, key, rank);
+            if (cur.n_routes == 1u) {
+                if (n <= 32u) pt_rank<1>(ws->key, n, lane, key, rank);
+                else if (n <= 64u) pt_rank<2>(ws->key, n, lane, key, rank);
+                else pt_rank<PT_PER_LANE>(ws->key, n, lane, key, rank);
+            } else {
+#pragma unroll
+                for (int s = 0; s < PT_PER_LANE; ++s) {
+                    const uint32_t j = lane + 32u * s;
+                    rank[s] = 0;
+                    if (j < n) {
+                        const uint32_t first = seg[s] & 0xFFu, last = first + (seg[s] >> 8);
+                        const unsigned long long mine = ((unsigned long long)key[s] << 32) | j;
+                        for (uint32_t m = first; m < last; ++m) rank[s] += (((unsigned long long)ws->key[m] << 32) | m) < mine;
+                    }
+                }
+            }
             uint32_t bus[PT_PER_LANE];
 #pragma unroll
             for (int s = 0; s < PT_PER_LANE; ++s) {
                 const uint32_t j = lane + 32u * s;
                 bus[s] = 0;
                 if (j < n) {
-                    bus[s] = (n - 1 - rank[s]) / cap;
-                    if (status_at(w[s], t, te, ti) == ST_I) atomicAdd(&ws->buscnt[bus[s]], 1u);
+                    const uint32_t first = seg[s] & 0xFFu, len = seg[s] >> 8;
+                    bus[s] = (len - 1 - rank[s]) / cap;
+                    if (status_at(w[s], t, te, ti) == ST_I) atomicAdd(&ws->buscnt[first + bus[s]], 1u);
                 }
             }
             __syncwarp();
@@ -1023,7 +1044,7 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
             for (int s = 0; s < PT_PER_LANE; ++s) {
                 const uint32_t j = lane + 32u * s;
                 if (j >= n) continue;
-                const uint32_t n_b = ws->buscnt[bus[s]];
+                const uint32_t n_b = ws->buscnt[(seg[s] & 0xFFu) + bus[s]];
                 if (v.record_buses) { v.rec_bus[idx[s]] = bus[s]; v.rec_businf[idx[s]] = n_b; }
                 if (n_b == 0 || !is_susceptible(w[s])) continue;
                 const uint32_t mc = (mask_everywhere && !(w[s] & CS_COMPLIANT)) ? 256u : 0u;
@@ -1039,7 +1060,9 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
         // advance the pipeline
         cur = nxt; nxt = nn; nn = nnn;
 #pragma unroll
-        for (int s = 0; s < PT_PER_LANE; ++s) { idx[s] = idx_n[s]; w[s] = w_n[s]; gid[s] = gid_n[s]; idx_n[s] = idx_nn[s]; }
+        for (int s = 0; s < PT_PER_LANE; ++s) {
+            idx[s] = idx_n[s]; seg[s] = seg_n[s]; w[s] = w_n[s]; gid[s] = gid_n[s]; idx_n[s] = idx_nn[s];
+        }
     }
     const uint32_t s = warp_sum(n_exposed);
     if (lane == 0 && s) atomicAdd(&v.ctrl->new_exp_pt, s);
@@ -1641,7 +1664,7 @@ constexpr size_t VP_SMEM = (2 * VP_HT + VAX_SHARD_DRAWS / 32) * sizeof(uint32_t)
 constexpr size_t HT_BYTES = 3 * HT_SIZE * sizeof(uint32_t);
 constexpr int PT_THREADS = 128;  // 4 routes per block: small blocks start (and, on idle hours, retire) quickly
 
-__global__ void __launch_bounds__(PT_THREADS) k_pt(const DevView v) {
+__global__ void __launch_bounds__(PT_THREADS, 5) k_pt(const DevView v) {
     KTrace kt; kt.start(v);
     pdl_prologue();
     __shared__ PtWarpSmem ws[PT_THREADS / 32];
@@ -1993,14 +2016,14 @@ void launch_expose(const DevView& v, cudaStream_t s) {
 }
 void launch_pt(const DevView& v, cudaStream_t s) {
     if (v.n_routes == 0) return;
-    // one warp per route, grid-stride over one resident wave: the warps pipeline their loads over the routes they walk
+    // one warp per span of routes, grid-stride over one resident wave: the warps pipeline their loads over the spans they walk
     static int per_sm = 0;
     if (per_sm == 0) {
         if (const char* env = getenv("ESIM_PT_BLOCKS")) per_sm = atoi(env);
         if (per_sm <= 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt, PT_THREADS, 0) != cudaSuccess) per_sm = 0;
         if (per_sm <= 0) per_sm = 4;
     }
-    launch_step_kernel(k_pt, blocks_for(v.n_routes, PT_THREADS / 32, (uint32_t)sm_count() * (uint32_t)per_sm), PT_THREADS, 0, s, v);
+    launch_step_kernel(k_pt, blocks_for(v.n_spans, PT_THREADS / 32, (uint32_t)sm_count() * (uint32_t)per_sm), PT_THREADS, 0, s, v);
 }
 void launch_tail(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_tail, 1, TAIL_THREADS, HT_BYTES, s, v);

@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t ld_pair_wait(const uint32_t* p, uint32_t tag
     while (true) {
         asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(value), "=r"(seen) : "l"(p) : "memory");
         if (seen == tag) return value;
-        if (++spins > (1u << 22)) { *error_word = (uint32_t)(-ESIM_ERR_COMM); return 0u; }   // a lost peer raises an error
+        if (++spins > (1u << 25)) { *error_word = (uint32_t)(-ESIM_ERR_COMM); return 0u; }   // a lost peer raises an error (after ~1 s: a peer whose host was descheduled for a moment is not lost)
         __nanosleep(32);
     }
 }

@@ -52,6 +52,7 @@ def host_lib() -> C.CDLL:
     lib.esim_population_file_area_code.restype = C.c_char_p
     lib.esim_population_file_destroy.argtypes = [vp]
     lib.esim_population_file_destroy.restype = None
+    lib.esim_pt_pack_spans.argtypes = [_abi.u32p, C.c_uint32, C.c_uint32, _abi.u32p, C.POINTER(C.c_uint16)]
     return lib
 
 

@@ -49,10 +49,10 @@ def host_compiler() -> str:
 
 def build_host(force: bool = False) -> Path:
     srcs = [CSRC / s for s in HOST_SOURCES]
-    deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h"]
+    deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h"] + sorted(CSRC.glob("*.h"))
     if not force and _newer(HOST_LIB, deps):
         return HOST_LIB
-    _run([host_compiler(), "-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-Wall", "-I", str(INCLUDE), "-o", str(HOST_LIB)]
+    _run([host_compiler(), "-O3", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-Wall", "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(HOST_LIB)]
          + [str(s) for s in srcs])
     return HOST_LIB
 

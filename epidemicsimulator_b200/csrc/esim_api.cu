@@ -21,6 +21,7 @@
 #include "esim.h"
 #include "esim_import.h"
 #include "esim_internal.h"
+#include "pt_spans.h"
 #include "esim_rng.h"
 
 using namespace esim;
@@ -596,23 +597,10 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
             std::vector<uint32_t> h_off((size_t)n_routes + 1);
             CK(cudaMemcpyAsync(h_off.data(), s->route_off.p, h_off.size() * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            std::vector<uint4> spans;
-            std::vector<uint16_t> seg(n_riders, 0);
-            spans.reserve(n_routes / 2 + 1);
-            uint32_t r = 0;
-            while (r < n_routes) {
-                const uint32_t first = r, span_off = h_off[r];
-                uint32_t total = h_off[r + 1] - h_off[r];
-                ++r;
-                if (total <= ESIM_PT_SPAN_RIDERS)
-                    while (r < n_routes && total + (h_off[r + 1] - h_off[r]) <= ESIM_PT_SPAN_RIDERS) { total += h_off[r + 1] - h_off[r]; ++r; }
-                spans.push_back(make_uint4(span_off, total, first, r - first));
-                if (total <= ESIM_PT_SPAN_RIDERS)
-                    for (uint32_t q = first; q < r; ++q) {
-                        const uint32_t start = h_off[q] - span_off, len = h_off[q + 1] - h_off[q];
-                        for (uint32_t j = h_off[q]; j < h_off[q + 1]; ++j) seg[j] = (uint16_t)(start | (len << 8));
-                    }
-            }
+            static_assert(sizeof(PtSpanRecord) == sizeof(uint4), "span records are uploaded as uint4");
+            std::vector<PtSpanRecord> spans;
+            std::vector<uint16_t> seg;
+            pack_pt_spans(h_off.data(), n_routes, ESIM_PT_SPAN_RIDERS, spans, seg);   // csrc/pt_spans.h
             n_spans = (uint32_t)spans.size();
             s->pt_span.alloc(n_spans); s->pt_seg.alloc(std::max<uint32_t>(n_riders, 1));
             CK(cudaMemcpyAsync(s->pt_span.p, spans.data(), spans.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "esim_popgen.h"
+#include "pt_spans.h"
 
 namespace {
 
@@ -208,5 +209,19 @@ const char* esim_population_file_area_code(const EsimPopulationFile* f, uint32_t
     return f->code_strings[area].c_str();
 }
 void esim_population_file_destroy(EsimPopulationFile* f) { delete f; }
+
+// the import's span packing (csrc/pt_spans.h), exported so that the CPU test-suite covers it
+int esim_pt_pack_spans(const uint32_t* route_off, uint32_t n_routes, uint32_t max_riders, uint32_t* span_out, uint16_t* seg_out) {
+    if (!route_off || !span_out || !seg_out || max_riders == 0 || max_riders > 128) return ESIM_ERR_INVALID_ARGUMENT;
+    std::vector<esim::PtSpanRecord> spans;
+    std::vector<uint16_t> seg;
+    esim::pack_pt_spans(route_off, n_routes, max_riders, spans, seg);
+    for (size_t k = 0; k < spans.size(); ++k) {
+        span_out[4 * k] = spans[k].first_rider; span_out[4 * k + 1] = spans[k].riders;
+        span_out[4 * k + 2] = spans[k].first_route; span_out[4 * k + 3] = spans[k].routes;
+    }
+    if (!seg.empty()) memcpy(seg_out, seg.data(), seg.size() * sizeof(uint16_t));
+    return (int)spans.size();
+}
 
 }  // extern "C"

@@ -1,0 +1,38 @@
+// Public-transport spans (host logic shared by libesim_b200.so's import and libesim_host.so, where the CPU tests reach it).
+//
+// The riders of a route (home area, work area) are contiguous in the rider list and routes are consecutive
+// (route_off[r] .. route_off[r + 1]).  The public-transport kernel gives one warp to a SPAN: consecutive whole routes packed
+// greedily while their riders fit into max_riders; a route with more riders than that is a span of its own (the kernel's
+// global-memory path).  Per rider the kernel needs the position of its route's first rider inside the span and the route's
+// length: seg = start | len << 8 (both <= 128 for packed spans; 0 for the riders of an over-long route).
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace esim {
+
+struct PtSpanRecord {
+    uint32_t first_rider, riders, first_route, routes;   // the layout of DevView::pt_span (uint4)
+};
+
+inline void pack_pt_spans(const uint32_t* route_off, uint32_t n_routes, uint32_t max_riders, std::vector<PtSpanRecord>& spans,
+                          std::vector<uint16_t>& seg) {
+    spans.clear();
+    seg.assign(n_routes ? route_off[n_routes] : 0u, 0);
+    uint32_t r = 0;
+    while (r < n_routes) {
+        const uint32_t first = r, span_off = route_off[r];
+        uint32_t total = route_off[r + 1] - route_off[r];
+        ++r;
+        if (total <= max_riders)
+            while (r < n_routes && total + (route_off[r + 1] - route_off[r]) <= max_riders) { total += route_off[r + 1] - route_off[r]; ++r; }
+        spans.push_back(PtSpanRecord{span_off, total, first, r - first});
+        if (total <= max_riders)
+            for (uint32_t q = first; q < r; ++q) {
+                const uint32_t start = route_off[q] - span_off, len = route_off[q + 1] - route_off[q];
+                for (uint32_t j = route_off[q]; j < route_off[q + 1]; ++j) seg[j] = (uint16_t)(start | (len << 8));
+            }
+    }
+}
+
+}  // namespace esim

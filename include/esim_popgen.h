@@ -85,6 +85,16 @@ const uint32_t* esim_population_file_area_offsets(const EsimPopulationFile* f); 
 const char*     esim_population_file_area_code(const EsimPopulationFile* f, uint32_t area); /* NULL if not stored */
 void esim_population_file_destroy(EsimPopulationFile* f);
 
+/*
+ * Host logic of esim_import_population that has no reference counterpart, exported for the CPU tests: the riders of the
+ * public-transport routes (route r = riders route_off[r] .. route_off[r + 1], simulator.rs:360-401) packed into spans of
+ * consecutive whole routes with at most max_riders (<= 128) riders, one warp of the public-transport kernel per span.
+ * span_out: 4 words per span (first rider, riders, first route, routes), room for n_routes spans; seg_out: one entry per
+ * rider (start of its route inside the span | riders of the route << 8; 0 for a route longer than max_riders, which is a
+ * span of its own).  Returns the number of spans.
+ */
+int esim_pt_pack_spans(const uint32_t* route_off, uint32_t n_routes, uint32_t max_riders, uint32_t* span_out, uint16_t* seg_out);
+
 #ifdef __cplusplus
 }
 #endif

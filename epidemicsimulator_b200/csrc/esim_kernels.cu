@@ -646,7 +646,7 @@ __device__ __forceinline__ void k_step_body2(const DevView& v) {
                                      : (at_work ? step_stream<false, true, P2P, true>(v, c, s_cnt, pushed) : step_stream<false, false, P2P, true>(v, c, s_cnt, pushed));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
-    if (P2P && pushed) v.ctrl->pushed_any = 1u;   // the tail fences system-wide before it sends its vector
+    if (P2P && pushed) v.ctrl->pushed_any = 1u;   // only consulted by the tail with ESIM_TAIL_FENCE=1 (signal_block_done fences)
     {   // the count buffer of step t + 2: nothing in this launch reads it
         uint4* __restrict__ cnt_zero = reinterpret_cast<uint4*>(v.cnt[cnt_slot(1u, kt_t + 2u)]);
         const uint32_t T = gridDim.x * blockDim.x;
@@ -826,7 +826,7 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
                                      : (at_work ? step_stream<false, true, P2P>(v, c, s_cnt, pushed) : step_stream<false, false, P2P>(v, c, s_cnt, pushed));
     const uint32_t s = warp_sum(n_exposed);
     if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
-    if (P2P && pushed) v.ctrl->pushed_any = 1u;   // the tail fences system-wide before it sends its vector
+    if (P2P && pushed) v.ctrl->pushed_any = 1u;   // only consulted by the tail with ESIM_TAIL_FENCE=1 (signal_block_done fences)
     signal_block_done(v, P2P && pushed);
     kt.end(v, kt_t, 0);
 }

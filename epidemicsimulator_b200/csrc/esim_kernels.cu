@@ -1664,7 +1664,7 @@ constexpr size_t VP_SMEM = (2 * VP_HT + VAX_SHARD_DRAWS / 32) * sizeof(uint32_t)
 constexpr size_t HT_BYTES = 3 * HT_SIZE * sizeof(uint32_t);
 constexpr int PT_THREADS = 128;  // 4 routes per block: small blocks start (and, on idle hours, retire) quickly
 
-__global__ void __launch_bounds__(PT_THREADS, 5) k_pt(const DevView v) {
+__global__ void __launch_bounds__(PT_THREADS, 5) k_pt(const __grid_constant__ DevView v) {
     KTrace kt; kt.start(v);
     pdl_prologue();
     __shared__ PtWarpSmem ws[PT_THREADS / 32];

@@ -26,7 +26,7 @@ namespace {
 
 constexpr char MAGIC[8] = {'E', 'S', 'I', 'M', 'P', 'O', 'P', 1};
 constexpr uint32_t VERSION = 1;
-enum : uint32_t { HAS_AGE = 1, HAS_OCCUPATION = 2, HAS_STATUS = 4, HAS_TIMER = 8, HAS_GLOBAL_ID = 16, HAS_AREA_OFFSETS = 32, HAS_AREA_CODES = 64 };
+constexpr uint32_t HAS_AGE = 1, HAS_OCCUPATION = 2, HAS_STATUS = 4, HAS_TIMER = 8, HAS_GLOBAL_ID = 16, HAS_AREA_OFFSETS = 32, HAS_AREA_CODES = 64;
 
 struct Header {
     char magic[8];
@@ -84,8 +84,8 @@ int esim_population_save(const EsimPopulationSoA* p, const uint32_t* area_first_
     h.version = VERSION; h.header_bytes = sizeof(Header);
     h.n_citizens = N; h.n_areas = A; h.n_buildings = B; h.n_rooms = R;
     h.n_global_citizens = p->n_global_citizens; h.n_shared_bldgs = p->n_shared_bldgs; h.n_shared_rooms = p->n_shared_rooms; h.n_shards = p->n_shards;
-    h.present = (p->age ? HAS_AGE : 0) | (p->occupation ? HAS_OCCUPATION : 0) | (p->status ? HAS_STATUS : 0) | (p->timer ? HAS_TIMER : 0) |
-                (p->global_id ? HAS_GLOBAL_ID : 0) | (area_first_citizen ? HAS_AREA_OFFSETS : 0) | (area_codes ? HAS_AREA_CODES : 0);
+    h.present = (p->age ? HAS_AGE : 0u) | (p->occupation ? HAS_OCCUPATION : 0u) | (p->status ? HAS_STATUS : 0u) | (p->timer ? HAS_TIMER : 0u) |
+                (p->global_id ? HAS_GLOBAL_ID : 0u) | (area_first_citizen ? HAS_AREA_OFFSETS : 0u) | (area_codes ? HAS_AREA_CODES : 0u);
     std::vector<uint32_t> code_off;
     std::string code_blob;
     if (area_codes) {

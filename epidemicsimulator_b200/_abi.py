@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK = 0
 ERR_DEFAULT = -1
@@ -31,7 +31,7 @@ CFG_NO_GRAPH = 0x2
 CFG_FLUSH_L2 = 0x4
 CFG_UNFUSED = 0x10
 CFG_TIME_KERNELS = 0x20
-CFG_PERSISTENT = 0x8
+CFG_CORRECTED = 0x40
 EXCH_COUNTS = 0
 EXCH_TAIL = 1
 

@@ -58,12 +58,14 @@ def host_lib() -> C.CDLL:
 
 @lru_cache(maxsize=None)
 def cuda_lib() -> C.CDLL:
+    host_lib()   # libesim_b200.so uses its sharding (esim_shard_create) for multi-device handles
     lib = _load(CUDA_LIB)
     vp = C.c_void_p
     lib.esim_abi_version.restype = C.c_int
     lib.esim_build_info.restype = C.c_char_p
     lib.esim_default_config.argtypes = [C.POINTER(_abi.EsimConfig)]
     lib.esim_create.argtypes = [C.POINTER(_abi.EsimConfig), C.POINTER(vp)]
+    lib.esim_create_multi.argtypes = [C.POINTER(_abi.EsimConfig), C.c_uint32, C.POINTER(C.c_int32), C.POINTER(vp)]
     lib.esim_import_population.argtypes = [vp, C.POINTER(_abi.EsimPopulationSoA)]
     lib.esim_destroy.argtypes = [vp]
     lib.esim_destroy.restype = None

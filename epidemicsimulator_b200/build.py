@@ -66,7 +66,8 @@ def nvcc() -> str:
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in CUDA_SOURCES]
-    deps = srcs + [INCLUDE / "esim.h"] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
+    build_host()   # libesim_b200.so links against the host library (sharding for multi-device handles)
+    deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h", HOST_LIB] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -74,7 +75,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
            "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(CUDA_LIB)]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in srcs] + ["-lcudart", "-ldl"]
+    cmd += [str(s) for s in srcs] + ["-lcudart", "-ldl", "-L", str(PKG), "-lesim_host", "-Xlinker", "-rpath=$ORIGIN"]
     out = _run(cmd)
     if verbose:
         print(out)

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "esim.h"
+#include "esim_popgen.h"
 #include "esim_import.h"
 #include "esim_internal.h"
 #include "pt_spans.h"
@@ -141,13 +142,14 @@ struct EsimSim {
     DevBuf<uint32_t> peer_mail;         // peer-to-peer exchange (sharded runs): this shard's mailbox in HBM
     DevBuf<PeerView> peer_view;         // pointer tables of the mapped peers
     std::vector<void*> peer_mappings;   // cudaIpcOpenMemHandle results
-    DevBuf<unsigned int> barrier;       // grid barrier of the persistent kernel
-    DevBuf<unsigned long long> pk_prof; // ESIM_TRACE: cycles per phase
     DevBuf<unsigned long long> ktrace_min, ktrace_max;   // ESIM_KTRACE: device-side timeline of the step kernels
-    bool use_persistent = false;
     bool fused = false;                 // one-pass step (k_step + k_tail_fused): single shard and peer-to-peer shards
     size_t cnt_stride = 0;              // words between the three count buffers inside cnt_all
     uint32_t world = 1, rank = 0, n_shared_bldgs = 0, n_shared_rooms = 0;
+    uint32_t share = 1;                 // handles of one multi-device handle that run on this device (they wait for each other inside kernels)
+    bool no_pdl = false;                // launch without programmatic dependent launch (ESIM_NO_PDL=1; forced when handles share a device)
+    unsigned long long peer_timeout_ns = 30ull * 1000000000ull;   // bound of every in-kernel wait for a peer (ESIM_PEER_TIMEOUT_MS)
+    uint32_t sync_seq = 0;              // timed steps of peer-to-peer shards: see k_peer_sync
     void* comm = nullptr;               // ncclComm_t
     DevBuf<Ctrl> ctrl;
     DevBuf<EsimStepStats> stats;
@@ -172,6 +174,12 @@ struct EsimSim {
     std::vector<float> step_phase_ms;   // 3 per recorded step
     size_t device_bytes = 0;
     std::string err;
+    // ---- single-process multi-device handle (esim_create_multi): this object owns one sub-handle per shard and nothing else
+    std::vector<EsimSim*> kids;
+    std::vector<EsimShard*> kid_shards;     // host-side shard descriptions (shard-local -> whole-population cell ids)
+    std::vector<int> kid_devices;
+    std::vector<uint32_t> kid_lo;           // first global citizen of each shard
+    uint32_t n_total = 0, nb_total = 0, nr_total = 0;
 
     void destroy_graphs() {
         for (int h = 0; h < 24; ++h) {
@@ -190,11 +198,16 @@ struct EsimSim {
         }
     }
     ~EsimSim() {
+        if (!kid_devices.empty()) {   // multi-device handle: no CUDA resources of its own
+            for (EsimSim* k : kids) delete k;
+            for (EsimShard* sh : kid_shards) esim_shard_destroy(sh);
+            return;
+        }
         if (device >= 0) cudaSetDevice(device);
         destroy_graphs();
         if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
         for (void* m : peer_mappings) cudaIpcCloseMemHandle(m);
-        exch.release(); vax_cand.release(); barrier.release(); pk_prof.release(); peer_mail.release(); peer_view.release();
+        exch.release(); vax_cand.release(); peer_mail.release(); peer_view.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         cstate.release(); home_cell.release(); work_cell.release(); gid.release(); room_parent.release(); cnt_all.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
@@ -256,17 +269,19 @@ unsigned long long threshold_for(double prob) {
     return lo;
 }
 
-void build_thresholds(const EsimConfig& c, unsigned long long out[512]) {
+// thr[2][n_mask + 1]: parity mode n_mask = 255 (`exposure_total as u8`, citizen.rs:239); corrected mode: n saturates at n_mask
+void build_thresholds(const EsimConfig& c, uint32_t n_mask, std::vector<unsigned long long>& out) {
     // DiseaseModel::get_exposure_chance (disease.rs:131-154) for the two cases that can occur for a non-vaccinated
-    // citizen: effective MaskStatus::None / PublicTransport (-> chance) and Everywhere (-> chance - chance*eff).
+    // citizen: no effective mask (-> chance) and an effective mask (-> chance - chance*eff).
     double chance[2];
     chance[0] = c.exposure_chance - 0.0 - 0.0;
     chance[1] = c.exposure_chance - c.exposure_chance * c.mask_effectiveness - 0.0;
+    out.resize((size_t)2 * (n_mask + 1u));
     for (int m = 0; m < 2; ++m) {
         if (std::signbit(chance[m])) chance[m] = 0.0;
-        for (int n = 0; n < 256; ++n) {
+        for (uint32_t n = 0; n <= n_mask; ++n) {
             const double prob = 1.0 - std::pow(1.0 - chance[m], (double)n);  // binomial (citizen.rs:47-49)
-            out[m * 256 + n] = threshold_for(prob);
+            out[(size_t)m * (n_mask + 1u) + n] = threshold_for(prob);
         }
     }
 }
@@ -290,6 +305,18 @@ void flush_l2(EsimSim* s) {
     if (!s->l2_scratch.p) return;
     CK(cudaMemsetAsync(s->l2_scratch.p, (int)(s->steps_done & 0xFF), s->l2_scratch.bytes(), s->stream));
     launch_flush_sweep(s->l2_scratch.p, s->l2_scratch.bytes(), s->exch.p + 7, s->stream);   // exch[7] is a spare word
+}
+
+// start of a timed step: cold L2 if configured, then - peer-to-peer shards - leave the flush together with the other shards, so
+// that the events around the step do not also measure the skew of the independent flushes (k_peer_sync)
+void begin_timed_step(EsimSim* s, cudaEvent_t ev) {
+    flush_l2(s);
+    if (s->v.p2p && s->world > 1) {
+        DevView v = s->v;
+        v.sync_seq = ++s->sync_seq;
+        launch_peer_sync(v, s->stream);
+    }
+    CK(cudaEventRecord(ev, s->stream));
 }
 
 // one time step whose number has the given parity; `with_pt` / `next_has_pt`: see the specialised day graphs below
@@ -379,12 +406,24 @@ void require_ready(EsimSim* s) {
 
 }  // namespace
 
+static int multi_import(EsimSim* s, const EsimPopulationSoA* p);
+static int multi_step(EsimSim* s, EsimStepStats* out, bool timed);
+static int multi_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done);
+static int multi_dump(EsimSim* s, const char* directory, const char* const* area_codes);
+static int multi_run_timed(EsimSim* s, uint32_t max_steps, uint32_t* steps_done);
+static int multi_read_state(EsimSim* s, EsimStateView* view);
+static int multi_read_building_counts(EsimSim* s, uint32_t* bldg, uint32_t* room);
+static int multi_read_buses(EsimSim* s, uint32_t* bus_index, uint32_t* bus_infected);
+static int multi_inject_rng(EsimSim* s, uint64_t seed);
+
 extern "C" {
 
 int esim_abi_version(void) { return ESIM_ABI_VERSION; }
 
 const char* esim_build_info(void) {
-    return "libesim_b200 abi " "1" " sm_100a cuda " __DATE__ " " __TIME__;
+#define ESIM_STR2(x) #x
+#define ESIM_STR(x) ESIM_STR2(x)
+    return "libesim_b200 abi " ESIM_STR(ESIM_ABI_VERSION) " sm_100a cuda " __DATE__ " " __TIME__;
 }
 
 int esim_default_config(EsimConfig* c) {
@@ -447,7 +486,8 @@ int esim_create(const EsimConfig* cfg, EsimSim** out) {
         s->h_stat = reinterpret_cast<EsimStepStats*>(s->mailbox + 256);
         for (auto& e : s->ev) CK(cudaEventCreate(&e));
         CK((cudaError_t)configure_kernels());
-        if (const char* e = getenv("ESIM_NO_PDL")) set_pdl(e[0] != '1');
+        if (const char* e = getenv("ESIM_NO_PDL")) s->no_pdl = e[0] == '1';
+        if (const char* e = getenv("ESIM_PEER_TIMEOUT_MS")) { const long ms = atol(e); if (ms > 0) s->peer_timeout_ns = (unsigned long long)ms * 1000000ull; }
         return ESIM_OK;
     });
     if (rc < 0) { g_create_error = s->err; delete s; return rc; }
@@ -498,6 +538,7 @@ void esim_destroy(EsimSim* s) { if (s) print_ktrace(s); delete s; }
 
 int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
     if (!s) return ESIM_ERR_INVALID_ARGUMENT;
+    if (!s->kid_devices.empty()) return multi_import(s, p);
     return guarded(s, [&]() -> int {
         if (!p || !p->home_bldg || !p->work_bldg || !p->room || !p->bldg_area || !p->bldg_type || (p->n_rooms && !p->room_bldg))
             throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population arrays missing"};
@@ -609,33 +650,32 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         }
         tr.mark("public-transport spans", st);
 
-        unsigned long long thr[512];
-        build_thresholds(s->cfg, thr);
+        const bool corrected = (s->cfg.flags & ESIM_CFG_CORRECTED) != 0;
+        const uint32_t n_mask = corrected ? 16383u : 255u;
+        std::vector<unsigned long long> thr;
+        build_thresholds(s->cfg, n_mask, thr);
 
         const bool sharded_pop = p->n_shards > 1;
         // three count buffers in one allocation (one CUDA IPC handle for peers); sharded handles decide at connect time
         // whether they run fused (esim_peer_connect) or not (esim_comm_init, esim_shard_step_*)
         s->cnt_stride = ((size_t)B + R + 4 + 31) & ~(size_t)31;
         s->cnt_all.alloc(3 * s->cnt_stride, sharded_pop);
-        s->fused = p->n_shards <= 1 && !(s->cfg.flags & (ESIM_CFG_UNFUSED | ESIM_CFG_PERSISTENT)) && !getenv("ESIM_UNFUSED");
+        s->fused = p->n_shards <= 1 && !(s->cfg.flags & ESIM_CFG_UNFUSED);
         if (sharded_pop) { s->peer_mail.alloc(MAIL_WORDS, true); CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st)); }
         s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
         s->pt_buscnt.alloc(std::max<uint32_t>(n_riders, 1));
         const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
         if (rec) { s->rec_bus.alloc(N); s->rec_businf.alloc(N); }
-        const uint32_t n_update_blocks = update_blocks(n_pad);
-        const int pk_grid = persistent_grid();
-        s->use_persistent = pk_grid > 0 && p->n_shards <= 1 && (s->cfg.flags & ESIM_CFG_PERSISTENT) && !(s->cfg.flags & ESIM_CFG_NO_GRAPH);
-        s->tally_partial.alloc((size_t)std::max<uint32_t>(std::max(n_update_blocks, step_blocks(n_pad)), (uint32_t)std::max(pk_grid, 1)) * 8);
-        s->barrier.alloc(4);
-        if (getenv("ESIM_TRACE")) { s->pk_prof.alloc(8); CK(cudaMemsetAsync(s->pk_prof.p, 0, s->pk_prof.bytes(), s->stream)); }
+        // per-block partial tallies of k_update / k_step: sized for a whole resident wave (the grids only shrink when handles share a device)
+        s->tally_partial.alloc((size_t)sm_count() * 6u * 8u);
         s->world = p->n_shards > 1 ? p->n_shards : 1;
         s->n_shared_bldgs = p->n_shared_bldgs; s->n_shared_rooms = p->n_shared_rooms;
-        s->exch.alloc(FEXCH_WORDS); s->vax_cand.alloc(ESIM_VAX_SHARD_DRAWS);
+        s->exch.alloc(EXCH_WORDS); s->vax_cand.alloc(ESIM_VAX_SHARD_DRAWS);
         CK(cudaMemsetAsync(s->exch.p, 0, s->exch.bytes(), st));
-        s->thr.alloc(512); s->ctrl.alloc(1); s->stats.alloc(s->cfg.max_time_step);
+        s->thr.alloc(thr.size()); s->ctrl.alloc(1); s->stats.alloc(s->cfg.max_time_step);
         if (s->cfg.flags & ESIM_CFG_FLUSH_L2) s->l2_scratch.alloc((size_t)256 << 20);  // 2x the 126 MB L2
-        CK(cudaMemcpyAsync(s->thr.p, thr, sizeof(thr), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s->thr.p, thr.data(), thr.size() * sizeof(thr[0]), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // `thr` is pageable: the copy is staged, but keep the vector's lifetime obviously safe
         CK(cudaMemsetAsync(s->cnt_all.p, 0, s->cnt_all.bytes(), st));
         CK(cudaMemsetAsync(s->tally_partial.p, 0, s->tally_partial.bytes(), st));
         if (rec) {
@@ -671,7 +711,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.world = s->world; v.exch = s->exch.p; v.vax_cand = s->vax_cand.p;
         v.p2p = 0; v.rank = 0; v.peer = nullptr;
         v.n_shared_b = s->n_shared_bldgs; v.n_shared_r = s->n_shared_rooms;
-        v.tally_partial = s->tally_partial.p; v.n_update_blocks = n_update_blocks;
+        v.tally_partial = s->tally_partial.p;
         v.ctrl = s->ctrl.p; v.stats = s->stats.p; v.max_steps = s->cfg.max_time_step;
         if (getenv("ESIM_KTRACE")) {
             s->ktrace_min.alloc((size_t)KTRACE_STEPS * KTRACE_KERNELS * 2); s->ktrace_max.alloc((size_t)KTRACE_STEPS * KTRACE_KERNELS);
@@ -685,6 +725,10 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         v.mp.th_mask_pt = s->cfg.mask_pt_threshold; v.mp.th_mask_everywhere = s->cfg.mask_everywhere_threshold;
         v.mp.seed_lo = (uint32_t)s->cfg.seed; v.mp.seed_hi = (uint32_t)(s->cfg.seed >> 32);
         v.mp.n_global_citizens = n_global; v.mp.shard_lo = shard_lo;
+        v.mp.corrected = corrected ? 1u : 0u; v.mp.n_mask = n_mask;
+        v.share = s->share; v.no_pdl = s->no_pdl ? 1u : 0u; v.sync_seq = 0;
+        v.peer_timeout_ns = s->peer_timeout_ns;
+        v.n_update_blocks = update_blocks(v);
 
         s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->gid.bytes() +
                           s->room_parent.bytes() + s->cnt_all.bytes() + s->route_off.bytes() + s->riders.bytes() * 4 +
@@ -702,75 +746,89 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
     });
 }
 
+// A step is queued (step_enqueue) and then waited for (step_collect), so that a multi-device handle can queue the step on every
+// device before it waits for any of them (the shards wait for each other inside their kernels).
+static void step_enqueue(EsimSim* s, bool timed) {
+    require_ready(s);
+    if (s->steps_done >= s->cfg.max_time_step && !s->finished)
+        throw ApiError{ESIM_ERR_SIMULATION, "max_time_step reached"};
+    const uint32_t before = s->steps_done;
+    const uint32_t parity = (before + 1u) & 1u;
+    if (s->world > 1 && !s->comm && !s->v.p2p)
+        throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
+    const bool time_kernels = timed && (s->cfg.flags & ESIM_CFG_TIME_KERNELS);
+    if (timed && !time_kernels) {
+        // whole-step timing: the kernels follow each other exactly as in the captured graphs (programmatic dependent
+        // launches, no public-transport kernel in hours without riders - the host has just read the control block)
+        begin_timed_step(s, s->ev[0]);
+        enqueue_step(s, parity, s->h_ctrl->pt_mode != ESIM_PT_NONE, true);
+        CK(cudaEventRecord(s->ev[4], s->stream));
+    } else if (timed) {
+        DevView v = s->v;
+        v.has_pt = (s->h_ctrl->pt_mode != ESIM_PT_NONE && v.n_routes) ? 1u : 0u;
+        begin_timed_step(s, s->ev[0]);
+        if (!s->fused) launch_update(v, s->stream);
+        if (s->world > 1 && !v.p2p && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
+        CK(cudaEventRecord(s->ev[1], s->stream));
+        if (s->fused) launch_step_fused(v, s->stream); else launch_expose(v, s->stream);
+        CK(cudaEventRecord(s->ev[2], s->stream));
+        // the host has just read the control block: it knows whether anybody rides in this step
+        if (s->h_ctrl->pt_mode != ESIM_PT_NONE) launch_pt(v, s->stream);
+        CK(cudaEventRecord(s->ev[3], s->stream));
+        if (s->world > 1 && !v.p2p) { launch_vax_prepare(v, s->stream); allreduce_tail(s); }
+        if (s->fused) launch_tail_fused(v, s->stream); else launch_tail(v, s->stream);
+        CK(cudaEventRecord(s->ev[4], s->stream));
+    } else if (s->exec1[parity]) {
+        CK(cudaGraphLaunch(s->exec1[parity], s->stream));
+    } else {
+        enqueue_step(s, parity);
+    }
+    if (!s->finished && before < s->cfg.max_time_step)
+        CK(cudaMemcpyAsync(s->h_stat, s->stats.p + before, sizeof(EsimStepStats), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+}
+
+static int step_collect(EsimSim* s, EsimStepStats* out, bool timed) {
+    CK(cudaSetDevice(s->device));
+    const uint32_t before = s->steps_done;
+    const bool time_kernels = timed && (s->cfg.flags & ESIM_CFG_TIME_KERNELS);
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaGetLastError());
+    const int rc = after_steps(s);
+    if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
+    if (timed && !time_kernels && s->steps_done > before) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[4]));
+        s->timings.total += ms * 1e-3;
+        s->timings.steps += 1;
+        s->step_total_ms[before] = ms;
+    } else if (timed && s->steps_done > before) {
+        float ms[4];
+        for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ms[k], s->ev[k], s->ev[k + 1]));
+        EsimTimings& T = s->timings;
+        T.k_update += ms[0] * 1e-3; T.k_expose += ms[1] * 1e-3; T.k_pt += ms[2] * 1e-3; T.k_tail += ms[3] * 1e-3;
+        T.generate_exposures += ms[0] * 1e-3;
+        T.apply_exposures += (ms[1] + ms[2]) * 1e-3;
+        T.apply_interventions += ms[3] * 1e-3;
+        T.total += (ms[0] + ms[1] + ms[2] + ms[3]) * 1e-3;
+        T.steps += 1;
+        s->step_total_ms[before] = ms[0] + ms[1] + ms[2] + ms[3];
+        s->step_phase_ms[(size_t)before * 3 + 0] = ms[0];
+        s->step_phase_ms[(size_t)before * 3 + 1] = ms[1] + ms[2];
+        s->step_phase_ms[(size_t)before * 3 + 2] = ms[3];
+    }
+    if (out) {
+        if (s->steps_done > before) *out = *s->h_stat;
+        else std::memset(out, 0, sizeof(*out));
+    }
+    return s->finished ? 0 : 1;
+}
+
 static int step_common(EsimSim* s, EsimStepStats* out, bool timed) {
+    if (s && !s->kids.empty()) return multi_step(s, out, timed);
     return guarded(s, [&]() -> int {
-        require_ready(s);
-        if (s->steps_done >= s->cfg.max_time_step && !s->finished)
-            throw ApiError{ESIM_ERR_SIMULATION, "max_time_step reached"};
-        const uint32_t before = s->steps_done;
-        const uint32_t parity = (before + 1u) & 1u;
-        if (s->world > 1 && !s->comm && !s->v.p2p)
-            throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
-        const bool time_kernels = timed && (s->cfg.flags & ESIM_CFG_TIME_KERNELS);
-        if (timed && !time_kernels) {
-            // whole-step timing: the kernels follow each other exactly as in the captured graphs (programmatic dependent
-            // launches, no public-transport kernel in hours without riders - the host has just read the control block)
-            flush_l2(s);
-            CK(cudaEventRecord(s->ev[0], s->stream));
-            enqueue_step(s, parity, s->h_ctrl->pt_mode != ESIM_PT_NONE, true);
-            CK(cudaEventRecord(s->ev[4], s->stream));
-        } else if (timed) {
-            DevView v = s->v;
-            v.has_pt = (s->h_ctrl->pt_mode != ESIM_PT_NONE && v.n_routes) ? 1u : 0u;
-            flush_l2(s);
-            CK(cudaEventRecord(s->ev[0], s->stream));
-            if (!s->fused) launch_update(v, s->stream);
-            if (s->world > 1 && !v.p2p && (s->n_shared_bldgs || s->n_shared_rooms)) allreduce_counts(s, parity);
-            CK(cudaEventRecord(s->ev[1], s->stream));
-            if (s->fused) launch_step_fused(v, s->stream); else launch_expose(v, s->stream);
-            CK(cudaEventRecord(s->ev[2], s->stream));
-            // the host has just read the control block: it knows whether anybody rides in this step
-            if (s->h_ctrl->pt_mode != ESIM_PT_NONE) launch_pt(v, s->stream);
-            CK(cudaEventRecord(s->ev[3], s->stream));
-            if (s->world > 1 && !v.p2p) { launch_vax_prepare(v, s->stream); allreduce_tail(s); }
-            if (s->fused) launch_tail_fused(v, s->stream); else launch_tail(v, s->stream);
-            CK(cudaEventRecord(s->ev[4], s->stream));
-        } else if (s->exec1[parity]) {
-            CK(cudaGraphLaunch(s->exec1[parity], s->stream));
-        } else {
-            enqueue_step(s, parity);
-        }
-        if (!s->finished && before < s->cfg.max_time_step)
-            CK(cudaMemcpyAsync(s->h_stat, s->stats.p + before, sizeof(EsimStepStats), cudaMemcpyDeviceToHost, s->stream));
-        fetch_ctrl(s);
-        const int rc = after_steps(s);
-        if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
-        if (timed && !time_kernels && s->steps_done > before) {
-            float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, s->ev[0], s->ev[4]));
-            s->timings.total += ms * 1e-3;
-            s->timings.steps += 1;
-            s->step_total_ms[before] = ms;
-        } else if (timed && s->steps_done > before) {
-            float ms[4];
-            for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ms[k], s->ev[k], s->ev[k + 1]));
-            EsimTimings& T = s->timings;
-            T.k_update += ms[0] * 1e-3; T.k_expose += ms[1] * 1e-3; T.k_pt += ms[2] * 1e-3; T.k_tail += ms[3] * 1e-3;
-            T.generate_exposures += ms[0] * 1e-3;
-            T.apply_exposures += (ms[1] + ms[2]) * 1e-3;
-            T.apply_interventions += ms[3] * 1e-3;
-            T.total += (ms[0] + ms[1] + ms[2] + ms[3]) * 1e-3;
-            T.steps += 1;
-            s->step_total_ms[before] = ms[0] + ms[1] + ms[2] + ms[3];
-            s->step_phase_ms[(size_t)before * 3 + 0] = ms[0];
-            s->step_phase_ms[(size_t)before * 3 + 1] = ms[1] + ms[2];
-            s->step_phase_ms[(size_t)before * 3 + 2] = ms[3];
-        }
-        if (out) {
-            if (s->steps_done > before) *out = *s->h_stat;
-            else std::memset(out, 0, sizeof(*out));
-        }
-        return s->finished ? 0 : 1;
+        step_enqueue(s, timed);
+        return step_collect(s, out, timed);
     });
 }
 
@@ -785,6 +843,7 @@ int esim_step_timed(EsimSim* s, EsimStepStats* out) { return step_common(s, out,
 // always has the next flush + step queued and the shards are paced by the devices alone.
 int esim_run_timed(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
     if (steps_done) *steps_done = 0;
+    if (s && !s->kids.empty()) return multi_run_timed(s, max_steps, steps_done);
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (s->world > 1 && !s->comm && !s->v.p2p)
@@ -817,8 +876,7 @@ int esim_run_timed(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
         try {
             auto enqueue = [&](uint32_t k, uint32_t pt_mode) {
                 Slot& sl = slot[k & 1u];
-                flush_l2(s);
-                CK(cudaEventRecord(sl.begin, s->stream));
+                begin_timed_step(s, sl.begin);
                 enqueue_step(s, (start + k + 1u) & 1u, pt_mode != ESIM_PT_NONE, true);
                 CK(cudaEventRecord(sl.end, s->stream));
                 CK(cudaMemcpyAsync(sl.ctrl, s->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
@@ -855,67 +913,61 @@ int esim_run_timed(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
     });
 }
 
+// esim_run queues a chunk of simulated days (run_enqueue) and then looks at the control block (run_collect); a multi-device
+// handle queues the chunk on every device before it waits for any of them.
+constexpr uint32_t CHUNK_DAYS = 8;   // the loop is device-resident: the host only looks at the control block every few simulated days
+static uint32_t run_enqueue(EsimSim* s, uint32_t budget) {
+    require_ready(s);
+    if (s->world > 1 && !s->comm && !s->v.p2p)
+        throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
+    uint32_t queued = 0;
+    const uint32_t parity = (s->steps_done + 1u) & 1u;   // GRAPH_DAY is even: the parity is the same for every day
+    if (s->exec_day[parity]) {
+        // h_ctrl is current here: no lockdown => the schedule of the coming hours is known
+        const bool spec = (s->world == 1 || s->v.p2p) && !s->h_ctrl->lockdown_some && GRAPH_DAY == 24;
+        cudaGraphExec_t day = spec ? spec_day_graph(s, s->steps_done + 1u) : s->exec_day[parity];
+        for (uint32_t d = 0; d < CHUNK_DAYS && budget - queued >= (uint32_t)GRAPH_DAY; ++d) {
+            CK(cudaGraphLaunch(day, s->stream));
+            queued += GRAPH_DAY;
+        }
+    }
+    if (queued == 0) {
+        const uint32_t n = std::min<uint32_t>(budget, GRAPH_DAY);
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t pk = (parity + k) & 1u;
+            if (s->exec1[pk]) CK(cudaGraphLaunch(s->exec1[pk], s->stream)); else enqueue_step(s, pk);
+        }
+        queued = n;
+    }
+    CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+    return queued;
+}
+// returns the number of steps the chunk executed
+static uint32_t run_collect(EsimSim* s) {
+    CK(cudaSetDevice(s->device));
+    const uint32_t before_chunk = s->steps_done;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaGetLastError());
+    const int rc = after_steps(s);
+    if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
+    if (s->h_ctrl->abort_graph) {
+        // the specialised graph stopped early (lockdown froze public transport): clear the flag, go on with the generic one
+        s->h_ctrl->abort_graph = 0;
+        CK(cudaMemsetAsync(&s->ctrl.p->abort_graph, 0, sizeof(uint32_t), s->stream));
+    }
+    return s->steps_done - before_chunk;
+}
+
 int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
     if (steps_done) *steps_done = 0;
+    if (s && !s->kids.empty()) return multi_run(s, max_steps, steps_done);
     return guarded(s, [&]() -> int {
         require_ready(s);
         const uint32_t start = s->steps_done;
         uint32_t budget = std::min<uint32_t>(max_steps, s->cfg.max_time_step - std::min(s->cfg.max_time_step, start));
-        // the loop is device-resident: the host only looks at the control block every few simulated days
-        constexpr uint32_t CHUNK_DAYS = 8;
-        if (s->world > 1 && !s->comm && !s->v.p2p)
-            throw ApiError{ESIM_ERR_COMM, "sharded handle: connect the peers (esim_peer_connect / esim_comm_init) or drive the esim_shard_step_* phases"};
         while (budget > 0 && !s->finished) {
-            uint32_t queued = 0;
-            const uint32_t before_chunk = s->steps_done;
-            if (s->use_persistent) {
-                // one cooperative launch runs the whole chunk; grid barriers separate the phases of a step
-                const uint32_t n = std::min<uint32_t>(budget, 4096u);
-                CK(cudaMemsetAsync(s->barrier.p, 0, s->barrier.bytes(), s->stream));
-                CK((cudaError_t)launch_persistent(s->v, n, s->barrier.p, s->pk_prof.p, s->stream));
-                fetch_ctrl(s);
-                if (s->pk_prof.p) {
-                    unsigned long long h[8];
-                    CK(cudaMemcpy(h, s->pk_prof.p, sizeof(h), cudaMemcpyDeviceToHost));
-                    static const char* nm[8] = {"ctrl", "update", "barrier1", "expose", "pt", "barrier2", "tail", "barrier3"};
-                    const double steps_run = std::max<double>(1.0, s->steps_done - before_chunk);
-                    for (int k = 0; k < 8; ++k) fprintf(stderr, "[esim] persistent %-9s %8.0f cycles/step\n", nm[k], h[k] / steps_run);
-                    CK(cudaMemset(s->pk_prof.p, 0, sizeof(h)));
-                }
-                const int prc = after_steps(s);
-                if (prc < 0) throw ApiError{prc, "device-side error flag raised"};
-                const uint32_t done_now = s->steps_done - before_chunk;
-                if (done_now == 0 && !s->finished) throw ApiError{ESIM_ERR_SIMULATION, "no progress"};
-                budget -= std::min(budget, done_now);
-                continue;
-            }
-            const uint32_t parity = (s->steps_done + 1u) & 1u;   // GRAPH_DAY is even: the parity is the same for every day
-            if (s->exec_day[parity]) {
-                // h_ctrl is current here: no lockdown => the schedule of the coming hours is known
-                const bool spec = (s->world == 1 || s->v.p2p) && !s->h_ctrl->lockdown_some && GRAPH_DAY == 24;
-                cudaGraphExec_t day = spec ? spec_day_graph(s, s->steps_done + 1u) : s->exec_day[parity];
-                for (uint32_t d = 0; d < CHUNK_DAYS && budget - queued >= (uint32_t)GRAPH_DAY; ++d) {
-                    CK(cudaGraphLaunch(day, s->stream));
-                    queued += GRAPH_DAY;
-                }
-            }
-            if (queued == 0) {
-                const uint32_t n = std::min<uint32_t>(budget, GRAPH_DAY);
-                for (uint32_t k = 0; k < n; ++k) {
-                    const uint32_t pk = (parity + k) & 1u;
-                    if (s->exec1[pk]) CK(cudaGraphLaunch(s->exec1[pk], s->stream)); else enqueue_step(s, pk);
-                }
-                queued = n;
-            }
-            fetch_ctrl(s);
-            const int rc = after_steps(s);
-            if (rc < 0) throw ApiError{rc, "device-side error flag raised"};
-            const uint32_t executed = s->steps_done - before_chunk;
-            if (s->h_ctrl->abort_graph) {
-                // the specialised graph stopped early (lockdown froze public transport): clear the flag, go on with the generic one
-                s->h_ctrl->abort_graph = 0;
-                CK(cudaMemsetAsync(&s->ctrl.p->abort_graph, 0, sizeof(uint32_t), s->stream));
-            }
+            run_enqueue(s, budget);
+            const uint32_t executed = run_collect(s);
             budget -= std::min(budget, executed);
             if (executed == 0 && !s->finished) throw ApiError{ESIM_ERR_SIMULATION, "no progress"};
         }
@@ -925,9 +977,13 @@ int esim_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
 }
 
 int esim_steps_done(EsimSim* s) { return s ? (int)s->steps_done : ESIM_ERR_INVALID_ARGUMENT; }
-int esim_is_fused(EsimSim* s) { return s && s->imported ? (s->fused ? 1 : 0) : ESIM_ERR_INITIALIZATION; }
+int esim_is_fused(EsimSim* s) {
+    if (s && !s->kids.empty()) return esim_is_fused(s->kids[0]);
+    return s && s->imported ? (s->fused ? 1 : 0) : ESIM_ERR_INITIALIZATION;
+}
 
 int esim_read_stats(EsimSim* s, uint32_t first, uint32_t count, EsimStepStats* out) {
+    if (s && !s->kids.empty()) return esim_read_stats(s->kids[0], first, count, out);
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (!out) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null output"};
@@ -965,6 +1021,7 @@ inline bool host_eligible(uint32_t w, const Ctrl& c) {
 }  // namespace
 
 int esim_read_state(EsimSim* s, EsimStateView* view) {
+    if (s && !s->kids.empty()) return multi_read_state(s, view);
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (!view) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null view"};
@@ -1007,6 +1064,7 @@ int esim_read_state(EsimSim* s, EsimStateView* view) {
 }
 
 int esim_read_building_counts(EsimSim* s, uint32_t* bldg, uint32_t* room) {
+    if (s && !s->kids.empty()) return multi_read_building_counts(s, bldg, room);
     return guarded(s, [&]() -> int {
         require_ready(s);
         const uint32_t* cnt = s->v.cnt[cnt_slot(s->v.fused, s->steps_done)];  // step t accumulates into cnt[t & 1] (fused: t % 3)
@@ -1019,6 +1077,7 @@ int esim_read_building_counts(EsimSim* s, uint32_t* bldg, uint32_t* room) {
 }
 
 int esim_read_buses(EsimSim* s, uint32_t* bus_index, uint32_t* bus_infected) {
+    if (s && !s->kids.empty()) return multi_read_buses(s, bus_index, bus_infected);
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (!s->v.record_buses) throw ApiError{ESIM_ERR_OPTION_RETRIEVAL, "ESIM_CFG_RECORD_BUSES was not set"};
@@ -1030,6 +1089,7 @@ int esim_read_buses(EsimSim* s, uint32_t* bus_index, uint32_t* bus_infected) {
 }
 
 int esim_inject_rng(EsimSim* s, uint64_t seed) {
+    if (s && !s->kids.empty()) return multi_inject_rng(s, seed);
     return guarded(s, [&]() -> int {
         if (!s) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null handle"};
         s->cfg.seed = seed;
@@ -1048,108 +1108,126 @@ int esim_inject_rng(EsimSim* s, uint64_t seed) {
 
 int esim_get_timings(EsimSim* s, EsimTimings* out) {
     if (!s || !out) return ESIM_ERR_INVALID_ARGUMENT;
+    if (!s->kids.empty()) return esim_get_timings(s->kids[0], out);
     *out = s->timings;
     return ESIM_OK;
 }
 
+// per output area the number of building exposures of every step (step -> count), from the citizens one handle holds
+// (StatisticsRecorder::add_exposure statistics.rs:181-195).  A citizen exposed in a building at step x was standing in its
+// workplace's area iff at_work(x), else in its household's area.
+typedef std::vector<std::map<uint32_t, uint32_t>> AreaExposures;
+static void collect_area_exposures(EsimSim* s, const std::vector<EsimStepStats>& st, AreaExposures& per_area) {
+    CK(cudaSetDevice(s->device));
+    g_pool_stream = s->stream;
+    HostState h;
+    download_state(s, h, true);
+    const uint32_t B = s->v.n_bldg, T = (uint32_t)st.size();
+    for (uint32_t i = 0; i < s->v.n; ++i) {
+        const uint32_t w = h.cstate[i], e = w & CS_EXPOSURE;
+        if (e <= EXPOSURE_BIAS || (w & CS_VIA_PT)) continue;
+        const uint32_t x = e - EXPOSURE_BIAS;
+        if (x == 0 || x > T) continue;
+        uint32_t cell = st[x - 1].at_work ? h.work[i] : h.home[i];
+        if (cell >= B) cell = s->h_room_parent[cell - B];
+        per_area[s->h_bldg_area[cell]][x] += 1;
+    }
+}
+
+// the four files of StatisticsRecorder::dump_to_file (statistics.rs:113-150)
+static void write_dump_files(const std::string& dir, const std::vector<EsimStepStats>& st, const AreaExposures& per_area,
+                             const char* const* area_codes, const std::vector<float>& step_phase_ms, const std::vector<float>& step_total_ms,
+                             size_t device_bytes) {
+    {   // fs::create_dir_all
+        std::string cur;
+        for (size_t k = 0; k < dir.size(); ++k) {
+            cur.push_back(dir[k]);
+            if (dir[k] == '/' && cur.size() > 1 && mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST)
+                throw ApiError{ESIM_ERR_IO, "Failed to create statistics directory: '" + dir + "'"};
+        }
+    }
+    const uint32_t T = (uint32_t)st.size(), n_areas = (uint32_t)per_area.size();
+    auto open = [&](const char* name) {
+        FILE* f = fopen((dir + name).c_str(), "w");
+        if (!f) throw ApiError{ESIM_ERR_IO, std::string("Failed to create results file: ") + name};
+        return f;
+    };
+    // exposures.json: per output area the non-zero per-step counts of building exposures, in step order
+    // (next() statistics.rs:161-164, dump :118-135)
+    {
+        FILE* f = open("exposures.json");
+        fputc('{', f);
+        bool any = false;
+        int last_area = -1;
+        for (uint32_t a = 0; a < n_areas; ++a) if (!per_area[a].empty()) last_area = (int)a;
+        auto write_series = [&](const std::map<uint32_t, uint32_t>& m) {
+            fputc('[', f);
+            bool first = true;
+            for (auto& kv : m) { fprintf(f, first ? "%u" : ",%u", kv.second); first = false; }
+            fputc(']', f);
+        };
+        if (last_area >= 0) {
+            // "All" holds whichever place the reference's HashMap drained last: here the last output area
+            fputs("\"All\":{\"All\":", f);
+            write_series(per_area[last_area]);
+            fputs("},\"OutputArea\":{", f);
+            for (uint32_t a = 0; a < n_areas; ++a) {
+                if (per_area[a].empty()) continue;
+                if (any) fputc(',', f);
+                any = true;
+                if (area_codes && area_codes[a]) fprintf(f, "\"%s\":", area_codes[a]); else fprintf(f, "\"%u\":", a);
+                write_series(per_area[a]);
+            }
+            fputc('}', f);
+            bool pt_any = false;
+            for (auto& e : st) pt_any = pt_any || e.exposures_pt;
+            if (pt_any) fputs(",\"PublicTransport\":{}", f);
+        }
+        fputc('}', f);
+        fclose(f);
+    }
+    {   // timings.json: one map per step (Timer::finished, statistics.rs:75-78)
+        FILE* f = open("timings.json");
+        fputc('[', f);
+        for (uint32_t k = 0; k < T; ++k) {
+            const float* ph = &step_phase_ms[(size_t)k * 3];
+            fprintf(f, "%s{\"Generate Exposures\":%.9g,\"Apply Exposures\":%.9g,\"Apply Interventions\":%.9g,\"total\":%.9g}",
+                    k ? "," : "", ph[0] * 1e-3, ph[1] * 1e-3, ph[2] * 1e-3, step_total_ms[k] * 1e-3);
+        }
+        fputc(']', f);
+        fclose(f);
+    }
+    {   // memory.json: get_memory_usage() per step (config.rs:42-47); here the device memory held by the handle
+        FILE* f = open("memory.json");
+        fputc('[', f);
+        const double gb = (double)(device_bytes / 1024 / 1024) / 1024.0;
+        for (uint32_t k = 0; k < T; ++k) fprintf(f, "%s\"%.2f GB\"", k ? "," : "", gb);
+        fputc(']', f);
+        fclose(f);
+    }
+    {   // global_stats.json: every entry plus the empty one pushed by the flush (statistics.rs:115,169)
+        FILE* f = open("global_stats.json");
+        fputc('[', f);
+        for (uint32_t k = 0; k < T; ++k)
+            fprintf(f, "%s{\"time_step\":%u,\"susceptible\":%u,\"exposed\":%u,\"infected\":%u,\"recovered\":%u,\"vaccinated\":%u}",
+                    k ? "," : "", st[k].time_step, st[k].susceptible, st[k].exposed, st[k].infected, st[k].recovered, st[k].vaccinated);
+        fprintf(f, "%s{\"time_step\":%u,\"susceptible\":0,\"exposed\":0,\"infected\":0,\"recovered\":0,\"vaccinated\":0}]", T ? "," : "", T + 1);
+        fclose(f);
+    }
+}
+
 // StatisticsRecorder::dump_to_file (statistics.rs:113-150)
 int esim_dump_statistics(EsimSim* s, const char* directory, const char* const* area_codes) {
+    if (s && !s->kids.empty()) return multi_dump(s, directory, area_codes);
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (!directory) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null directory"};
-        const std::string dir(directory);
-        {   // fs::create_dir_all
-            std::string cur;
-            for (size_t k = 0; k < dir.size(); ++k) {
-                cur.push_back(dir[k]);
-                if (dir[k] == '/' && cur.size() > 1 && mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST)
-                    throw ApiError{ESIM_ERR_IO, "Failed to create statistics directory: '" + dir + "'"};
-            }
-        }
         const uint32_t T = s->steps_done;
         std::vector<EsimStepStats> st(T);
         if (T) CK(cudaMemcpy(st.data(), s->stats.p, (size_t)T * sizeof(EsimStepStats), cudaMemcpyDeviceToHost));
-        HostState h;
-        download_state(s, h, true);
-        auto open = [&](const char* name) {
-            FILE* f = fopen((dir + name).c_str(), "w");
-            if (!f) throw ApiError{ESIM_ERR_IO, std::string("Failed to create results file: ") + name};
-            return f;
-        };
-        // exposures.json: per output area the non-zero per-step counts of building exposures, in step order
-        // (StatisticsRecorder::add_exposure statistics.rs:181-195, next() :161-164, dump :118-135).  A citizen exposed in a
-        // building at step x was standing in its workplace's area iff at_work(x), else in its household's area.
-        {
-            const uint32_t B = s->v.n_bldg;
-            std::vector<std::map<uint32_t, uint32_t>> per_area(s->n_areas);
-            for (uint32_t i = 0; i < s->v.n; ++i) {
-                const uint32_t w = h.cstate[i], e = w & CS_EXPOSURE;
-                if (e <= EXPOSURE_BIAS || (w & CS_VIA_PT)) continue;
-                const uint32_t x = e - EXPOSURE_BIAS;
-                if (x == 0 || x > T) continue;
-                uint32_t cell = st[x - 1].at_work ? h.work[i] : h.home[i];
-                if (cell >= B) cell = s->h_room_parent[cell - B];
-                per_area[s->h_bldg_area[cell]][x] += 1;
-            }
-            FILE* f = open("exposures.json");
-            fputc('{', f);
-            bool any = false;
-            int last_area = -1;
-            for (uint32_t a = 0; a < s->n_areas; ++a) if (!per_area[a].empty()) last_area = (int)a;
-            auto write_series = [&](const std::map<uint32_t, uint32_t>& m) {
-                fputc('[', f);
-                bool first = true;
-                for (auto& kv : m) { fprintf(f, first ? "%u" : ",%u", kv.second); first = false; }
-                fputc(']', f);
-            };
-            if (last_area >= 0) {
-                // "All" holds whichever place the reference's HashMap drained last: here the last output area
-                fputs("\"All\":{\"All\":", f);
-                write_series(per_area[last_area]);
-                fputs("},\"OutputArea\":{", f);
-                for (uint32_t a = 0; a < s->n_areas; ++a) {
-                    if (per_area[a].empty()) continue;
-                    if (any) fputc(',', f);
-                    any = true;
-                    if (area_codes && area_codes[a]) fprintf(f, "\"%s\":", area_codes[a]); else fprintf(f, "\"%u\":", a);
-                    write_series(per_area[a]);
-                }
-                fputc('}', f);
-                bool pt_any = false;
-                for (auto& e : st) pt_any = pt_any || e.exposures_pt;
-                if (pt_any) fputs(",\"PublicTransport\":{}", f);
-            }
-            fputc('}', f);
-            fclose(f);
-        }
-        {   // timings.json: one map per step (Timer::finished, statistics.rs:75-78)
-            FILE* f = open("timings.json");
-            fputc('[', f);
-            for (uint32_t k = 0; k < T; ++k) {
-                const float* ph = &s->step_phase_ms[(size_t)k * 3];
-                fprintf(f, "%s{\"Generate Exposures\":%.9g,\"Apply Exposures\":%.9g,\"Apply Interventions\":%.9g,\"total\":%.9g}",
-                        k ? "," : "", ph[0] * 1e-3, ph[1] * 1e-3, ph[2] * 1e-3, s->step_total_ms[k] * 1e-3);
-            }
-            fputc(']', f);
-            fclose(f);
-        }
-        {   // memory.json: get_memory_usage() per step (config.rs:42-47); here the device memory held by the handle
-            FILE* f = open("memory.json");
-            fputc('[', f);
-            const double gb = (double)(s->device_bytes / 1024 / 1024) / 1024.0;
-            for (uint32_t k = 0; k < T; ++k) fprintf(f, "%s\"%.2f GB\"", k ? "," : "", gb);
-            fputc(']', f);
-            fclose(f);
-        }
-        {   // global_stats.json: every entry plus the empty one pushed by the flush (statistics.rs:115,169)
-            FILE* f = open("global_stats.json");
-            fputc('[', f);
-            for (uint32_t k = 0; k < T; ++k)
-                fprintf(f, "%s{\"time_step\":%u,\"susceptible\":%u,\"exposed\":%u,\"infected\":%u,\"recovered\":%u,\"vaccinated\":%u}",
-                        k ? "," : "", st[k].time_step, st[k].susceptible, st[k].exposed, st[k].infected, st[k].recovered, st[k].vaccinated);
-            fprintf(f, "%s{\"time_step\":%u,\"susceptible\":0,\"exposed\":0,\"infected\":0,\"recovered\":0,\"vaccinated\":0}]", T ? "," : "", T + 1);
-            fclose(f);
-        }
+        AreaExposures per_area(s->n_areas);
+        collect_area_exposures(s, st, per_area);
+        write_dump_files(directory, st, per_area, area_codes, s->step_phase_ms, s->step_total_ms, s->device_bytes);
         return ESIM_OK;
     });
 }
@@ -1164,6 +1242,7 @@ static_assert(sizeof(PeerInfo) <= ESIM_PEER_INFO_BYTES, "peer info does not fit"
 }  // namespace
 
 int esim_peer_info(EsimSim* s, uint8_t info[ESIM_PEER_INFO_BYTES]) {
+    if (s && !s->kid_devices.empty()) return fail(s, ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle exchanges by itself");
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (!info) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null info"};
@@ -1172,7 +1251,7 @@ int esim_peer_info(EsimSim* s, uint8_t info[ESIM_PEER_INFO_BYTES]) {
         std::memset(&pi, 0, sizeof(pi));
         CK(cudaIpcGetMemHandle(&pi.cnt, s->cnt_all.p));
         pi.cnt_stride = (uint32_t)s->cnt_stride;
-        pi.fused_ok = !(s->cfg.flags & (ESIM_CFG_UNFUSED | ESIM_CFG_PERSISTENT)) && !getenv("ESIM_UNFUSED") ? 1u : 0u;
+        pi.fused_ok = 1u;   // peer-to-peer shards always run the fused pipeline
         CK(cudaIpcGetMemHandle(&pi.mail, s->peer_mail.p));
         pi.n_bldg = s->v.n_bldg; pi.n_rooms = s->v.n_rooms; pi.n_shared_b = s->n_shared_bldgs; pi.n_shared_r = s->n_shared_rooms;
         pi.world = s->world; pi.device = (uint32_t)s->device;
@@ -1183,6 +1262,7 @@ int esim_peer_info(EsimSim* s, uint8_t info[ESIM_PEER_INFO_BYTES]) {
 }
 
 int esim_peer_connect(EsimSim* s, uint32_t rank, uint32_t world, const uint8_t* all_infos) {
+    if (s && !s->kid_devices.empty()) return fail(s, ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle exchanges by itself");
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (!all_infos || world != s->world || rank >= world || world > MAX_WORLD)
@@ -1245,6 +1325,7 @@ int esim_comm_unique_id(uint8_t id[128]) {
 }
 
 int esim_comm_init(EsimSim* s, const uint8_t id[128], uint32_t rank, uint32_t world) {
+    if (s && !s->kid_devices.empty()) return fail(s, ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle exchanges by itself");
     return guarded(s, [&]() -> int {
         require_ready(s);
         NcclApi* n = nccl_api();
@@ -1265,6 +1346,7 @@ int esim_comm_init(EsimSim* s, const uint8_t id[128], uint32_t rank, uint32_t wo
 }
 
 int esim_shard_step_begin(EsimSim* s) {
+    if (s && !s->kid_devices.empty()) return fail(s, ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle exchanges by itself");
     return guarded(s, [&]() -> int {
         require_ready(s);
         if (s->steps_done >= s->cfg.max_time_step && !s->finished) throw ApiError{ESIM_ERR_SIMULATION, "max_time_step reached"};
@@ -1275,6 +1357,7 @@ int esim_shard_step_begin(EsimSim* s) {
 }
 
 int esim_shard_step_middle(EsimSim* s) {
+    if (s && !s->kid_devices.empty()) return fail(s, ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle exchanges by itself");
     return guarded(s, [&]() -> int {
         require_ready(s);
         launch_expose(s->v, s->stream);
@@ -1286,6 +1369,7 @@ int esim_shard_step_middle(EsimSim* s) {
 }
 
 int esim_shard_step_end(EsimSim* s, EsimStepStats* out) {
+    if (s && !s->kid_devices.empty()) return fail(s, ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle exchanges by itself");
     return guarded(s, [&]() -> int {
         require_ready(s);
         const uint32_t before = s->steps_done;
@@ -1342,3 +1426,290 @@ void esim_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 const char* esim_last_error(EsimSim* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
 
 }  // extern "C"
+
+// ---- single-process multi-device handle -----------------------------------------------------------------------------------
+// "one handle drives all local GPUs ... so the caller stays single-threaded like the reference" (simulator.rs:87-103,
+// run/src/main.rs:290-306).  The handle shards the population by output area (esim_shard_create), owns one sub-handle per
+// shard, maps the shards' count buffers and mailboxes into each other with CUDA peer access (no IPC: one address space) and
+// runs the same peer-to-peer kernels as one-process-per-GPU shards.  Every call queues its work on all devices before it waits
+// for any of them: the shards wait for each other inside their kernels.
+namespace {
+
+int kid_rc(EsimSim* k, int rc, uint32_t r) {
+    if (rc < 0) throw ApiError{rc, "shard " + std::to_string(r) + " (device " + std::to_string(k->device) + "): " + k->err};
+    return rc;
+}
+
+void multi_sync_parent(EsimSim* s) {
+    s->steps_done = s->kids[0]->steps_done;
+    s->finished = s->kids[0]->finished;
+    for (size_t r = 1; r < s->kids.size(); ++r)
+        if (s->kids[r]->steps_done != s->steps_done || s->kids[r]->finished != s->finished)
+            throw ApiError{ESIM_ERR_SIMULATION, "the shards of a multi-device handle disagree about the step they have reached"};
+}
+
+// map every shard's count buffers and mailbox into every other shard (same process: plain device pointers + peer access),
+// switch the shards to the fused peer-to-peer pipeline and run its boot pass on all of them
+void multi_connect(EsimSim* s) {
+    const uint32_t world = (uint32_t)s->kids.size();
+    if (world < 2) return;
+    if (world > MAX_WORLD) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "at most 8 shards"};
+    for (uint32_t a = 0; a < world; ++a)
+        for (uint32_t b = 0; b < world; ++b) {
+            const int da = s->kids[a]->device, db = s->kids[b]->device;
+            if (da == db) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, da, db));
+            if (!can) throw ApiError{ESIM_ERR_COMM, "device " + std::to_string(da) + " cannot access device " + std::to_string(db) + " (no NVLink / peer access)"};
+            CK(cudaSetDevice(da));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CK(e);
+        }
+    for (uint32_t r = 0; r < world; ++r) {
+        EsimSim* k = s->kids[r];
+        CK(cudaSetDevice(k->device));
+        g_pool_stream = k->stream;
+        PeerView pv;
+        std::memset(&pv, 0, sizeof(pv));
+        for (uint32_t p = 0; p < world; ++p) {
+            EsimSim* o = s->kids[p];
+            if (o->n_shared_bldgs != k->n_shared_bldgs || o->n_shared_rooms != k->n_shared_rooms)
+                throw ApiError{ESIM_ERR_INVALID_POPULATION, "the shards disagree about the shared cells"};
+            pv.n_bldg[p] = o->v.n_bldg;
+            for (int c = 0; c < 3; ++c) pv.cnt[c][p] = o->v.cnt[c];
+            pv.mail[p] = o->peer_mail.p;
+        }
+        k->peer_view.alloc(1);
+        CK(cudaMemcpyAsync(k->peer_view.p, &pv, sizeof(pv), cudaMemcpyHostToDevice, k->stream));
+        k->v.rank = r; k->rank = r;
+        k->v.peer = k->peer_view.p;
+        k->v.p2p = 1;
+        k->fused = true; k->v.fused = 1;
+        const uint32_t zero = 0;
+        CK(cudaMemcpyAsync(&k->ctrl.p->t, &zero, sizeof(zero), cudaMemcpyHostToDevice, k->stream));
+        CK(cudaStreamSynchronize(k->stream));   // `pv` and `zero` are on this stack frame
+    }
+    // boot pass ("step 0") on every device before anybody waits: its tail exchanges the first class counts
+    for (EsimSim* k : s->kids) { CK(cudaSetDevice(k->device)); launch_boot_fused(k->v, k->stream); CK(cudaGetLastError()); }
+    for (EsimSim* k : s->kids) {
+        CK(cudaSetDevice(k->device));
+        g_pool_stream = k->stream;
+        if (!(k->cfg.flags & ESIM_CFG_NO_GRAPH)) capture_graphs(k);
+        CK(cudaMemcpyAsync(k->h_ctrl, k->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, k->stream));
+    }
+    for (EsimSim* k : s->kids) { CK(cudaSetDevice(k->device)); CK(cudaStreamSynchronize(k->stream)); CK(cudaGetLastError()); }
+    for (uint32_t r = 0; r < world; ++r)
+        if (s->kids[r]->h_ctrl->error) throw ApiError{-(int)s->kids[r]->h_ctrl->error, "boot pass of shard " + std::to_string(r) + " raised a device-side error"};
+}
+
+void require_multi_ready(EsimSim* s) {
+    if (!s) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null handle"};
+    if (!s->imported) throw ApiError{ESIM_ERR_INITIALIZATION, "Population has not been Initialized"};
+}
+
+}  // namespace
+
+static int multi_import(EsimSim* s, const EsimPopulationSoA* p) {
+    return guarded(s, [&]() -> int {
+        if (!p || !p->home_bldg || !p->work_bldg || !p->room || !p->bldg_area || !p->bldg_type || (p->n_rooms && !p->room_bldg))
+            throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population arrays missing"};
+        if (s->imported) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population already imported"};
+        if (p->n_shards > 1 || p->global_id) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle takes the whole population and shards it itself"};
+        const uint32_t N = p->n_citizens, A = p->n_areas, B = p->n_buildings, world = (uint32_t)s->kid_devices.size();
+        if (N == 0 || B == 0 || A == 0) throw ApiError{ESIM_ERR_INVALID_POPULATION, "empty population"};
+        // the shards are contiguous ranges of output areas: citizens must be grouped by home area, ascending - the order
+        // `impl From<SimulatorBuilder> for Simulator` walks them in (simulator.rs:601-644)
+        std::vector<uint32_t> area_off((size_t)A + 1, 0);
+        {
+            uint32_t prev = 0;
+            for (uint32_t i = 0; i < N; ++i) {
+                const uint32_t h = p->home_bldg[i];
+                if (h >= B) throw ApiError{ESIM_ERR_MISSING_CITIZEN, "citizen references a building that does not exist (index " + std::to_string(i) + ")"};
+                const uint32_t a = p->bldg_area[h];
+                if (a >= A) throw ApiError{ESIM_ERR_INVALID_POPULATION, "building with invalid area"};
+                if (a < prev) throw ApiError{ESIM_ERR_INVALID_POPULATION, "a multi-device handle needs the citizens grouped by home output area, ascending (citizen " + std::to_string(i) + ")"};
+                for (uint32_t x = prev + 1; x <= a; ++x) area_off[x] = i;
+                prev = a;
+            }
+            for (uint32_t x = prev + 1; x <= A; ++x) area_off[x] = N;
+        }
+        for (uint32_t r = 0; r < world; ++r) {
+            EsimShard* sh = nullptr;
+            const int src = esim_shard_create(p, area_off.data(), r, world, &sh);
+            if (src < 0) throw ApiError{src, "sharding the population failed"};
+            s->kid_shards.push_back(sh);
+            EsimPopulationSoA sp;
+            esim_shard_view(sh, &sp);
+            if (sp.n_citizens == 0) throw ApiError{ESIM_ERR_INVALID_POPULATION, "fewer populated output areas than devices"};
+            EsimConfig c = s->cfg;
+            c.device = s->kid_devices[r];
+            EsimSim* k = nullptr;
+            const int crc = esim_create(&c, &k);
+            if (crc < 0) throw ApiError{crc, "device " + std::to_string(c.device) + ": " + g_create_error};
+            s->kids.push_back(k);
+            // shards that share a device wait for each other inside their kernels: their grids must be resident together and no
+            // block may sit on an SM waiting for its predecessor (programmatic launch) while the peer it depends on needs the SM
+            uint32_t share = 0;
+            for (int d : s->kid_devices) share += d == c.device;
+            k->share = share;
+            if (share > 1) k->no_pdl = true;
+            if (world == 1) { sp.n_shards = 0; sp.global_id = nullptr; }   // one device: a plain single-shard handle
+            kid_rc(k, esim_import_population(k, &sp), r);
+            s->kid_lo.push_back(world == 1 ? 0u : sp.global_id[0]);
+        }
+        multi_connect(s);
+        s->n_total = N; s->nb_total = B; s->nr_total = p->n_rooms; s->n_areas = A;
+        s->imported = true;
+        multi_sync_parent(s);
+        return ESIM_OK;
+    });
+}
+
+static int multi_step(EsimSim* s, EsimStepStats* out, bool timed) {
+    return guarded(s, [&]() -> int {
+        require_multi_ready(s);
+        for (EsimSim* k : s->kids) step_enqueue(k, timed);
+        int rc = 1;
+        for (size_t r = 0; r < s->kids.size(); ++r) {
+            try { rc = step_collect(s->kids[r], r == 0 ? out : nullptr, timed); }
+            catch (const ApiError& e) { throw ApiError{e.code, "shard " + std::to_string(r) + ": " + e.msg}; }
+        }
+        multi_sync_parent(s);
+        return rc;
+    });
+}
+
+static int multi_run(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
+    return guarded(s, [&]() -> int {
+        require_multi_ready(s);
+        const uint32_t start = s->steps_done;
+        uint32_t budget = std::min<uint32_t>(max_steps, s->cfg.max_time_step - std::min(s->cfg.max_time_step, start));
+        while (budget > 0 && !s->finished) {
+            // the control blocks are replicated, so every shard queues the same chunk
+            for (EsimSim* k : s->kids) run_enqueue(k, budget);
+            uint32_t executed = 0;
+            for (size_t r = 0; r < s->kids.size(); ++r) {
+                try { executed = run_collect(s->kids[r]); }
+                catch (const ApiError& e) { throw ApiError{e.code, "shard " + std::to_string(r) + ": " + e.msg}; }
+            }
+            multi_sync_parent(s);
+            budget -= std::min(budget, executed);
+            if (executed == 0 && !s->finished) throw ApiError{ESIM_ERR_SIMULATION, "no progress"};
+        }
+        if (steps_done) *steps_done = s->steps_done - start;
+        return s->finished ? 0 : 1;
+    });
+}
+
+// timed steps of a multi-device handle: one host thread, so no look-ahead is needed to keep the shards in phase
+static int multi_run_timed(EsimSim* s, uint32_t max_steps, uint32_t* steps_done) {
+    const uint32_t start = s ? s->steps_done : 0u;
+    int rc = 1;
+    for (uint32_t k = 0; s && k < max_steps && !s->finished && s->steps_done < s->cfg.max_time_step; ++k) {
+        rc = multi_step(s, nullptr, true);
+        if (rc < 0) return rc;
+    }
+    if (s && steps_done) *steps_done = s->steps_done - start;
+    return s ? (s->finished ? 0 : 1) : ESIM_ERR_INVALID_ARGUMENT;
+}
+
+static int multi_read_state(EsimSim* s, EsimStateView* view) {
+    return guarded(s, [&]() -> int {
+        require_multi_ready(s);
+        if (!view) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null view"};
+        for (size_t r = 0; r < s->kids.size(); ++r) {
+            const uint32_t lo = s->kid_lo[r];
+            EsimStateView v{};
+            v.status = view->status ? view->status + lo : nullptr;
+            v.timer = view->timer ? view->timer + lo : nullptr;
+            v.current_bldg = view->current_bldg ? view->current_bldg + lo : nullptr;
+            v.on_pt = view->on_pt ? view->on_pt + lo : nullptr;
+            v.vax_eligible = view->vax_eligible ? view->vax_eligible + lo : nullptr;
+            kid_rc(s->kids[r], esim_read_state(s->kids[r], &v), (uint32_t)r);
+            if (view->current_bldg && s->kids.size() > 1) {   // shard-local building ids -> the caller's
+                const uint32_t* g = esim_shard_bldg_global(s->kid_shards[r]);
+                const uint32_t n = s->kids[r]->v.n;
+                for (uint32_t i = 0; i < n; ++i) v.current_bldg[i] = g[v.current_bldg[i]];
+            }
+        }
+        return ESIM_OK;
+    });
+}
+
+static int multi_read_building_counts(EsimSim* s, uint32_t* bldg, uint32_t* room) {
+    return guarded(s, [&]() -> int {
+        require_multi_ready(s);
+        if (s->kids.size() == 1) return kid_rc(s->kids[0], esim_read_building_counts(s->kids[0], bldg, room), 0);
+        if (bldg) std::fill(bldg, bldg + s->nb_total, 0u);
+        if (room) std::fill(room, room + s->nr_total, 0u);
+        for (size_t r = 0; r < s->kids.size(); ++r) {
+            EsimSim* k = s->kids[r];
+            std::vector<uint32_t> b(k->v.n_bldg), m(std::max<uint32_t>(k->v.n_rooms, 1));
+            kid_rc(k, esim_read_building_counts(k, bldg ? b.data() : nullptr, room ? m.data() : nullptr), (uint32_t)r);
+            // a shared cell holds the global count on every shard, any other cell exists on one shard only
+            const uint32_t* bg = esim_shard_bldg_global(s->kid_shards[r]);
+            const uint32_t* rg = esim_shard_room_global(s->kid_shards[r]);
+            if (bldg) for (uint32_t l = 0; l < k->v.n_bldg; ++l) bldg[bg[l]] = b[l];
+            if (room) for (uint32_t l = 0; l < k->v.n_rooms; ++l) room[rg[l]] = m[l];
+        }
+        return ESIM_OK;
+    });
+}
+
+static int multi_read_buses(EsimSim* s, uint32_t* bus_index, uint32_t* bus_infected) {
+    return guarded(s, [&]() -> int {
+        require_multi_ready(s);
+        for (size_t r = 0; r < s->kids.size(); ++r) {
+            const uint32_t lo = s->kid_lo[r];
+            kid_rc(s->kids[r], esim_read_buses(s->kids[r], bus_index ? bus_index + lo : nullptr, bus_infected ? bus_infected + lo : nullptr), (uint32_t)r);
+        }
+        return ESIM_OK;
+    });
+}
+
+static int multi_inject_rng(EsimSim* s, uint64_t seed) {
+    return guarded(s, [&]() -> int {
+        s->cfg.seed = seed;
+        for (size_t r = 0; r < s->kids.size(); ++r) kid_rc(s->kids[r], esim_inject_rng(s->kids[r], seed), (uint32_t)r);
+        return ESIM_OK;
+    });
+}
+
+static int multi_dump(EsimSim* s, const char* directory, const char* const* area_codes) {
+    return guarded(s, [&]() -> int {
+        require_multi_ready(s);
+        if (!directory) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "null directory"};
+        EsimSim* k0 = s->kids[0];
+        const uint32_t T = s->steps_done;
+        std::vector<EsimStepStats> st(T);
+        CK(cudaSetDevice(k0->device));
+        if (T) CK(cudaMemcpy(st.data(), k0->stats.p, (size_t)T * sizeof(EsimStepStats), cudaMemcpyDeviceToHost));
+        AreaExposures per_area(s->n_areas);
+        size_t bytes = 0;
+        for (EsimSim* k : s->kids) { collect_area_exposures(k, st, per_area); bytes += k->device_bytes; }
+        write_dump_files(directory, st, per_area, area_codes, k0->step_phase_ms, k0->step_total_ms, bytes);
+        return ESIM_OK;
+    });
+}
+
+extern "C" int esim_create_multi(const EsimConfig* cfg, uint32_t n_devices, const int32_t* devices, EsimSim** out) {
+    if (!cfg || !out) return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (n_devices == 0 || n_devices > MAX_WORLD) return fail(nullptr, ESIM_ERR_INVALID_ARGUMENT, "between 1 and 8 devices");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, ESIM_ERR_NO_DEVICE, "no CUDA device: libesim_b200 has no CPU fallback");
+    }
+    EsimSim* s = new (std::nothrow) EsimSim();
+    if (!s) return fail(nullptr, ESIM_ERR_DEFAULT, "out of host memory");
+    s->cfg = *cfg;
+    s->device = -1;
+    for (uint32_t r = 0; r < n_devices; ++r) {
+        const int d = devices ? devices[r] : (int)r;
+        if (d < 0 || d >= n_dev) { delete s; return fail(nullptr, ESIM_ERR_NO_DEVICE, "device ordinal out of range"); }
+        s->kid_devices.push_back(d);
+    }
+    *out = s;
+    return ESIM_OK;
+}

@@ -41,37 +41,40 @@ constexpr uint32_t CS_HAS_WORK    = 1u << 20;
 constexpr uint32_t CS_PADDING     = 0xFFFFu;
 constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 2
 constexpr uint32_t MAX_STEPS      = CS_EXPOSURE - EXPOSURE_BIAS - 1;
-constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer, see k_vax_prepare
-// fused pipeline: one nibble per candidate draw instead of one bit (8 = owned, eligible, first occurrence; low 3 bits = the
-// class k_step counted the citizen in for the next step, 4 = already vaccinated), so that every shard can correct the global
-// class counts for the citizens chosen on other shards without a second exchange
-constexpr uint32_t FEXCH_WORDS    = 8 + ESIM_VAX_SHARD_DRAWS / 8;
+constexpr uint32_t EXCH_WORDS     = 8 + ESIM_VAX_SHARD_DRAWS / 32;  // second exchange buffer of the three-kernel pipeline, see k_vax_prepare
+// Fused pipeline over peer-to-peer shards: the candidate draws of the vaccination stream are examined in chunks of
+// ESIM_VAX_SHARD_DRAWS; a round of the tail exchange carries between 1 and VAX_MAX_CHUNKS chunks (as many as the eligible
+// share of the population makes necessary, decided from replicated state) and further rounds follow until the hourly
+// rate is met, so that shards and a single GPU choose the same citizens for ANY eligible share.  One nibble per draw
+// (8 = owned, eligible, first occurrence; low 3 bits = the class k_step counted the citizen in for the next step, 4 = already
+// vaccinated), so that every shard can correct the global class counts for the citizens chosen on other shards.
+constexpr uint32_t VAX_MAX_CHUNKS  = 8;
+constexpr uint32_t VAX_CHUNK_WORDS = ESIM_VAX_SHARD_DRAWS / 8;        // nibble words per chunk
+constexpr uint32_t FEXCH_HEAD      = 8;                               // S,E,I,R,V of step t + 1, building / public-transport exposures of step t, spare
+constexpr uint32_t FEXCH_WORDS     = FEXCH_HEAD + VAX_MAX_CHUNKS * VAX_CHUNK_WORDS;
 
 constexpr uint32_t KTRACE_STEPS = 1024, KTRACE_KERNELS = 6;   // 0 = update / step, 1 = expose or exchange wait, 2 = pt, 3 = tail, 4 = tail: loads -> vector sent, 5 = spare
 
 // index of the count buffer that holds the infected occupants of step t
 __host__ __device__ inline uint32_t cnt_slot(uint32_t fused, uint32_t t) { return fused ? t % 3u : t & 1u; }
 
-// ---- peer-to-peer exchange of a sharded run (one process per GPU, NVLink peer mappings) --------------------------------
+// ---- peer-to-peer exchange of a sharded run (NVLink peer mappings: CUDA IPC between processes, peer access inside one) -------
 // Every shard owns a mailbox in its own HBM that its peers write into:
-//   flag_a[r]  time step for which peer r has finished pushing its infected counts into this shard's count buffer
-//   flag_b[r]  time step for which peer r's tail vector has arrived
-//   flag_c[r]  (fused) peer r's tail has finished taking the citizens it vaccinated out of this shard's count buffer
-//   vec_b[t & 1][r][..]  peer r's tail vector of step t (double-buffered: a peer can be at most one step ahead)
-// Three-kernel pipeline: flags hold t.  Fused pipeline: flags hold t + 1 (its boot pass runs as "step 0"), flag_a is raised by
-// k_step of step t for the counts of step t + 1.
+//   flag_c[r]   peer r's tail has finished taking the citizens it vaccinated out of this shard's count buffer (value t + 1)
+//   sync[r]     esim_step_timed / esim_run_timed: peer r has reached the start of timed step number `value` (benchmark hygiene:
+//               the shards leave their L2 flushes together, so that a timed step does not contain the skew of the flushes)
+//   ll2[t & 1][r][8]                     small second exchange of a tail (value, tag) - only when a whole eligible set is chosen
+//   ll[t & 1][round & 1][r][FEXCH_WORDS] the tail vectors as (value, tag) pairs written with one 8-byte store each
+//               (tag = (t + 1) | round << 16); the receiver spins on the tag of every pair it needs, so neither a system-wide
+//               fence nor a separate arrival flag is on the critical path.  A peer can be at most one round ahead.
+// The fused pipeline's boot pass runs as "step 0"; infected counts of shared cells are pushed by k_step of step t for step t + 1.
 constexpr uint32_t MAX_WORLD      = 8;
-constexpr uint32_t MAIL_FLAG_A    = 0;
-constexpr uint32_t MAIL_FLAG_B    = MAX_WORLD;
-constexpr uint32_t MAIL_FLAG_C    = 2 * MAX_WORLD;
-constexpr uint32_t MAIL_VEC_B     = 32;
-constexpr uint32_t MAIL_VEC_STRIDE = EXCH_WORDS;
-// Fused pipeline: the tail vectors travel as (value, tag) pairs written with one 8-byte store each (tag = t + 1); the receiver
-// spins on the tag of every pair it needs, so neither a system-wide fence nor a separate arrival flag is on the critical path.
-//   ll[t & 1][r][FEXCH_WORDS] pairs of peer r
-constexpr uint32_t MAIL_LL        = MAIL_VEC_B + 2 * MAX_WORLD * MAIL_VEC_STRIDE;   // first word of the pair region (8-byte aligned)
-constexpr uint32_t MAIL_WORDS     = MAIL_LL + 2 * (2 * MAX_WORLD * FEXCH_WORDS);
-static_assert(MAIL_LL % 2 == 0, "pairs must be 8-byte aligned");
+constexpr uint32_t MAIL_FLAG_C    = 0;
+constexpr uint32_t MAIL_SYNC      = MAX_WORLD;
+constexpr uint32_t MAIL_LL2       = 32;
+constexpr uint32_t MAIL_LL        = MAIL_LL2 + 2 * (2 * MAX_WORLD * 8);   // first word of the pair region (8-byte aligned)
+constexpr uint32_t MAIL_WORDS     = MAIL_LL + 2 * (2 * 2 * MAX_WORLD * FEXCH_WORDS);
+static_assert(MAIL_LL % 2 == 0 && MAIL_LL2 % 2 == 0, "pairs must be 8-byte aligned");
 struct PeerView {                       // lives in device memory: kernel parameters stay small
     uint32_t n_bldg[MAX_WORLD];         // peers' n_bldg (their room cells start there)
     uint32_t* cnt[3][MAX_WORLD];        // peers' count buffers
@@ -105,7 +108,7 @@ struct Ctrl {
     uint32_t next_at_work, next_pt_mode;
     uint32_t vax_event;      // update_status raised the Vaccination event for step t: the tail of step t takes the snapshot
     uint32_t vax_all_done;   // the whole eligible set has been vaccinated once: choosing all of it again changes nothing
-    uint32_t pushed_any;     // fused peer-to-peer shards: k_step (or the boot k_update) added to a peer's count buffer
+    uint32_t lockdown_event; // corrected mode: update_status raised the Lockdown event: everybody is sent home (simulator.rs:467-479)
 };
 
 struct ModelParams {
@@ -113,6 +116,13 @@ struct ModelParams {
     double th_lockdown, th_vaccination, th_mask_pt, th_mask_everywhere;
     uint32_t seed_lo, seed_hi;
     uint32_t n_global_citizens, shard_lo;
+    // ESIM_CFG_CORRECTED (the reference's own TODOs fixed, strictly opt-in): masks protect the compliant citizens
+    // (citizen.rs:228-232 inverted), on public transport from MaskStatus::PublicTransport on; `exposure_total` is not cut to
+    // u8 (citizen.rs:239) but saturates at n_mask; every exposure and every vaccination removes the citizen from the eligible
+    // set, so only Susceptible citizens are vaccinated (simulator.rs:346-348, :482); a Lockdown event sends everybody home
+    // (simulator.rs:467-479).
+    uint32_t corrected;
+    uint32_t n_mask;        // trial threshold table: thr[2][n_mask + 1]; parity mode 255 (n as u8), corrected mode 16383
 };
 
 // everything a kernel needs, passed by value
@@ -152,8 +162,12 @@ struct DevView {
     uint32_t n_shared_b, n_shared_r;   // the first cells of the building / room ranges exist on every shard
     const PeerView* peer;        // device memory, valid when p2p
     uint32_t world;              // number of shards (1 = the whole population is here)
-    uint32_t* exch;              // [FEXCH_WORDS] second exchange buffer of a sharded step
-    uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] candidate citizen of every draw of this step
+    uint32_t* exch;              // [EXCH_WORDS] second exchange buffer of a sharded step of the three-kernel pipeline
+    uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] three-kernel pipeline: candidate citizen of every draw of this step
+    uint32_t share;              // handles that share this device and wait for each other inside their kernels (0 / 1 = alone)
+    uint32_t no_pdl;             // launch the step kernels without programmatic dependent launch
+    uint32_t sync_seq;           // esim_step_timed on peer-to-peer shards: number of the timed step (see MAIL_SYNC), 0 = no barrier
+    unsigned long long peer_timeout_ns;   // a wait for a peer that lasts longer raises ESIM_ERR_COMM instead of hanging the GPU (ESIM_PEER_TIMEOUT_MS, default 30 s)
     uint32_t* tally_partial;     // [n_update_blocks * 8] per-block S,E,I,R,V partial sums of k_update
     uint32_t n_update_blocks;
     // ESIM_KTRACE=1: device-side timeline (%globaltimer) of the step kernels, [KTRACE_STEPS][KTRACE_KERNELS] slots each for
@@ -170,18 +184,16 @@ void launch_update(const DevView& v, cudaStream_t s);
 void launch_expose(const DevView& v, cudaStream_t s);
 void launch_pt(const DevView& v, cudaStream_t s);
 void launch_tail(const DevView& v, cudaStream_t s);
-void launch_vax_prepare(const DevView& v, cudaStream_t s);  // sharded runs only
-// fused pipeline (single shard): k_step = apply_exposures of step t + generate_exposures of step t + 1 in one pass
+void launch_vax_prepare(const DevView& v, cudaStream_t s);  // NCCL / phase-level sharded runs only
+// fused pipeline: k_step = apply_exposures of step t + generate_exposures of step t + 1 in one pass
 void launch_step_fused(const DevView& v, cudaStream_t s);
 void launch_tail_fused(const DevView& v, cudaStream_t s);
 void launch_boot_fused(const DevView& v, cudaStream_t s);   // once, with Ctrl::t == 0: k_update counts step 1, the tail runs as "step 0"
-uint32_t step_blocks(uint32_t n_pad);
+void launch_peer_sync(const DevView& v, cudaStream_t s);    // peer-to-peer shards: one-thread barrier kernel (MAIL_SYNC)
+uint32_t step_blocks(const DevView& v);
+uint32_t update_blocks(const DevView& v);
 void launch_flush_sweep(const void* scratch, size_t bytes, uint32_t* sink, cudaStream_t s);   // ESIM_CFG_FLUSH_L2
 int  configure_kernels();   // opt-in shared memory etc.; returns cudaError_t as int
 int  sm_count();
-void set_pdl(bool on);   // programmatic dependent launch of the step kernels (default on)
-uint32_t update_blocks(uint32_t n_pad);
-int  persistent_grid();   // co-resident blocks of k_persistent (0 = unavailable)
-int  launch_persistent(const DevView& v, uint32_t n_steps, unsigned int* barrier_counter, unsigned long long* prof, cudaStream_t s);
 
 }  // namespace esim

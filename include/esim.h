@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ESIM_ABI_VERSION 1
+#define ESIM_ABI_VERSION 2
 
 /* ---- error codes: SimError variants (sim/src/error.rs:24-52) mapped to integers ---------------- */
 #define ESIM_OK                      0
@@ -71,13 +71,17 @@ extern "C" {
 /* config flag bits */
 #define ESIM_CFG_RECORD_BUSES 0x1u /* keep per-rider (bus, infected-on-bus) of the last PT step for parity reads */
 #define ESIM_CFG_NO_GRAPH     0x2u /* launch kernels directly instead of replaying the captured CUDA graph   */
-#define ESIM_CFG_PERSISTENT   0x8u /* experimental: esim_run launches one cooperative kernel with grid-wide barriers between the
-                                      phases instead of replaying CUDA graphs (single shard; currently slower) */
 #define ESIM_CFG_UNFUSED      0x10u /* single shard: use the three-kernel step (k_update, k_expose, k_tail) instead of the fused
                                        one-pass step (k_step, k_tail_fused); results are identical (parity tests run both)   */
 #define ESIM_CFG_TIME_KERNELS 0x20u /* esim_step_timed records a CUDA event between every two kernels (per-kernel split in
                                        EsimTimings; each event costs ~2.5 us of stream time and ends the programmatic overlap
                                        of consecutive kernels).  Without it only the whole step is timed.            */
+#define ESIM_CFG_CORRECTED    0x40u /* opt-in "corrected semantics" (the reference's own TODOs at simulator.rs:467,482,
+                                       citizen.rs:228-239 fixed): masks protect the COMPLIANT citizens (on public transport from
+                                       MaskStatus::PublicTransport on), the infected count of a trial is not cut to u8 (it saturates at
+                                       16383), every exposure and every vaccination leaves the eligible set (only Susceptible citizens
+                                       are vaccinated), and a Lockdown event sends everybody home.  Parity mode (flag clear) reproduces
+                                       the reference's behaviour bit for bit; the two never mix. */
 #define ESIM_CFG_FLUSH_L2     0x4u /* esim_step_timed overwrites a 256 MiB scratch buffer before every step, so
                                       that each timed step starts with a cold L2 (benchmark hygiene only)       */
 
@@ -205,6 +209,19 @@ int esim_default_config(EsimConfig* cfg);
 int  esim_create(const EsimConfig* cfg, EsimSim** out);
 int  esim_import_population(EsimSim* sim, const EsimPopulationSoA* pop);
 void esim_destroy(EsimSim* sim);
+
+/*
+ * One handle, one host thread, several GPUs: what the reference's single-process `run` binary needs to use more than one GPU
+ * as a drop-in (run/src/main.rs:290-306 builds ONE Simulator and calls simulate on it; simulator.rs:87-103).
+ * devices: n_devices CUDA ordinals (NULL = 0 .. n_devices-1), at most 8.  esim_import_population then takes the WHOLE population
+ * (citizens grouped by home output area, ascending - the order Simulator::from walks them in), splits it into contiguous
+ * output-area ranges balanced by residents, one per device, and connects the shards through CUDA peer access; every other entry
+ * point (esim_step, esim_run, esim_read_*, esim_dump_statistics, esim_inject_rng ...) works on the handle as on a single-GPU one
+ * and returns whole-population results in the caller's numbering.  The esim_peer_* / esim_comm_* / esim_shard_step_* entry points
+ * (one handle per process and GPU) do not apply to it.  A device may be named more than once (several shards share it) - meant
+ * for tests on a single-GPU machine with small populations.
+ */
+int  esim_create_multi(const EsimConfig* cfg, uint32_t n_devices, const int32_t* devices /* nullable */, EsimSim** out);
 
 /* Simulator::step (simulator.rs:131-152): returns 1 = disease still exists, 0 = finished, <0 = error. */
 int esim_step(EsimSim* sim, EsimStepStats* out /* nullable */);

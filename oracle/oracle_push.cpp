@@ -154,6 +154,9 @@ struct DiseaseModel {  // disease.rs:97-109, covid() :118-129
     double exposure_chance, mask_effectiveness;
     uint16_t exposed_time, infected_time;
     uint32_t max_time_step, vaccination_rate;
+    // ESIM_CFG_CORRECTED ("corrected semantics"): the reference's own TODOs fixed - NOT the reference's
+    // behaviour, a separate opt-in mode with its own parity tests.  See include/esim.h.
+    bool corrected = false;
 
     // disease.rs:131-154
     double get_exposure_chance(bool is_vaccinated, const MaskStatus& global_mask_status,
@@ -191,6 +194,8 @@ static DiseaseStatus disease_execute_time_step(const DiseaseStatus& status, cons
 
 // citizen.rs:47-49
 static double binomial(double probability, uint8_t n) { return 1.0 - std::pow(1.0 - probability, (double)n); }
+// corrected mode: the number of infected sources is not cut to u8; it saturates at 16383 (the size of the kernels' table)
+static double binomial_wide(double probability, size_t n) { return 1.0 - std::pow(1.0 - probability, (double)std::min<size_t>(n, 16383)); }
 
 // ---------------------------------------------------------------------------------------------------------
 // sim/src/models
@@ -246,13 +251,23 @@ struct Citizen {  // citizen.rs:109-135
     }
 
     // citizen.rs:221-248
-    bool expose(size_t exposure_total, const DiseaseModel& disease_model, const MaskStatus& global, double uniform_sample) {
+    // trial_on_bus: the trial happens on a bus (expose_citizens) - only the corrected mode looks at it
+    bool expose(size_t exposure_total, const DiseaseModel& disease_model, const MaskStatus& global, double uniform_sample, bool trial_on_bus) {
         const MaskStatus none{MaskNone, 0};
-        const MaskStatus& mask_status = is_mask_compliant ? none : global;
-        const double exposure_chance = binomial(
-            disease_model.get_exposure_chance(disease_status.kind == Vaccinated, mask_status,
-                                              is_mask_compliant && on_public_transport),
-            (uint8_t)exposure_total);  // `exposure_total as u8` wraps modulo 256 (citizen.rs:239)
+        double exposure_chance;
+        if (disease_model.corrected) {
+            // the compliant citizens are the ones who wear the mask; MaskStatus::PublicTransport protects them on the bus
+            const MaskStatus& mask_status = is_mask_compliant ? global : none;
+            exposure_chance = binomial_wide(
+                disease_model.get_exposure_chance(disease_status.kind == Vaccinated, mask_status, is_mask_compliant && trial_on_bus),
+                exposure_total);
+        } else {
+            const MaskStatus& mask_status = is_mask_compliant ? none : global;
+            exposure_chance = binomial(
+                disease_model.get_exposure_chance(disease_status.kind == Vaccinated, mask_status,
+                                                  is_mask_compliant && on_public_transport),
+                (uint8_t)exposure_total);  // `exposure_total as u8` wraps modulo 256 (citizen.rs:239)
+        }
         if (disease_status.kind == Susceptible && uniform_sample < exposure_chance) {
             disease_status.kind = Exposed; disease_status.time = 0;
             return true;
@@ -520,8 +535,16 @@ struct Oracle {
                     const uint32_t slot = building.id.type == ESIM_BLDG_HOUSEHOLD ? 0u : next_work_slot(citizen_id);
                     const double sample = rng_mode == 0 ? rng.building_trial(citizen_id, current_time_step, slot)
                                                         : thread_rngs[(size_t)omp_get_thread_num()].uniform();
-                    if (citizen.expose(exposure_count, disease_model, mask_status, sample))
+                    if (citizen.expose(exposure_count, disease_model, mask_status, sample, false)) {
                         exposure_statistics[area_index].push_back(building_id);
+                        // corrected mode: the removal the reference aims at a field that is always None (simulator.rs:346-348,
+                        // output_area.rs:113) takes effect; each citizen is visited by one thread only (its current area's)
+                        if (disease_model.corrected && eligible_some && citizens_eligible_for_vaccine[citizen_id]) {
+                            citizens_eligible_for_vaccine[citizen_id] = 0;
+#pragma omp atomic
+                            --eligible_count;
+                        }
+                    }
                 }
             }
         }
@@ -571,7 +594,7 @@ struct Oracle {
             const auto& ref = citizen_output_area_lookup[citizen_id];
             Citizen& citizen = output_areas[ref.first].citizens[ref.second];
             const double sample = rng_mode == 0 ? rng.pt_trial(citizen_id, current_time_step) : seq_rng.uniform();
-            if (citizen.is_susceptible() & citizen.expose(exposure_count, disease_model, interventions.mask_status, sample)) {
+            if (citizen.is_susceptible() & citizen.expose(exposure_count, disease_model, interventions.mask_status, sample, true)) {
                 if (!add_exposure_pt()) error = "Cannot expose citizen as no citizens are susceptible!";
                 if (eligible_some && citizens_eligible_for_vaccine[citizen_id]) {
                     citizens_eligible_for_vaccine[citizen_id] = 0;
@@ -585,7 +608,23 @@ struct Oracle {
     void apply_interventions() {
         const double infected_percent = global_stats.back().infected_percentage();
         const uint32_t new_interventions = interventions.update_status(infected_percent);
-        // Lockdown event: the body is a no-op (simulator.rs:467-479)
+        // Lockdown event: the body is a no-op (simulator.rs:467-479) ...
+        if ((new_interventions & 1) && disease_model.corrected) {
+            // ... corrected mode: "Send every Citizen home" - position, bus and the area the citizen is filed under
+            std::vector<std::vector<Citizen>> kept(output_areas.size());
+            std::vector<std::pair<uint32_t, Citizen>> moving;
+            for (size_t ai = 0; ai < output_areas.size(); ++ai)
+                for (Citizen& citizen : output_areas[ai].citizens) {
+                    citizen.current_building_position = citizen.household_code;
+                    citizen.on_public_transport = false; citizen.pt_direction = ESIM_PT_NONE; citizen.at_workplace = false;
+                    if (citizen.household_code.area != (uint32_t)ai) moving.push_back({citizen.household_code.area, citizen});
+                    else kept[ai].push_back(citizen);
+                }
+            for (size_t ai = 0; ai < output_areas.size(); ++ai) output_areas[ai].citizens.swap(kept[ai]);
+            for (auto& mv : moving) output_areas[mv.first].citizens.push_back(mv.second);
+            for (auto& area : output_areas)
+                for (size_t k = 0; k < area.citizens.size(); ++k) citizen_output_area_lookup[area.citizens[k].id] = {area.index, (uint32_t)k};
+        }
         if (new_interventions & 2) {  // Vaccination event (simulator.rs:481-514)
             citizens_eligible_for_vaccine.assign(n_citizens, 0);
             eligible_count = 0;
@@ -623,6 +662,8 @@ struct Oracle {
                 const auto& ref = citizen_output_area_lookup[citizen_id];
                 Citizen& citizen = output_areas[ref.first].citizens[ref.second];
                 citizen.disease_status.kind = Vaccinated; citizen.disease_status.time = 0;
+                // corrected mode: a vaccinated citizen leaves the set (the reference keeps choosing it again, simulator.rs:482)
+                if (disease_model.corrected) { member[citizen_id] = 0; --eligible_count; }
             }
             vaccinated_now = (uint32_t)chosen.size();
         }
@@ -675,6 +716,7 @@ int oracle_create(const EsimConfig* cfg, const EsimPopulationSoA* pop, Oracle** 
     o->disease_model.infected_time = (uint16_t)cfg->infected_time;
     o->disease_model.max_time_step = cfg->max_time_step;
     o->disease_model.vaccination_rate = cfg->vaccination_rate;
+    o->disease_model.corrected = (cfg->flags & ESIM_CFG_CORRECTED) != 0;
     o->interventions.th_lockdown = cfg->lockdown_threshold;
     o->interventions.th_vaccination = cfg->vaccination_threshold;
     o->interventions.th_mask_pt = cfg->mask_pt_threshold;

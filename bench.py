@@ -1,21 +1,39 @@
 #!/usr/bin/env python
 """Benchmark of the per-timestep agent update loop (Simulator::step) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--areas A] [--cross X]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config NAME] [--areas A] [--cross X]
 
-A "step" is one simulated hour over the whole population.  The N=1 workload is BASELINE.json configs[1]: a 3.5 M-citizen
-synthetic census-shaped population (11 300 output areas, pop_seed 20110327), 5000 hourly time steps from 10 initial
-infections with the reference's constants.  Prints ONE JSON line (see README / DESIGN.md for the keys).
+A "step" is one simulated hour over the whole population.  Workloads (BASELINE.json `configs`, synthetic census-shaped
+populations, pop_seed 20110327, reference constants, 10 initial infections):
 
-  value        citizen-timesteps/s with the population resident in HBM: sum over the K steps of the CUDA-event time of each
-               step (events recorded by the library on its own stream around the kernels, esim_run_timed), L2 flushed
-               before every step.
-  e2e          the same metric through the public API with host buffers: esim_import_population (host -> device) +
-               esim_run(K) + esim_read_stats + esim_read_state (device -> host), wall clock between synchronisations.
-  roofline     dominant kernel (k_expose): algorithmic bytes of its launches / its CUDA-event time, against the measured
-               HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline the CPU oracle (a port of the reference's push loop, OpenMP over output areas) on a bounded number of
-               steps of the same workload on this box's host cores.
+  baseline   configs[1]  11 300 output areas, ~3.45 M citizens, one GPU                      (default at N = 1)
+  uk67       configs[4]  27 500 output areas (~8.4 M citizens) PER GPU, cross-area fraction 0.9 ("dense public-transport
+                         mixing"), weak scaling                                                (default at N > 1)
+  england56  configs[3]  183 300 output areas, ~56 M citizens in total, cross-area fraction 0.6, strong scaling over 2 / 4 / 8 GPUs
+  yh         configs[2]  17 246 output areas, ~5.3 M citizens (Yorkshire & Humber shape), one GPU
+  york       configs[0]  637 output areas, ~197 k citizens
+
+Prints ONE JSON line.  Keys beyond the driver's contract:
+
+  value             citizen-timesteps/s with the population resident in HBM: sum over the K steps of the CUDA-event time of
+                    each step (events recorded by the library on its own stream, esim_run_timed), L2 flushed before every
+                    step; on N > 1 GPUs the shards leave their flushes together (a one-warp barrier kernel in front of the
+                    first event), so a step's interval does not contain the skew of the independent flushes.
+  e2e               the same metric through the public API from PAGEABLE host arrays (what a Rust Vec is):
+                    esim_create + esim_import_population (host -> device) [+ peer set-up] + esim_run(K) + esim_read_stats +
+                    esim_read_state (device -> host), wall clock.  `setup_seconds` / `run_seconds` / `readback_seconds` split
+                    it; `e2e_pinned` is the same with page-locked host arrays.
+  roofline          k_step, the dominant kernel: algorithmic bytes of its launches / its CUDA-event time against the
+                    measured HBM copy bandwidth (MEASURED_PEAKS.json).  N = 1 adds `roofline_8p4M` (the same kernel, same
+                    timing, on the per-GPU population of configs[4]: a working set above the L2) and `roofline_peak_mix`
+                    (imported state S 30 / E 20 / I 40 / R 3 / V 7 %: trials and contended counters in every quad).
+  parity_checked    every rank holds the same statistics for every timed step, the three passes over the workload agree,
+                    and a side population of <= 100 k citizens run through the SAME configuration of ranks and exchange
+                    equals the CPU oracle bit for bit (statistics of every step and the per-citizen state).
+  weak_scaling_reference (N > 1, weak scaling)  the per-GPU workload on ONE GPU without shards, measured in the same run by
+                    rank 0: value(N) / (N x this) is the parallel efficiency on the SAME per-GPU workload.
+  cpu_baseline      the CPU oracle (a port of the reference's push loop, OpenMP over output areas) on a bounded number of
+                    steps of the same workload on this box's host cores (N = 1 only).
 
 `--impl reference` times that CPU port alone, on all host threads (the Rust reference cannot be built in this image).
 """
@@ -40,6 +58,15 @@ UNIT = "citizen-timesteps/s"
 POP_SEED = 20110327
 FALLBACK_HBM_GBS = 6650.0
 
+CONFIGS = {
+    # name: (areas, per_gpu?, cross, areas_per_school, scaling, description)
+    "baseline": (11300, True, 0.0, 67, "weak", "3.5M-citizen synthetic census-shaped population, 5000 hourly steps"),
+    "uk67": (27500, True, 0.9, 67, "weak", "UK-scale weak scaling: 27500 output areas (~8.4M citizens) per GPU, dense public-transport mixing (cross-area fraction 0.9)"),
+    "england56": (183300, False, 0.6, 67, "strong", "England-scale 56M synthetic citizens (183300 output areas), cross-area fraction 0.6, sharded by output area"),
+    "yh": (17246, True, 0.0, 100, "weak", "Yorkshire & Humber shape: 17246 output areas (~5.3M citizens), interventions enabled"),
+    "york": (637, True, 0.0, 25, "weak", "York shape: 637 output areas (~197k citizens), 5000 hourly steps"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -47,25 +74,29 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--areas", type=int, default=0, help="output areas per GPU (0 = the BASELINE workload)")
-    ap.add_argument("--cross", type=float, default=-1.0, help="cross-area workplace fraction x")
+    ap.add_argument("--config", default="", choices=[""] + sorted(CONFIGS), help="BASELINE configuration (default: baseline at N = 1, uk67 at N > 1)")
+    ap.add_argument("--areas", type=int, default=0, help="override: output areas per GPU")
+    ap.add_argument("--cross", type=float, default=-1.0, help="override: cross-area workplace fraction x")
     ap.add_argument("--sim-seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip roofline_8p4M / roofline_peak_mix / weak_scaling_reference")
+    ap.add_argument("--host-popgen", action="store_true", help="generate the population on the host (default: on the GPU, per rank)")
     return ap.parse_args()
 
 
 def workload(args, world):
-    """configs[1] on one GPU.  For N > 1 the same per-GPU workload is replicated N times along the output-area axis
-    (weak scaling: 11 300 areas ~ 3.45 M citizens per GPU), sharded by output area; --areas / --cross select the other
-    BASELINE configurations (e.g. --areas 27500 --cross 0.9 = configs[4], ~8.4 M citizens per GPU with dense mixing)."""
-    per_gpu = args.areas or 11300
-    cross = args.cross if args.cross >= 0 else 0.0
-    if world == 1 and not args.areas and cross == 0.0:
-        name = "3.5M-citizen synthetic census-shaped population, 5000 hourly steps"
-    else:
-        name = "synthetic census-shaped population, %d output areas per GPU x %d GPU(s), cross-area fraction %.2f" % (per_gpu, world, cross)
-    return dict(name=name, n_areas=per_gpu * world, areas_per_school=67, cross_area_fraction=cross)
+    name = args.config or ("baseline" if world == 1 else "uk67")
+    areas, per_gpu, cross, aps, scaling, desc = CONFIGS[name]
+    if args.areas:
+        areas, per_gpu = args.areas, True
+    if args.cross >= 0:
+        cross = args.cross
+    n_areas = areas * world if per_gpu else areas
+    if args.areas or args.cross >= 0:
+        desc = "synthetic census-shaped population, %d output areas%s, cross-area fraction %.2f" % (areas, " per GPU" if per_gpu else "", cross)
+    return dict(config=name, name=desc, n_areas=n_areas, areas_per_gpu=areas if per_gpu else None, areas_per_school=aps,
+                cross_area_fraction=cross, scaling=scaling)
 
 
 class ClockSampler:
@@ -81,7 +112,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -94,6 +125,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)   # at least two sampling periods, however short the timed region was
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -151,7 +183,6 @@ def traffic_from_profile(kernel):
     p = ROOT / "profiles" / "traffic.json"
     try:
         table = json.loads(p.read_text())
-        # the capture names the instantiation that ran (k_step_occ4, k_step_p2p, ...)
         for name in sorted(table, key=len):
             if name == kernel or name.startswith(kernel + "_"):
                 return float(table[name]["dram_bytes_per_launch"])
@@ -160,10 +191,13 @@ def traffic_from_profile(kernel):
     return None
 
 
+def host_threads():
+    return os.cpu_count() or 1
+
+
 def cpu_baseline(pop, cfg_kwargs, seconds, min_steps=8):
     from oracle.oracle_py import Oracle, default_config
-    if int(os.environ.get("OMP_NUM_THREADS", "0") or 0) <= 1:
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
     orc = Oracle(pop, default_config(**cfg_kwargs))
     orc.run(2)  # touch every page once
     t0 = time.perf_counter()
@@ -174,9 +208,9 @@ def cpu_baseline(pop, cfg_kwargs, seconds, min_steps=8):
         if (dt >= seconds and steps >= min_steps) or steps >= 5000:
             break
     orc.close()
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-    return {"value": pop.n_citizens * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "time steps 3..%d of the same population and seed (%.1f s of CPU work)" % (steps + 2, dt)}
+    return {"value": pop.n_citizens * steps / dt, "unit": UNIT, "cores": host_threads(), "host_cpus": host_threads(), "kind": "port",
+            "sample": "time steps 3..%d of the same population and seed (%.1f s of CPU work, %d OpenMP threads = every host CPU)" % (
+                steps + 2, dt, host_threads())}
 
 
 def run_reference(args, wl, rank, world):
@@ -184,7 +218,7 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread it can get
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
     from epidemicsimulator_b200 import synthetic_population
     from oracle.oracle_py import Oracle, default_config
     pop = synthetic_population(wl["n_areas"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"])
@@ -199,18 +233,39 @@ def run_reference(args, wl, rank, world):
         if n == 0 or time.perf_counter() - t0 > budget:
             break
     dt = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    cores = host_threads()
     value = pop.n_citizens * steps / dt
-    sample = "%d of %d time steps after %d warm-up steps (%.1f s), whole population" % (steps, args.steps, max(args.warmup, 1), dt)
+    sample = "%d of %d time steps after %d warm-up steps (%.1f s), whole population, %d OpenMP threads" % (
+        steps, args.steps, max(args.warmup, 1), dt, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / max(steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / max(steps, 1) * 1e3, "higher_is_better": True, "scaling": wl["scaling"],
         "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "citizens": pop.n_citizens, "output_areas": pop.n_areas, "pop_seed": POP_SEED,
-                   "cross_area_fraction": wl["cross_area_fraction"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wl["name"], "baseline_config": wl["config"], "citizens": pop.n_citizens, "output_areas": pop.n_areas,
+                   "pop_seed": POP_SEED, "cross_area_fraction": wl["cross_area_fraction"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "host_cpus": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def peak_mix(pop, seed=5):
+    """A copy of `pop` in the state mix of an epidemic's peak (S 30 / E 20 / I 40 / R 3 / V 7 %, timers uniform)."""
+    from epidemicsimulator_b200 import _abi
+    out = pop.copy()
+    rng = np.random.default_rng(seed)
+    u = rng.random(out.n_citizens)
+    status = np.full(out.n_citizens, _abi.STATUS_SUSCEPTIBLE, np.uint8)
+    status[u >= 0.30] = _abi.STATUS_EXPOSED
+    status[u >= 0.50] = _abi.STATUS_INFECTED
+    status[u >= 0.90] = _abi.STATUS_RECOVERED
+    status[u >= 0.93] = _abi.STATUS_VACCINATED
+    timer = np.zeros(out.n_citizens, np.uint16)
+    e, i = status == _abi.STATUS_EXPOSED, status == _abi.STATUS_INFECTED
+    timer[e] = rng.integers(0, 97, int(e.sum()))
+    timer[i] = rng.integers(0, 337, int(i.sum()))
+    out.status[:] = status
+    out.timer[:] = timer
+    return out
 
 
 def main():
@@ -231,7 +286,7 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
-    from epidemicsimulator_b200 import _abi, build, synthetic_population, shard_population
+    from epidemicsimulator_b200 import _abi, synthetic_population, shard_population
     from epidemicsimulator_b200.simulator import Simulator, default_config, pin_population
 
     if not torch.cuda.is_available():
@@ -245,24 +300,64 @@ def main():
         if world > 1:
             dist.barrier()
 
-    whole = synthetic_population(wl["n_areas"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"])
-    pop = whole if world == 1 else shard_population(whole, rank, world)
-    pop = pin_population(pop)   # page-locked host arrays: the host -> device copies of the import run at link speed
-    n_total = whole.n_citizens
+    f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
+
+    # ---- the population: this rank's shard as pageable host arrays ------------------------------------------------
+    t_pop = time.perf_counter()
+    from epidemicsimulator_b200 import population as _population
+    if args.host_popgen or not hasattr(_population, "device_population"):
+        whole = synthetic_population(wl["n_areas"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"])
+        pop = whole if world == 1 else shard_population(whole, rank, world)
+        n_total, n_areas_total = whole.n_citizens, whole.n_areas
+        popgen = "host (libesim_host.so), whole population on every rank, then esim_shard_create"
+    else:
+        from epidemicsimulator_b200.population import device_population
+        pop = device_population(wl["n_areas"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"], rank=rank, world=world,
+                                device=local_rank)
+        whole = pop if world == 1 else None
+        n_total, n_areas_total = pop.n_global_citizens or pop.n_citizens, pop.n_areas
+        popgen = "device (esim_popgen_device): every rank generates the population on its GPU and keeps its shard"
+    popgen_seconds = time.perf_counter() - t_pop
+    pinned = pin_population(pop)   # page-locked copy: the device-resident passes and `e2e_pinned`
     cfg_kwargs = dict(seed=args.sim_seed, device=local_rank, max_time_step=max(5000, args.steps + args.warmup))
 
-    def make_sim(flags=0):
-        sim = Simulator.from_population(pop, default_config(flags=flags, **cfg_kwargs))
-        if world > 1:
+    def make_sim(p, flags=0, **over):
+        kw = dict(cfg_kwargs)
+        kw.update(over)
+        sim = Simulator.from_population(p, default_config(flags=flags, **kw))
+        if world > 1 and p.n_shards > 1:
             if os.environ.get("ESIM_COMM", "p2p") == "nccl":
                 sim.attach_comm(dist)      # NCCL all-reduces inside the captured graphs
             else:
                 sim.connect_peers(dist)    # in-kernel exchange over NVLink peer mappings
         return sim
 
+    def kernel_pass(p, steps, flags=0, **over):
+        """`steps` steps with an event between every two kernels; returns (timings, statistics, cells)."""
+        sim = make_sim(p, _abi.CFG_FLUSH_L2 | _abi.CFG_TIME_KERNELS | flags, **over)
+        barrier()
+        done = 0
+        for _ in range(steps):
+            alive = sim.step(timed=True)
+            done += 1
+            if not alive:
+                break
+        barrier()
+        tm, st = sim.timings(), sim.statistics()
+        sim.close()
+        return tm, st, done
+
+    def roofline_of(tm, st, p, steps_run, peak, peak_src, share=1.0, traffic=None):
+        _, _, fused_b = algorithmic_bytes(st[:steps_run], p.n_citizens, p.n_buildings + p.n_rooms, share)
+        dom_bytes, dom_s = float(fused_b.sum()), tm["k_expose"]
+        achieved = dom_bytes / dom_s / 1e9 if dom_s > 0 else 0.0
+        return {"bound": "hbm", "kernel": "k_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes / max(steps_run, 1),
+                "avg_launch_us": dom_s / max(steps_run, 1) * 1e6, "citizens": p.n_citizens, "launches": steps_run}
+
     # ---- warm-up on a throw-away handle (module load, graph capture, clocks) --------------------------------------
     w = max(args.warmup, 3)
-    sim = make_sim(_abi.CFG_FLUSH_L2)
+    sim = make_sim(pinned, _abi.CFG_FLUSH_L2)
     for _ in range(w):
         sim.step(timed=True)
     sim.run_timed(w)
@@ -273,7 +368,7 @@ def main():
     clocks.start()
 
     # ---- device-resident number: CUDA events around every step, cold L2 -------------------------------------------
-    sim = make_sim(_abi.CFG_FLUSH_L2)
+    sim = make_sim(pinned, _abi.CFG_FLUSH_L2)
     fused = sim.fused
     barrier()
     steps_run = sim.run_timed(args.steps)   # CUDA events around every step; step k + 1 is queued before step k is read back
@@ -284,95 +379,185 @@ def main():
     sim.close()
 
     # ---- the same steps again with an event between every two kernels: per-kernel durations for the roofline --------
-    sim = make_sim(_abi.CFG_FLUSH_L2 | _abi.CFG_TIME_KERNELS)
-    barrier()
-    for _ in range(steps_run):
-        if not sim.step(timed=True):
-            break
-    barrier()
-    tm = sim.timings()
-    sim.close()
+    tm, stats_k, _ = kernel_pass(pinned, steps_run)
 
     # ---- back-to-back graph replay (warm L2, the way the job really runs) -----------------------------------------
-    sim = make_sim()
+    sim = make_sim(pinned)
     barrier()
     t0 = time.perf_counter()
     n_graph = sim.run(args.steps)
     barrier()
     graph_seconds = time.perf_counter() - t0
-    sim.close()
-
-    # ---- end to end through the public API with host buffers ------------------------------------------------------
-    state_out = Simulator.state_buffers(pop.n_citizens, pinned=True)   # caller-owned page-locked result buffers
-    barrier()
-    t0 = time.perf_counter()
-    sim = make_sim()
-    n_e2e = sim.run(args.steps)
-    st_e2e = sim.statistics()
-    state = sim.state(out=state_out)
-    barrier()
-    e2e_seconds = time.perf_counter() - t0
-    h2d = pop.input_bytes()
-    d2h = st_e2e.shape[0] * 64 + sum(a.nbytes for a in state.values())
+    stats_g = sim.statistics()
     sim.close()
     clock_info = clocks.stop()
 
+    # ---- end to end through the public API with host buffers: pageable (the headline), then page-locked --------------
+    def e2e_pass(p, pinned_out):
+        state_out = Simulator.state_buffers(p.n_citizens, pinned=pinned_out)
+        barrier()
+        t0 = time.perf_counter()
+        sim = make_sim(p)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        n = sim.run(args.steps)
+        t2 = time.perf_counter()
+        st = sim.statistics()
+        state = sim.state(out=state_out)
+        barrier()
+        t3 = time.perf_counter()
+        d2h = st.shape[0] * 64 + sum(a.nbytes for a in state.values())
+        sim.close()
+        return dict(seconds=t3 - t0, setup_seconds=t1 - t0, run_seconds=t2 - t1, readback_seconds=t3 - t2, steps=n, d2h=d2h, stats=st)
+
+    e2e = e2e_pass(pop, False)
+    e2e_pin = e2e_pass(pinned, True)
+    h2d = pop.input_bytes()
+
+    # ---- parity: the passes agree with each other, the ranks agree with each other, a side population equals the oracle ----
+    parity = {"passes_agree": bool(np.array_equal(stats, stats_k[:steps_run]) and np.array_equal(stats, stats_g[:steps_run])
+                                   and np.array_equal(stats, e2e["stats"][:steps_run]))}
     if world > 1:
-        t = torch.tensor([dev_seconds, graph_seconds, e2e_seconds], dtype=torch.float64, device="cuda")
+        mine = torch.from_numpy(np.ascontiguousarray(stats)).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([1 if torch.equal(mine, ref) else 0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        parity["ranks_hold_identical_statistics"] = bool(same.item())
+    side = synthetic_population(300, POP_SEED + 1, 10, wl["cross_area_fraction"])
+    side_cfg = dict(exposure_chance=0.02, vaccination_rate=120, seed=99)
+    side_steps = 360
+    side_shard = side if world == 1 else shard_population(side, rank, world)
+    sim = make_sim(side_shard, **side_cfg)
+    for _ in range(3):
+        sim.step()
+    n_side = 3 + sim.run(side_steps - 3)
+    side_stats, side_state = sim.statistics(), sim.state()
+    sim.close()
+    side_ok = True
+    if rank == 0:
+        from oracle.oracle_py import Oracle, default_config as ocfg
+        os.environ["OMP_NUM_THREADS"] = str(host_threads())
+        orc = Oracle(side, ocfg(**side_cfg))
+        m_side = orc.run(side_steps)
+        ost, ostate = orc.stats(), orc.state()
+        orc.close()
+        side_ok = n_side == m_side and bool(np.array_equal(side_stats, ost))
+        ids = side_shard.global_id if side_shard.global_id is not None else np.arange(side.n_citizens)
+        for k in ("status", "timer", "on_pt", "vax_eligible"):
+            side_ok = side_ok and bool(np.array_equal(side_state[k], ostate[k][ids]))
+        parity["side_population"] = {"citizens": side.n_citizens, "steps": n_side, "ranks": world, "equals_oracle": side_ok,
+                                     "vaccinated": int(ost[-1, f["vaccinated"]]), "exposures_pt": int(ost[:, f["exposures_pt"]].sum()),
+                                     "shared_cells": int(side_shard.n_shared_bldgs + side_shard.n_shared_rooms)}
+    parity_ok = all(v if isinstance(v, bool) else v.get("equals_oracle", True) for v in parity.values())
+
+    # ---- extra legs (rank 0's GPU, single shard): other sizes and state mixes of the same kernel, same timing -----
+    extra = {}
+    peak, peak_src = hbm_peak()
+    if not args.no_extra_legs and rank == 0:
+        leg_steps = min(steps_run, 240)
+        if world == 1:
+            big = synthetic_population(27500, POP_SEED, 67, 0.9)
+            big_p = pin_population(big)
+            tmb, stb, nb = kernel_pass(big_p, leg_steps)
+            extra["roofline_8p4M"] = roofline_of(tmb, stb, big, nb, peak, peak_src)
+            extra["roofline_8p4M"]["workload"] = "the per-GPU population of BASELINE configs[4] (27500 output areas, cross-area fraction 0.9), time steps 1..%d" % nb
+            del big_p
+            mix = pin_population(peak_mix(whole))
+            tmm, stm, nm = kernel_pass(mix, leg_steps)
+            extra["roofline_peak_mix"] = roofline_of(tmm, stm, mix, nm, peak, peak_src)
+            extra["roofline_peak_mix"]["workload"] = "the N=1 population imported at S30/E20/I40/R3/V7 %% (an epidemic's peak), time steps 1..%d" % nm
+            extra["roofline_peak_mix"]["k_step_us_all_susceptible"] = tm["k_expose"] / max(steps_run, 1) * 1e6
+        elif wl["scaling"] == "weak" and wl["areas_per_gpu"]:
+            one = pin_population(synthetic_population(wl["areas_per_gpu"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"]))
+            s1 = Simulator.from_population(one, default_config(flags=_abi.CFG_FLUSH_L2, **cfg_kwargs))
+            s1.run_timed(w)
+            s1.close()
+            s1 = Simulator.from_population(one, default_config(flags=_abi.CFG_FLUSH_L2, **cfg_kwargs))
+            n1 = s1.run_timed(steps_run)
+            t1 = s1.timings()["total"]
+            s1.close()
+            s1 = Simulator.from_population(one, default_config(**cfg_kwargs))
+            tg0 = time.perf_counter()
+            ng1 = s1.run(args.steps)
+            torch.cuda.synchronize()
+            tg1 = time.perf_counter() - tg0
+            s1.close()
+            extra["weak_scaling_reference"] = {
+                "what": "the per-GPU workload on ONE GPU without shards (rank 0's GPU, same run, same timing, the other ranks idle)",
+                "citizens": one.n_citizens, "value": one.n_citizens * n1 / t1, "ms_per_step": t1 / max(n1, 1) * 1e3,
+                "value_graph_replay": one.n_citizens * ng1 / tg1, "graph_replay_ms_per_step": tg1 / max(ng1, 1) * 1e3}
+    if world > 1:
+        dist.barrier()
+
+    if world > 1:
+        t = torch.tensor([dev_seconds, graph_seconds, e2e["seconds"], e2e_pin["seconds"], e2e["setup_seconds"], e2e["run_seconds"],
+                          popgen_seconds, 0.0 if parity_ok else 1.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_seconds, graph_seconds, e2e_seconds = [float(x) for x in t.tolist()]
+        dev_seconds, graph_seconds, e2e["seconds"], e2e_pin["seconds"], e2e["setup_seconds"], e2e["run_seconds"], popgen_seconds, bad = [
+            float(x) for x in t.tolist()]
+        parity_ok = bad == 0.0
 
     if rank == 0:
-        peak, peak_src = hbm_peak()
-        upd_b, exp_b, fused_b = algorithmic_bytes(stats, pop.n_citizens, n_cells, pop.n_citizens / n_total)
-        f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
+        share = pop.n_citizens / n_total
         pt_steps = int((stats[:, f["pt_mode"]] != 0).sum())
         if fused:
             # the slot in front of k_step is empty in the fused pipeline: its duration is what one CUDA event costs
             kernel_seconds = {"k_step": tm["k_expose"], "k_pt": tm["k_pt"], "k_tail_fused": tm["k_tail"], "empty_event_interval": tm["k_update"]}
-            dominant, dom_bytes, dom_s = "k_step", float(fused_b.sum()), tm["k_expose"]
             launches = 2 * steps_run + pt_steps
+            roof = roofline_of(tm, stats, pop, steps_run, peak, peak_src, share,
+                               traffic_from_profile("k_step") if wl["config"] == "baseline" and not args.areas else None)
         else:
             kernel_seconds = {k: tm[k] for k in ("k_update", "k_expose", "k_pt", "k_tail")}
-            k_exp_s, k_upd_s = tm["k_expose"], tm["k_update"]
-            dominant = "k_expose" if k_exp_s >= k_upd_s else "k_update"
+            upd_b, exp_b, _ = algorithmic_bytes(stats, pop.n_citizens, n_cells, share)
+            dominant = "k_expose" if tm["k_expose"] >= tm["k_update"] else "k_update"
             dom_bytes = float(exp_b.sum() if dominant == "k_expose" else upd_b.sum())
-            dom_s = k_exp_s if dominant == "k_expose" else k_upd_s
+            dom_s = tm[dominant]
+            roof = {"bound": "hbm", "kernel": dominant, "achieved": dom_bytes / dom_s / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": dom_bytes / dom_s / 1e9 / peak, "traffic": None, "peak_source": peak_src}
             launches = 3 * steps_run + pt_steps
-        achieved = dom_bytes / dom_s / 1e9 if dom_s > 0 else 0.0
         out = {
             "metric": METRIC, "value": n_total * steps_run / dev_seconds, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_seconds / max(steps_run, 1) * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (integer trial thresholds from f64)",
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "u32 (integer trial thresholds from f64)",
             "data": "synthetic",
-            "config": {"workload": wl["name"], "citizens": n_total, "citizens_per_gpu": pop.n_citizens,
-                       "output_areas": whole.n_areas, "pop_seed": POP_SEED, "sim_seed": args.sim_seed,
+            "config": {"workload": wl["name"], "baseline_config": wl["config"], "citizens": n_total, "citizens_per_gpu": pop.n_citizens,
+                       "output_areas": n_areas_total, "pop_seed": POP_SEED, "sim_seed": args.sim_seed,
                        "cross_area_fraction": wl["cross_area_fraction"], "steps_executed": steps_run,
-                       "l2": "flushed before every timed step (256 MiB memset); working set %.0f MB" % (
+                       "shared_cells": int(pop.n_shared_bldgs + pop.n_shared_rooms),
+                       "l2": "flushed before every timed step (256 MiB memset + read sweep); working set %.0f MB" % (
                            (pop.n_citizens * 16 + n_cells * 4) / 1e6),
-                       "parallelism": "output-area shards x%d" % world},
+                       "parallelism": "output-area shards x%d, one process per GPU, %s" % (
+                           world, "in-kernel peer-to-peer exchange over NVLink" if os.environ.get("ESIM_COMM", "p2p") != "nccl" else "NCCL all-reduces")
+                       if world > 1 else "one GPU",
+                       "population_generator": popgen, "population_seconds": popgen_seconds},
             "value_graph_replay": n_total * n_graph / graph_seconds,
             "graph_replay_ms_per_step": graph_seconds / max(n_graph, 1) * 1e3,
-            "e2e": {"value": n_total * n_e2e / e2e_seconds, "unit": UNIT, "h2d_bytes_per_step": h2d / max(n_e2e, 1),
-                    "d2h_bytes_per_step": d2h / max(n_e2e, 1), "seconds": e2e_seconds,
-                    "what": "esim_create + esim_import_population(host SoA) + esim_run(%d) + esim_read_stats + esim_read_state" % args.steps},
+            "e2e": {"value": n_total * e2e["steps"] / e2e["seconds"], "unit": UNIT, "h2d_bytes_per_step": h2d / max(e2e["steps"], 1),
+                    "d2h_bytes_per_step": e2e["d2h"] / max(e2e["steps"], 1), "seconds": e2e["seconds"],
+                    "setup_seconds": e2e["setup_seconds"], "run_seconds": e2e["run_seconds"], "readback_seconds": e2e["readback_seconds"],
+                    "host_memory": "pageable",
+                    "what": "esim_create + esim_import_population(pageable host SoA)%s + esim_run(%d) + esim_read_stats + esim_read_state" % (
+                        " + peer set-up (IPC handles, boot pass, graph capture)" if world > 1 else "", args.steps)},
+            "e2e_pinned": {"value": n_total * e2e_pin["steps"] / e2e_pin["seconds"], "unit": UNIT, "seconds": e2e_pin["seconds"],
+                           "setup_seconds": e2e_pin["setup_seconds"], "run_seconds": e2e_pin["run_seconds"], "host_memory": "page-locked"},
             "gpu_launches": launches,
             "kernel_seconds": kernel_seconds,
             "kernel_seconds_note": "second pass over the same steps with a CUDA event between every two kernels (each event "
                                    "adds ~2.5 us and ends the programmatic overlap of consecutive kernels)",
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # the committed ncu capture is of the BASELINE per-GPU workload: no figure for other sizes
-                         "traffic": traffic_from_profile(dominant) if not args.areas else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": dom_bytes / max(steps_run, 1),
-                         "avg_launch_us": dom_s / max(steps_run, 1) * 1e6},
+            "roofline": roof,
+            "parity_checked": parity_ok,
+            "parity": parity,
             "clocks": clock_info,
         }
-        if not args.no_cpu_baseline and world == 1:
+        out.update(extra)
+        if not args.no_cpu_baseline and world == 1 and whole is not None:
             out["cpu_baseline"] = cpu_baseline(whole, dict(seed=args.sim_seed), args.cpu_seconds)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit("bench.py: PARITY CHECK FAILED (see the `parity` object of the JSON line)")
 
 
 if __name__ == "__main__":

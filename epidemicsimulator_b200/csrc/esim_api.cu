@@ -660,7 +660,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         // whether they run fused (esim_peer_connect) or not (esim_comm_init, esim_shard_step_*)
         s->cnt_stride = ((size_t)B + R + 4 + 31) & ~(size_t)31;
         s->cnt_all.alloc(3 * s->cnt_stride, sharded_pop);
-        s->fused = p->n_shards <= 1 && !(s->cfg.flags & ESIM_CFG_UNFUSED);
+        s->fused = p->n_shards <= 1 && !(s->cfg.flags & ESIM_CFG_UNFUSED) && !getenv("ESIM_UNFUSED");   // (the env switch: the GPU parity suite runs every test on both pipelines)
         if (sharded_pop) { s->peer_mail.alloc(MAIL_WORDS, true); CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st)); }
         s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
         s->pt_buscnt.alloc(std::max<uint32_t>(n_riders, 1));
@@ -1036,10 +1036,13 @@ int esim_read_state(EsimSim* s, EsimStateView* view) {
             CK(cudaMemcpyAsync(&last, s->stats.p + (s->steps_done - 1), sizeof(last), cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
             a.at_work = last.at_work; a.pt_mode = last.pt_mode;
+            // corrected mode: the Lockdown event of the last step (Some(0)) has already sent everybody home
+            if ((s->cfg.flags & ESIM_CFG_CORRECTED) && last.lockdown_hours == 0u) { a.at_work = 0; a.pt_mode = ESIM_PT_NONE; }
         }
         // fused pipeline: the state machine is one step ahead; the eligible set exists once the tail has taken the snapshot
         a.vax_some = c.vax_some && !(s->fused && c.vax_event); a.vax_start_step = c.vax_start_step; a.vax_all_pending = c.vax_all_pending;
         a.exposed_time = s->cfg.exposed_time; a.infected_time = s->cfg.infected_time;
+        a.corrected = (s->cfg.flags & ESIM_CFG_CORRECTED) ? 1u : 0u;
         a.cstate = s->cstate.p; a.home_cell = s->home_cell.p; a.work_cell = s->work_cell.p; a.room_parent = s->room_parent.p;
         const size_t n = s->v.n;
         DevBuf<uint8_t> d_status, d_on_pt, d_elig;

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) k_export_state(ExportArgs a) {
     const uint32_t e = w & CS_EXPOSURE;
     bool elig = false;
     if (a.vax_some) elig = e == 0 || ((int)e - (int)EXPOSURE_BIAS > (int)a.vax_start_step && !(w & CS_VIA_PT));
-    if (a.vax_all_pending && elig) w |= CS_VACCINATED;
+    if (a.vax_some && a.corrected) elig = (w & CS_LOW16) == 0u;   // corrected mode: the set is the citizens still Susceptible
+    if (a.vax_all_pending && elig) { w |= CS_VACCINATED; if (a.corrected) elig = false; }
     uint32_t st, tm = 0;
     if (w & CS_VACCINATED) st = ESIM_STATUS_VACCINATED;
     else if (e == 0) st = ESIM_STATUS_SUSCEPTIBLE;

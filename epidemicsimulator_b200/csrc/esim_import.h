@@ -24,7 +24,7 @@ struct ImportOut {
 };
 
 struct ExportArgs {
-    uint32_t n, n_bldg, t_last, at_work, pt_mode, vax_some, vax_start_step, vax_all_pending, exposed_time, infected_time;
+    uint32_t n, n_bldg, t_last, at_work, pt_mode, vax_some, vax_start_step, vax_all_pending, exposed_time, infected_time, corrected;
     const uint32_t *cstate, *home_cell, *work_cell, *room_parent;
     uint8_t* status; uint16_t* timer; uint32_t* current_bldg; uint8_t* on_pt; uint8_t* vax_eligible;   // device, nullable
 };

@@ -93,11 +93,19 @@ class DiseaseModel:
 
 
 class Simulator:
-    def __init__(self, cfg: Optional[_abi.EsimConfig] = None, **overrides):
+    def __init__(self, cfg: Optional[_abi.EsimConfig] = None, devices=None, **overrides):
+        """devices: a list of CUDA ordinals makes this ONE handle that drives several GPUs from this thread
+        (esim_create_multi): the population is sharded by output area inside the library and every method returns
+        whole-population results.  None = a single-GPU handle on cfg.device."""
         self._lib = cuda_lib()
         self.cfg = cfg if cfg is not None else default_config(**overrides)
         self._h = C.c_void_p()
-        rc = self._lib.esim_create(C.byref(self.cfg), C.byref(self._h))
+        self.devices = list(devices) if devices is not None else None
+        if self.devices is not None:
+            arr = (C.c_int32 * len(self.devices))(*self.devices)
+            rc = self._lib.esim_create_multi(C.byref(self.cfg), len(self.devices), arr, C.byref(self._h))
+        else:
+            rc = self._lib.esim_create(C.byref(self.cfg), C.byref(self._h))
         if rc < 0:
             raise _abi.SimError(rc, (self._lib.esim_last_error(None) or b"").decode())
         self.pop: Optional[Population] = None
@@ -105,8 +113,8 @@ class Simulator:
 
     # -- construction ---------------------------------------------------------------------------------
     @classmethod
-    def from_population(cls, pop: Population, cfg: Optional[_abi.EsimConfig] = None, **overrides) -> "Simulator":
-        sim = cls(cfg, **overrides)
+    def from_population(cls, pop: Population, cfg: Optional[_abi.EsimConfig] = None, devices=None, **overrides) -> "Simulator":
+        sim = cls(cfg, devices=devices, **overrides)
         sim.import_population(pop)
         return sim
 

@@ -675,17 +675,10 @@ struct Oracle {
         exposures_building_now = exposures_pt_now = 0;
         GeneratedExposures exposures = generate_exposures();
         apply_exposures(exposures);
-        apply_interventions();
         EsimStepStats s;
         std::memset(&s, 0, sizeof(s));
-        const StatisticEntry& e = global_stats.back();
-        s.time_step = e.time_step; s.susceptible = e.susceptible; s.exposed = e.exposed; s.infected = e.infected;
-        s.recovered = e.recovered; s.vaccinated = e.vaccinated;
-        s.exposures_building = exposures_building_now; s.exposures_pt = exposures_pt_now;
-        s.lockdown_hours = interventions.lockdown_some ? interventions.lockdown : ESIM_NONE_U32;
-        s.vaccination_hours = interventions.vaccination_some ? interventions.vaccination : ESIM_NONE_U32;
-        s.mask_status = interventions.mask_status.kind; s.mask_hours = interventions.mask_status.hours;
-        // everyone shares the schedule (citizen.rs:154-155): report it from the first citizen / first PT user
+        // everyone shares the schedule (citizen.rs:154-155): report where people were DURING this step from the first citizen /
+        // first public-transport user (before apply_interventions: the corrected mode's Lockdown event sends them home)
         s.at_work = 0; s.pt_mode = ESIM_PT_NONE;
         {
             bool have_any = false, have_pt = false;
@@ -698,6 +691,14 @@ struct Oracle {
                 if (have_any && have_pt) break;
             }
         }
+        apply_interventions();
+        const StatisticEntry& e = global_stats.back();
+        s.time_step = e.time_step; s.susceptible = e.susceptible; s.exposed = e.exposed; s.infected = e.infected;
+        s.recovered = e.recovered; s.vaccinated = e.vaccinated;
+        s.exposures_building = exposures_building_now; s.exposures_pt = exposures_pt_now;
+        s.lockdown_hours = interventions.lockdown_some ? interventions.lockdown : ESIM_NONE_U32;
+        s.vaccination_hours = interventions.vaccination_some ? interventions.vaccination : ESIM_NONE_U32;
+        s.mask_status = interventions.mask_status.kind; s.mask_hours = interventions.mask_status.hours;
         s.vaccine_eligible = eligible_some ? eligible_count : 0;
         s.vaccinated_now = vaccinated_now;
         step_stats.push_back(s);

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True, params=["fused", "unfused"])
 def pipeline(request, monkeypatch):
     """Every test runs on both single-shard pipelines: the fused one-pass step (k_step + k_tail_fused, the default) and the
-    three-kernel step (k_update, k_expose, k_tail) that the sharded and persistent paths are built from."""
+    three-kernel step (k_update, k_expose, k_tail) that the NCCL shards and the phase-level ABI are built from."""
     if request.param == "unfused":
         monkeypatch.setenv("ESIM_UNFUSED", "1")
     else:
@@ -321,16 +321,3 @@ def test_device_resident_run_across_lockdown_changes(onset):
     assert (so[:, 8] != _abi.NONE_U32).any() and (so[-1, 8] == _abi.NONE_U32)   # a lockdown started and ended
     _compare_state(sim, orc, n)
     sim.close(); orc.close()
-
-
-def test_persistent_cooperative_kernel_matches_graph_replay():
-    # ESIM_CFG_PERSISTENT: the whole step loop in one cooperative launch with grid barriers between the phases
-    pop = synthetic_population(n_areas=300, areas_per_school=25, cross_area_fraction=0.2)
-    cfg = dict(exposure_chance=0.004, vaccination_rate=300, seed=77)
-    a = _sim(pop, flags=_abi.CFG_PERSISTENT, **cfg)
-    b = _sim(pop, **cfg)
-    orc = Oracle(pop, default_config(**cfg))
-    assert a.run(900) == b.run(900) == orc.run(900)
-    assert np.array_equal(a.statistics(), orc.stats()) and np.array_equal(b.statistics(), orc.stats())
-    _compare_state(a, orc, 900)
-    a.close(); b.close(); orc.close()

@@ -80,19 +80,3 @@ def test_sharded_handle_refuses_to_step_without_exchange():
         sim.step()
     assert e.value.code == _abi.ERR_COMM
     sim.close()
-
-
-def test_nccl_ranks_match_the_oracle():
-    """Two ranks, two GPUs, NCCL inside the captured graphs (skipped on a single-GPU box)."""
-    import subprocess
-    import sys
-    from pathlib import Path
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    root = Path(__file__).resolve().parent.parent
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", str(root / "scripts" / "sharded_check.py")]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
-    assert "OK" in proc.stdout

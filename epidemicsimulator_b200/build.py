@@ -82,6 +82,18 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     return CUDA_LIB
 
 
+def build_variant(name: str, defines) -> Path:
+    """A/B builds of the CUDA library with other compile-time switches (scripts/kstep_ab.py selects one with ESIM_B200_LIB)."""
+    out = PKG / ("libesim_b200_%s.so" % name)
+    build_host()
+    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+           "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-ccbin", host_compiler(),
+           "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(out)] + ["-D" + d for d in defines]
+    cmd += [str(CSRC / s) for s in CUDA_SOURCES] + ["-lcudart", "-ldl", "-L", str(PKG), "-lesim_host", "-Xlinker", "-rpath=$ORIGIN"]
+    _run(cmd)
+    return out
+
+
 DRIVER = ROOT / "drivers" / "esim_run"
 
 

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_import(ImportRaw r, ImportOut o, uint32
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= o.n_pad) return;
     if (i >= r.n) {
-        o.cstate[i] = CS_PADDING; o.home_cell[i] = 0; o.work_cell[i] = 0; o.gid[i] = 0; o.is_rider[i] = 0; o.route_key[i] = 0;
+        o.cstate[i] = CS_PADDING; o.home_cell[i] = 0; o.work_cell[i] = 0; o.is_rider[i] = 0; o.route_key[i] = 0;
         return;
     }
     const uint32_t h = r.home[i], w = r.work[i], m = r.room[i];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k_import(ImportRaw r, ImportOut o, uint32
         wcell = school ? r.n_bldg + m : w;
         if (f & ESIM_FLAG_USES_PT) { is_rider = 1; key = ((unsigned long long)ah << 32) | aw; }
     }
-    o.cstate[i] = word; o.home_cell[i] = h; o.work_cell[i] = wcell; o.gid[i] = r.shard_lo + i;
+    o.cstate[i] = word; o.home_cell[i] = h; o.work_cell[i] = wcell;
     o.is_rider[i] = is_rider;
     o.route_key[i] = key;
 }

@@ -138,7 +138,6 @@ struct DevView {
     uint32_t* cstate;      // [n_pad]
     const uint32_t* home_cell;   // [n_pad] building id
     const uint32_t* work_cell;   // [n_pad] building id, or n_bldg + room id for school members
-    const uint32_t* global_id;   // [n_pad]
     const uint32_t* room_parent; // [n_rooms] school building of a room
     uint32_t* cnt[3];      // [n_cells] x 2 (x 3 fused): infected occupants present per building / room.  Step t accumulates into
                            // cnt[t & 1] while k_update zeroes cnt[(t + 1) & 1] for the next step.  Fused pipeline: k_step of

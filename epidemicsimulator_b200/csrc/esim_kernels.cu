@@ -139,30 +139,36 @@ __device__ __forceinline__ bool push_to_peers(const DevView& v, uint32_t slot, u
     }
     return false;
 }
-// An infected citizen present in `cell` adds itself to the count buffer of the step being counted - and, inside a school,
-// to the school's total (building.rs:494-522: n = infected in the whole school).  Warp-aggregated: the lanes that get here
-// together and hold the same cell elect one lane that adds the size of the group (citizens are stored in household / area
-// order, so lanes collide all the time: the members of a household at night, the staff of a workplace, and above all the
-// pupils of a school - a few hundred counters for a fifth of the population).  Returns true if it wrote to a peer.
+// `k` infected citizens present in `cell` add themselves to the count buffer of the step being counted - and, inside a school,
+// to the school's total (building.rs:494-522: n = infected in the whole school).  The caller has already merged the members of
+// a quad that stand in the same cell (citizens are stored in household order).  The school totals are a few hundred counters
+// for a fifth of the population: there the lanes of a warp that get here together and name the same school elect one lane
+// that adds for the group.  (The same aggregation for EVERY cell was measured slower at an epidemic's peak, 54.5 us against
+// 48.5 us per k_step launch: lanes rarely share a household, and the match costs more than the reduction it saves.)
+// Returns true if it wrote to a peer.
 #ifndef ESIM_WARP_AGGREGATE
 #define ESIM_WARP_AGGREGATE 1
 #endif
 template <bool P2P>
-__device__ __forceinline__ bool add_present(const DevView& v, uint32_t* __restrict__ cnt, uint32_t slot, uint32_t cell) {
-#if ESIM_WARP_AGGREGATE
-    const unsigned same = __match_any_sync(__activemask(), cell);
-    if ((same & ((1u << lane_id()) - 1u)) != 0u) return false;   // a lower lane adds for this group
-    const uint32_t k = (uint32_t)__popc(same);
-#else
-    const uint32_t k = 1u;
-#endif
+__device__ __forceinline__ bool count_present(const DevView& v, uint32_t* __restrict__ cnt, uint32_t slot, uint32_t cell, uint32_t k = 1u) {
     atomicAdd(&cnt[cell], k);
-    return P2P ? push_to_peers(v, slot, cell, k) : false;
-}
-template <bool P2P>
-__device__ __forceinline__ bool count_present(const DevView& v, uint32_t* __restrict__ cnt, uint32_t slot, uint32_t cell) {
-    bool pushed = add_present<P2P>(v, cnt, slot, cell);
-    if (cell >= v.n_bldg) pushed |= add_present<P2P>(v, cnt, slot, __ldg(&v.room_parent[cell - v.n_bldg]));
+    bool pushed = P2P ? push_to_peers(v, slot, cell, k) : false;
+    if (cell >= v.n_bldg) {
+        const uint32_t school = __ldg(&v.room_parent[cell - v.n_bldg]);
+#if ESIM_WARP_AGGREGATE
+        const unsigned act = __activemask();
+        const unsigned same = __match_any_sync(act, school);
+        uint32_t total = 0;
+        for (unsigned m = same; m; m &= m - 1u) total += __shfl_sync(same, k, __ffs((int)m) - 1);   // the group's lanes all walk the same mask
+        if ((same & ((1u << lane_id()) - 1u)) == 0u) {   // lowest lane of the group
+            atomicAdd(&cnt[school], total);
+            if (P2P) pushed |= push_to_peers(v, slot, school, total);
+        }
+#else
+        atomicAdd(&cnt[school], k);
+        if (P2P) pushed |= push_to_peers(v, slot, school, k);
+#endif
+    }
     return pushed;
 }
 // threads 0 .. world-1 of the block wait until the flag of "their" peer has reached `t` (the polls overlap)
@@ -410,7 +416,7 @@ __device__ __forceinline__ uint32_t trial_quad(const DevView& v, const uint32_t*
         }
         if (thr_h == 0 && k_w == 0) continue;
         const uint32_t i = (q << 2) + (uint32_t)k;
-        if (run_trials(thr_h, thr_w, k_w, __ldg(&v.global_id[i]), t, v.mp.seed_lo, v.mp.seed_hi)) {
+        if (run_trials(thr_h, thr_w, k_w, v.mp.shard_lo + i, t, v.mp.seed_lo, v.mp.seed_hi)) {
             w[k] |= t + EXPOSURE_BIAS;                 // DiseaseStatus::Exposed(0) (citizen.rs:244)
             v.cstate[i] = w[k];
             ++n_exposed;
@@ -495,98 +501,180 @@ __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
 constexpr int STEP_THREADS = 256;
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
+// ---- the trial queue of a warp --------------------------------------------------------------------------------------------
+// While nearly everybody is susceptible and nobody infected, trials are rare and k_step is a stream.  At an epidemic's peak
+// almost every susceptible citizen has an infected room-mate, but only ~2 of the 8 citizens a thread holds per iteration are
+// susceptible: run where they are found, the Philox rounds would execute eight times per iteration with a quarter of the
+// lanes active.  Instead every lane appends the citizens that need trials to a queue in shared memory, and as soon as the
+// queue holds 32 entries the warp runs them, one per lane.  A citizen whose trial succeeds is written back by the lane that
+// ran it; that lane also accounts for it in the class tally of step t + 1 (newly exposed: one more in every cumulative count),
+// so nothing has to travel back to the lane that owns the citizen - which keeps treating it as Susceptible, i.e. as nothing.
+// An entry is the citizen's index: the lane that runs the trial reads the state word, the cell ids and the counts again (L1 /
+// L2 hits: the owner has just read them), so the queue costs 4 bytes per entry and the owner keeps nothing alive for it.
+constexpr uint32_t TQ_CAP = 31 + 8 * 32;   // at most 31 entries wait when an iteration appends up to 8 per lane
+struct StepTally { uint32_t c_exp = 0, c_inf = 0, c_ei = 0, c_vax = 0, n_exposed = 0; };
+
+struct StepCtx {   // uniform values of a k_step launch
+    uint32_t t, mask_everywhere, i_lo, e_lo, rider_mask, slot_next;
+    const uint32_t* cnt;
+    uint32_t* cnt_next;
+    const uint32_t* pos_next;
+};
+
+template <bool AT_WORK, bool P2P>
+__device__ __forceinline__ void run_queued_trial(const DevView& v, const StepCtx& x, const uint32_t i, StepTally& tl, bool& pushed) {
+    constexpr uint32_t HOME_TEST = AT_WORK ? (CS_LOW16 | CS_SAME_AREA) : CS_LOW16;
+    constexpr uint32_t HOME_WANT = AT_WORK ? CS_SAME_AREA : 0u;
+    constexpr uint32_t WORK_TEST = AT_WORK ? (CS_LOW16 | CS_HAS_WORK) : (CS_LOW16 | CS_HAS_WORK | CS_SAME_AREA);
+    constexpr uint32_t WORK_WANT = AT_WORK ? CS_HAS_WORK : (CS_HAS_WORK | CS_SAME_AREA);
+    const uint32_t w = v.cstate[i], hc = __ldg(&v.home_cell[i]), wc = __ldg(&v.work_cell[i]);
+    const uint32_t n_h = (w & HOME_TEST) == HOME_WANT ? __ldg(&x.cnt[hc]) : 0u;
+    const uint32_t n_w = (w & WORK_TEST) == WORK_WANT ? __ldg(&x.cnt[wc]) : 0u;
+    const uint32_t mc = mask_table(v, w, x.mask_everywhere);
+    unsigned long long thr_h = 0, thr_w = 0;
+    uint32_t k_w = 0;
+    if (n_h) thr_h = __ldg(&v.thr[mc + thr_index(v, n_h)]);
+    if (n_w) {
+        // a room member gets one trial per infected member of its own room, each with n = infected in the school
+        const uint32_t n_total = wc >= v.n_bldg ? __ldg(&x.cnt[__ldg(&v.room_parent[wc - v.n_bldg])]) : n_w;
+        thr_w = __ldg(&v.thr[mc + thr_index(v, n_total)]);
+        k_w = thr_w ? (wc >= v.n_bldg ? n_w : 1u) : 0u;
+    }
+    if (thr_h == 0 && k_w == 0) return;
+    if (!run_trials(thr_h, thr_w, k_w, v.mp.shard_lo + i, x.t, v.mp.seed_lo, v.mp.seed_hi)) return;   // (out of line: the Philox rounds)
+    const uint32_t code = x.t + EXPOSURE_BIAS;      // DiseaseStatus::Exposed(0) (citizen.rs:244)
+    v.cstate[i] = w | code;
+    tl.n_exposed += 1;
+    // generate_exposures of step t + 1 for the citizen (its owner counted it as Susceptible, i.e. not at all)
+    tl.c_exp += 1; tl.c_inf += code >= x.i_lo; tl.c_ei += code >= x.e_lo;
+    if (code >= x.i_lo && code < x.e_lo && (w & x.rider_mask) == 0u)   // (only a model with exposed_time = 0 gets here)
+        pushed |= count_present<P2P>(v, x.cnt_next, x.slot_next, __ldg(&x.pos_next[i]));
+}
+
 template <bool EAGER, bool AT_WORK, bool P2P>
-__device__ __forceinline__ uint32_t step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* s_cnt, bool& pushed) {
-    const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void step_stream(const DevView& v, const Ctrl* __restrict__ c, uint32_t* __restrict__ tq, StepTally& tl, bool& pushed) {
+    const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x, lane = lane_id();
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
     const uint4* __restrict__ hc4 = reinterpret_cast<const uint4*>(v.home_cell);
     const uint4* __restrict__ wc4 = reinterpret_cast<const uint4*>(v.work_cell);
     const uint32_t t = c->t, t1 = t + 1u;
-    const uint32_t mask_everywhere = c->mask_cur == ESIM_MASK_EVERYWHERE;
-    const uint32_t* __restrict__ cnt = v.cnt[cnt_slot(1u, t)];
-    uint32_t* __restrict__ cnt_next = v.cnt[cnt_slot(1u, t1)];
+    StepCtx x;
+    x.t = t;
+    x.mask_everywhere = c->mask_cur == ESIM_MASK_EVERYWHERE;
+    x.cnt = v.cnt[cnt_slot(1u, t)];
+    x.cnt_next = v.cnt[cnt_slot(1u, t1)];
+    x.slot_next = cnt_slot(1u, t1);
     uint4* __restrict__ cnt_zero = reinterpret_cast<uint4*>(v.cnt[cnt_slot(1u, t1 + 1u)]);
     // step t + 1: riders only count on their bus (simulator.rs:181-198); thresholds of the order-preserving state code
-    const uint32_t rider_mask = c->next_pt_mode != ESIM_PT_NONE ? CS_USES_PT : 0u;
-    const uint32_t e_lo = t1 + EXPOSURE_BIAS - v.mp.exposed_time;
-    const uint32_t i_lo = e_lo - 1u - v.mp.infected_time;
-    const uint32_t* __restrict__ pos_next = c->next_at_work ? v.work_cell : v.home_cell;
+    x.rider_mask = c->next_pt_mode != ESIM_PT_NONE ? CS_USES_PT : 0u;
+    x.e_lo = t1 + EXPOSURE_BIAS - v.mp.exposed_time;
+    x.i_lo = x.e_lo - 1u - v.mp.infected_time;
+    x.pos_next = c->next_at_work ? v.work_cell : v.home_cell;
+    const uint4* __restrict__ pos4 = reinterpret_cast<const uint4*>(x.pos_next);
     const uint4 pad4 = make_uint4(CS_PADDING, CS_PADDING, CS_PADDING, CS_PADDING);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
-    uint32_t n_exposed = 0;
-    uint32_t c_exp = 0, c_inf = 0, c_ei = 0, c_vax = 0;   // #(code != 0), #(code >= i_lo), #(code >= e_lo), #(code >= 0x8000)
+    uint32_t qn = 0;   // entries waiting in this warp's queue (uniform over the warp)
     bool zeroed = false;
-    for (uint32_t q0 = gtid; q0 < n_quads; q0 += 2u * T) {
+    // the trip count is uniform over a warp (the queue is a warp-wide affair): lanes past the end hold padding
+    for (uint32_t q0 = gtid; q0 - lane < n_quads; q0 += 2u * T) {
         const uint32_t q1 = q0 + T;
-        const bool have1 = q1 < n_quads;
-        const uint4 wa = cs4[q0];
+        const bool have0 = q0 < n_quads, have1 = q1 < n_quads;
+        const uint4 wa = have0 ? cs4[q0] : pad4;
         const uint4 wb = have1 ? cs4[q1] : pad4;
-        uint4 ha, ka, hb, kb;
+        uint4 ha = zero4, ka = zero4, hb = zero4, kb = zero4;
         if (EAGER) {
-            ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0);
-            if (have1) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); } else { hb = kb = make_uint4(0u, 0u, 0u, 0u); }
+            if (have0) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
+            if (have1) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
         }
         if (!zeroed) {
             // the count buffer of step t + 2 (nothing in this launch reads it): behind the first loads, far from the final fence
             zeroed = true;
-            for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
+            for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = zero4;
         }
-        uint32_t w[2][4] = {{wa.x, wa.y, wa.z, wa.w}, {wb.x, wb.y, wb.z, wb.w}};
+        const uint32_t w[2][4] = {{wa.x, wa.y, wa.z, wa.w}, {wb.x, wb.y, wb.z, wb.w}};
         const bool sa = any_susceptible(wa), sb = any_susceptible(wb);
         if (!EAGER) {
             if (sa) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
             if (sb) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
         }
-        // apply_exposures of step t
-        if (sa) n_exposed += expose_quad<AT_WORK>(v, cnt, q0, w[0], ha, ka, t, mask_everywhere);
-        if (sb) n_exposed += expose_quad<AT_WORK>(v, cnt, q1, w[1], hb, kb, t, mask_everywhere);
-        // generate_exposures of step t + 1 on the updated words.  Eight citizens that were never exposed add nothing to the
-        // cumulative counts: one test skips them (the common case for most of an epidemic).
-        if (((w[0][0] | w[0][1] | w[0][2] | w[0][3] | w[1][0] | w[1][1] | w[1][2] | w[1][3]) & CS_LOW16) == 0u) continue;
-        uint32_t any_present_infected = 0;
+        // ---- apply_exposures of step t: the infected counts of every source of both quads are requested together
+        uint32_t n_h[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, n_w[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+        if (sa) gather_quad<AT_WORK>(x.cnt, w[0], ha, ka, n_h[0], n_w[0]);
+        if (sb) gather_quad<AT_WORK>(x.cnt, w[1], hb, kb, n_h[1], n_w[1]);
+        uint32_t need = 0;   // bit 4 u + k: the citizen has an infected room-mate somewhere
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) need |= (n_h[u][k] | n_w[u][k]) ? 1u << (4 * u + k) : 0u;
+        if (__any_sync(0xffffffffu, need != 0u)) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool mine = (need >> (4 * u + k)) & 1u;
+                    const unsigned votes = __ballot_sync(0xffffffffu, mine);
+                    if (mine) tq[qn + __popc(votes & ((1u << lane) - 1u))] = ((u ? q1 : q0) << 2) + (uint32_t)k;
+                    qn += __popc(votes);
+                }
+        }
+        // ---- generate_exposures of step t + 1.  Eight citizens that were never exposed add nothing to the cumulative
+        // counts: one test skips them (the common case for most of an epidemic).
+        uint32_t present = 0;   // bit 4 u + k: Infected in step t + 1 and not on a bus
+        const bool any_code = ((w[0][0] | w[0][1] | w[0][2] | w[0][3] | w[1][0] | w[1][1] | w[1][2] | w[1][3]) & CS_LOW16) != 0u;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
+            if (!any_code) break;
             if (u == 1 && !have1) break;
+            if (u == 0 && !have0) continue;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t code = w[u][k] & CS_LOW16;
-                c_exp += code != 0u;
-                c_inf += code >= i_lo;
-                c_ei += code >= e_lo;
-                c_vax += code >> 15;
-                any_present_infected |= (code >= i_lo) & (code < e_lo) & ((w[u][k] & rider_mask) == 0u);
+                tl.c_exp += code != 0u;
+                tl.c_inf += code >= x.i_lo;
+                tl.c_ei += code >= x.e_lo;
+                tl.c_vax += code >> 15;
+                present |= ((code >= x.i_lo) & (code < x.e_lo) & ((w[u][k] & x.rider_mask) == 0u)) ? 1u << (4 * u + k) : 0u;
             }
         }
-        if (any_present_infected) {
+        if (present) {
+            // an infected citizen marks the building it stands in, and its room inside a school (simulator.rs:187-198).  The
+            // members of a quad that stand in the same cell (a household at night) are added with one reduction.
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                if (u == 1 && !have1) break;
+                const uint32_t pu = (present >> (4 * u)) & 15u;
+                if (pu == 0u) continue;
+                const uint4 c4 = __ldg(pos4 + (u ? q1 : q0));   // (L1: the eager build has just read the line)
+                const uint32_t cell[4] = {c4.x, c4.y, c4.z, c4.w};
+                uint32_t run = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t code = w[u][k] & CS_LOW16;
-                    if (code >= i_lo && code < e_lo && (w[u][k] & rider_mask) == 0u) {
-                        const uint32_t cell = __ldg(&pos_next[((u ? q1 : q0) << 2) + (uint32_t)k]);
-                        pushed |= count_present<P2P>(v, cnt_next, cnt_slot(1u, t1), cell);
+                    run += (pu >> k) & 1u;
+                    if ((k == 3 || cell[k + 1 < 4 ? k + 1 : 3] != cell[k]) && run) {
+                        pushed |= count_present<P2P>(v, x.cnt_next, x.slot_next, cell[k], run);
+                        run = 0;
+                    } else if (k < 3 && cell[k + 1] != cell[k]) {
+                        run = 0;
                     }
                 }
             }
         }
+        // ---- the queued trials, a full warp at a time (nothing of this iteration is alive any more)
+        if (qn >= 32u) {
+            __syncwarp();
+            do {
+                qn -= 32u;
+                run_queued_trial<AT_WORK, P2P>(v, x, tq[qn + lane], tl, pushed);
+            } while (qn >= 32u);
+            __syncwarp();
+        }
     }
     if (!zeroed)   // a thread without a quad still owns its share of the zeroing
-        for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = make_uint4(0u, 0u, 0u, 0u);
-    // block reduction of the class counts -> tally_partial[block]
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t r4[4] = {warp_sum(c_exp), warp_sum(c_inf), warp_sum(c_ei), warp_sum(c_vax)};
-    if (lane_id() == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (r4[k]) atomicAdd(&s_cnt[k], r4[k]);
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
-    return n_exposed;
+        for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = zero4;
+    // the entries still waiting
+    __syncwarp();
+    if (lane < qn) run_queued_trial<AT_WORK, P2P>(v, x, tq[lane], tl, pushed);
 }
 
 template <bool P2P>
@@ -594,6 +682,7 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     KTrace kt; kt.start(v);
     pdl_prologue_wait_first();
     __shared__ uint32_t s_cnt[4];
+    __shared__ uint32_t s_tq[STEP_THREADS / 32][TQ_CAP];
     // the state words of the first iteration: their addresses only depend on the launch geometry, so the requests (L2
     // prefetches: no register is held) leave before the control block has been read
     {
@@ -614,10 +703,23 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     kt.begin(v, kt_t, 0);
     const bool eager = c->eager_expose != 0, at_work = c->at_work != 0;
     bool pushed = false;
-    const uint32_t n_exposed = eager ? (at_work ? step_stream<true, true, P2P>(v, c, s_cnt, pushed) : step_stream<true, false, P2P>(v, c, s_cnt, pushed))
-                                     : (at_work ? step_stream<false, true, P2P>(v, c, s_cnt, pushed) : step_stream<false, false, P2P>(v, c, s_cnt, pushed));
-    const uint32_t s = warp_sum(n_exposed);
-    if (lane_id() == 0 && s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+    StepTally tl;
+    uint32_t* tq = s_tq[threadIdx.x >> 5];
+    if (eager) { if (at_work) step_stream<true, true, P2P>(v, c, tq, tl, pushed); else step_stream<true, false, P2P>(v, c, tq, tl, pushed); }
+    else { if (at_work) step_stream<false, true, P2P>(v, c, tq, tl, pushed); else step_stream<false, false, P2P>(v, c, tq, tl, pushed); }
+    // block reduction of the class counts -> tally_partial[block]; successful exposures -> the control block
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t r4[4] = {warp_sum(tl.c_exp), warp_sum(tl.c_inf), warp_sum(tl.c_ei), warp_sum(tl.c_vax)};
+    const uint32_t s = warp_sum(tl.n_exposed);
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (r4[k]) atomicAdd(&s_cnt[k], r4[k]);
+        if (s) atomicAdd(&v.ctrl->new_exp_bldg, s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
     signal_block_done(v, P2P && pushed);
     kt.end(v, kt_t, 0);
 }
@@ -633,7 +735,10 @@ constexpr int PT_MAX_FAST = ESIM_PT_SPAN_RIDERS;   // riders of a span (whole ro
 constexpr int PT_PER_LANE = PT_MAX_FAST / 32;
 struct __align__(16) PtWarpSmem {
     uint32_t buscnt[PT_MAX_FAST];   // infected riders per bus: slot (start of the route inside the span + bus)
-    uint8_t bus[PT_MAX_FAST];       // bus of rider j of the span
+    uint32_t hist[PT_MAX_FAST];     // riders per bucket, then the fill cursor of the bucket
+    uint32_t start[PT_MAX_FAST];    // riders in earlier buckets of the span
+    uint32_t mkey[PT_MAX_FAST];     // shuffle keys, grouped by bucket
+    uint8_t mj[PT_MAX_FAST];        // ... and the position of their rider inside the span
 };
 
 // slow path for routes with more than PT_MAX_FAST riders: global scratch, same arithmetic
@@ -644,7 +749,7 @@ __device__ __noinline__ uint32_t pt_route_slow(const DevView& v, uint32_t off, u
     for (uint32_t j = lane; j < n; j += 32) {
         const uint32_t i = v.riders[off + j];
         const uint32_t w = __ldcg(&v.cstate[i]);
-        const Philox4 p = philox4x32_10(v.global_id[i], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
+        const Philox4 p = philox4x32_10(v.mp.shard_lo + i, t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
         v.pt_key[off + j] = p.v[0];
         v.pt_bus[off + j] = (status_at(w, t, te, ti) == ST_I) ? 0x80000000u : 0u;
         if (j < n_buses) v.pt_buscnt[off + j] = 0;
@@ -673,7 +778,7 @@ __device__ __noinline__ uint32_t pt_route_slow(const DevView& v, uint32_t off, u
         if (!is_susceptible(w)) continue;
         const unsigned long long thr = __ldg(&v.thr[mask_table(v, w, mask_everywhere) + thr_index(v, n_b)]);
         if (thr == 0) continue;
-        const Philox4 p = philox4x32_10(v.global_id[i], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
+        const Philox4 p = philox4x32_10(v.mp.shard_lo + i, t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
         if (u52_from(p, 1) < thr) {
             v.cstate[i] = w | (t + EXPOSURE_BIAS) | CS_VIA_PT;
             ++n_exposed;
@@ -690,49 +795,14 @@ __device__ __noinline__ uint32_t pt_route_slow(const DevView& v, uint32_t off, u
 // A span costs three dependent memory round trips (span record -> rider indices and segments -> state words and global ids)
 // and a warp walks several spans, so the loads are software-pipelined: while span k is being ranked, the state words of span
 // k + 1, the rider indices of span k + 2 and the record of span k + 3 are in flight.
-// The shuffle of a span's routes as ONE sort: every rider carries the 64-bit word
-//     (start of its route inside the span : 7 | Philox key : 32 | position inside the span : 7 | 0 : 18)
-// and a bitonic network orders the <= 128 words of the span across the warp, four per lane (element e lives in lane e / 4,
-// register e % 4).  Routes occupy consecutive positions of the span, so after the sort the riders of a route stand together, in
-// (key, position) order, starting at the route's own start: rank inside the route = sorted position - start.  28
-// compare-exchange stages (13 inside a lane, 15 across lanes by shuffle), the same for every span whatever its routes look
-// like - the round-1 kernel counted smaller keys per rider, O(n^2 / 32) 64-bit comparisons with divergent trip counts.
-// Padding words are all-ones and end up behind every rider.
-template <uint32_t K, uint32_t D>
-__device__ __forceinline__ void pt_sort_stage(unsigned long long (&x)[PT_PER_LANE], uint32_t lane) {
-    if (D >= (uint32_t)PT_PER_LANE) {
-        constexpr uint32_t LD = D / PT_PER_LANE, LK = K / PT_PER_LANE;   // the partner's lane: lane ^ LD, same register
-        const bool keep_min = ((lane & LD) == 0u) == ((lane & LK) == 0u);    // lower element of an ascending pair, or upper of a descending one
-#pragma unroll
-        for (int r = 0; r < PT_PER_LANE; ++r) {
-            const unsigned long long y = __shfl_xor_sync(0xffffffffu, x[r], LD);
-            x[r] = ((y < x[r]) == keep_min) ? y : x[r];
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < PT_PER_LANE; ++r) {
-            if ((uint32_t)r & D) continue;
-            // ascending iff bit K of the element index (lane * PT_PER_LANE + r) is clear
-            const bool up = K >= (uint32_t)PT_PER_LANE ? (lane & (K / PT_PER_LANE)) == 0u : ((uint32_t)r & K) == 0u;
-            const unsigned long long a = x[r], b = x[r | D];
-            const bool swap = (b < a) == up;
-            x[r] = swap ? b : a;
-            x[r | D] = swap ? a : b;
-        }
-    }
-}
-template <uint32_t K, uint32_t D>
-__device__ __forceinline__ void pt_sort_merge(unsigned long long (&x)[PT_PER_LANE], uint32_t lane) {
-    pt_sort_stage<K, D>(x, lane);
-    if constexpr (D > 1u) pt_sort_merge<K, D / 2u>(x, lane);
-}
-template <uint32_t K>
-__device__ __forceinline__ void pt_sort_from(unsigned long long (&x)[PT_PER_LANE], uint32_t lane) {
-    pt_sort_merge<K, K / 2u>(x, lane);
-    if constexpr (K < (uint32_t)PT_MAX_FAST) pt_sort_from<K * 2u>(x, lane);
-}
-static_assert(PT_PER_LANE == 4 && PT_MAX_FAST == 128, "the sort network is written for 128 words, four per lane");
-
+// The shuffle of a route = ascending order of (Philox key, position); a rider's bus follows from its RANK in that order.  The
+// keys are uniform 32-bit numbers, so the rank is found without sorting: a route of `len` riders owns `len` buckets (the
+// positions of its riders inside the span), a rider falls into bucket floor(key * len / 2^32) - monotone in the key - and
+//     rank = riders of the route in earlier buckets + riders of the same bucket with a smaller (key, position).
+// One shared-memory histogram, one warp scan, and a look at the one or two riders that share the bucket: ~100 instructions per
+// lane and span, the same for every span whatever its routes look like.  (Round 1 counted smaller keys per rider, O(n^2 / 32)
+// 64-bit comparisons with divergent trip counts, 25.8 us per public-transport hour; a bitonic network over the span's
+// (route, key, position) words, tried first in round 2, was no faster: 28 dependent shuffle stages per span.)
 struct PtSpan {
     uint32_t off, n, n_routes;
 };
@@ -748,14 +818,11 @@ __device__ __forceinline__ void pt_load_idx(const DevView& v, const PtSpan& x, u
         idx[s] = (j < x.n && x.n <= PT_MAX_FAST) ? __ldg(&v.riders[x.off + j]) : 0xFFFFFFFFu;
     }
 }
-// state words and global ids of a span's riders
-__device__ __forceinline__ void pt_load_riders(const DevView& v, const uint32_t (&idx)[PT_PER_LANE], uint32_t (&w)[PT_PER_LANE], uint32_t (&gid)[PT_PER_LANE]) {
+// state words of a span's riders.  (CitizenID::global_index needs no array: the citizens of a shard are a contiguous,
+// ascending range of the population - checked at import - so it is shard_lo + index.)
+__device__ __forceinline__ void pt_load_riders(const DevView& v, const uint32_t (&idx)[PT_PER_LANE], uint32_t (&w)[PT_PER_LANE]) {
 #pragma unroll
-    for (int s = 0; s < PT_PER_LANE; ++s) {
-        const bool have = idx[s] != 0xFFFFFFFFu;
-        w[s] = have ? __ldcg(&v.cstate[idx[s]]) : CS_PADDING;
-        gid[s] = have ? __ldg(&v.global_id[idx[s]]) : 0u;
-    }
+    for (int s = 0; s < PT_PER_LANE; ++s) w[s] = idx[s] != 0xFFFFFFFFu ? __ldcg(&v.cstate[idx[s]]) : CS_PADDING;
 }
 
 __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint32_t t, uint32_t mask_everywhere) {
@@ -764,65 +831,87 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t stride = gridDim.x * warps_per_block;
     uint32_t n_exposed = 0;
-    uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    // fill the pipeline: records of three spans, rider indices of two, riders of one
-    PtSpan cur = pt_load_span(v, k), nxt = pt_load_span(v, k + stride), nn = pt_load_span(v, k + 2u * stride);
-    uint32_t idx[PT_PER_LANE], w[PT_PER_LANE], gid[PT_PER_LANE], idx_n[PT_PER_LANE];
-    pt_load_idx(v, cur, lane, idx);
-    pt_load_idx(v, nxt, lane, idx_n);
-    pt_load_riders(v, idx, w, gid);
-    for (; k < v.n_spans; k += stride) {
-        // requests of the spans behind this one
-        uint32_t w_n[PT_PER_LANE], gid_n[PT_PER_LANE], idx_nn[PT_PER_LANE];
-        pt_load_riders(v, idx_n, w_n, gid_n);
-        pt_load_idx(v, nn, lane, idx_nn);
-        const PtSpan nnn = pt_load_span(v, k + 3u * stride);
+    // One span per warp and many more warps than an SM holds: the three dependent memory round trips of a span (record -> rider
+    // indices -> state words) are hidden by the other warps and by the blocks that start as earlier ones retire.  (Round 1
+    // walked the spans grid-stride with one resident wave and software-pipelined loads: with 1.5 spans per warp the second
+    // half of the kernel ran at half occupancy, and the pipeline's registers cost a third of the resident warps.)
+    for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < v.n_spans; k += stride) {
+        const PtSpan cur = pt_load_span(v, k);
+        uint32_t idx[PT_PER_LANE], w[PT_PER_LANE];
+        pt_load_idx(v, cur, lane, idx);
+        pt_load_riders(v, idx, w);
         const uint32_t n = cur.n;
-        // route segments of this span's riders (start of the route inside the span | riders of the route << 8): a coalesced
-        // load whose latency the Philox rounds below cover - not worth pipeline registers
+        // route segments of this span's riders (start of the route inside the span | riders of the route << 8)
         uint32_t seg[PT_PER_LANE];
 #pragma unroll
         for (int s = 0; s < PT_PER_LANE; ++s) seg[s] = (lane + 32u * s < n && n <= PT_MAX_FAST) ? (uint32_t)__ldg(&v.pt_seg[cur.off + lane + 32u * s]) : 0u;
         if (n > PT_MAX_FAST) {
             n_exposed += pt_route_slow(v, cur.off, n, t, mask_everywhere);   // a single long route
         } else {
-            // pass 1: shuffle keys and trial words of the lane's riders (rider j = lane + 32 s of the span)
-            uint32_t u_lo[PT_PER_LANE], u_hi[PT_PER_LANE];
-            unsigned long long x[PT_PER_LANE];
+            // pass 1: shuffle keys and trial words of the lane's riders (rider j = lane + 32 s of the span); bucket of every rider
+            uint32_t key[PT_PER_LANE], u_lo[PT_PER_LANE], u_hi[PT_PER_LANE], slot[PT_PER_LANE];
 #pragma unroll
             for (int s = 0; s < PT_PER_LANE; ++s) {
                 const uint32_t j = lane + 32u * s;
-                u_lo[s] = u_hi[s] = 0u;
-                x[s] = ~0ull;
-                if (j < n) {
-                    const Philox4 p = philox4x32_10(gid[s], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
-                    u_lo[s] = p.v[2]; u_hi[s] = p.v[3];
-                    x[s] = ((unsigned long long)(seg[s] & 0xFFu) << 57) | ((unsigned long long)p.v[0] << 25) | ((unsigned long long)j << 18);
-                }
-                ws->buscnt[j] = 0;
-            }
-            // pass 2: the shuffled order of every route of the span -> bus of each rider (PublicTransport buses are filled
-            // by popping from the end of the shuffled list, simulator.rs:364-388)
-            pt_sort_from<2u>(x, lane);
-#pragma unroll
-            for (int r = 0; r < PT_PER_LANE; ++r) {
-                if (x[r] == ~0ull) continue;
-                const uint32_t pos = lane * PT_PER_LANE + (uint32_t)r;           // position in the sorted span
-                const uint32_t first = (uint32_t)(x[r] >> 57), j = (uint32_t)(x[r] >> 18) & 127u;
-                const uint32_t len = (uint32_t)__ldg(&v.pt_seg[cur.off + j]) >> 8;   // (L1: requested for the whole span a moment ago)
-                ws->bus[j] = (uint8_t)((len - 1u - (pos - first)) / cap);
+                ws->buscnt[j] = 0; ws->hist[j] = 0;
             }
             __syncwarp();
-            // infected riders per bus (PublicTransport::exposure_count).  Counter of bus b of a route = slot (route start + b):
-            // b < riders of the route.
+#pragma unroll
+            for (int s = 0; s < PT_PER_LANE; ++s) {
+                const uint32_t j = lane + 32u * s;
+                key[s] = u_lo[s] = u_hi[s] = slot[s] = 0u;
+                if (j < n) {
+                    const Philox4 p = philox4x32_10(v.mp.shard_lo + idx[s], t, 0u, DOM_PT, v.mp.seed_lo, v.mp.seed_hi);
+                    key[s] = p.v[0]; u_lo[s] = p.v[2]; u_hi[s] = p.v[3];
+                    slot[s] = (seg[s] & 0xFFu) + __umulhi(key[s], seg[s] >> 8);
+                    atomicAdd(&ws->hist[slot[s]], 1u);
+                }
+            }
+            __syncwarp();
+            // riders in earlier buckets: exclusive scan over the span's 128 buckets, four consecutive buckets per lane
+            {
+                const uint4 h4 = reinterpret_cast<const uint4*>(ws->hist)[lane];
+                const uint32_t mine = h4.x + h4.y + h4.z + h4.w;
+                uint32_t incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += y;
+                }
+                const uint32_t e0 = incl - mine;
+                reinterpret_cast<uint4*>(ws->start)[lane] = make_uint4(e0, e0 + h4.x, e0 + h4.x + h4.y, e0 + h4.x + h4.y + h4.z);
+                reinterpret_cast<uint4*>(ws->hist)[lane] = make_uint4(0u, 0u, 0u, 0u);   // from now on: the fill cursor of the bucket
+            }
+            __syncwarp();
+            uint32_t base[PT_PER_LANE];
+#pragma unroll
+            for (int s = 0; s < PT_PER_LANE; ++s) {
+                const uint32_t j = lane + 32u * s;
+                base[s] = 0;
+                if (j < n) {
+                    base[s] = ws->start[slot[s]];
+                    const uint32_t m = base[s] + atomicAdd(&ws->hist[slot[s]], 1u);
+                    ws->mkey[m] = key[s]; ws->mj[m] = (uint8_t)j;
+                }
+            }
+            __syncwarp();
+            // pass 2: rank in the shuffled order of the rider's own route -> bus (PublicTransport buses are filled by popping
+            // from the end of the shuffled list, simulator.rs:364-388).  The riders of earlier routes of the span fill exactly
+            // the buckets in front of the route's first one, so "earlier buckets of the route" = start[bucket] - route start.
             uint32_t bus[PT_PER_LANE];
 #pragma unroll
             for (int s = 0; s < PT_PER_LANE; ++s) {
                 const uint32_t j = lane + 32u * s;
                 bus[s] = 0;
                 if (j < n) {
-                    bus[s] = ws->bus[j];
-                    if (status_at(w[s], t, te, ti) == ST_I) atomicAdd(&ws->buscnt[(seg[s] & 0xFFu) + bus[s]], 1u);
+                    const uint32_t first = seg[s] & 0xFFu, len = seg[s] >> 8, end = base[s] + ws->hist[slot[s]];
+                    uint32_t rank = base[s] - first;
+                    for (uint32_t m = base[s]; m < end; ++m) {
+                        const uint32_t km = ws->mkey[m];
+                        rank += (km < key[s]) || (km == key[s] && (uint32_t)ws->mj[m] < j);
+                    }
+                    bus[s] = (len - 1u - rank) / cap;
+                    if (status_at(w[s], t, te, ti) == ST_I) atomicAdd(&ws->buscnt[first + bus[s]], 1u);
                 }
             }
             __syncwarp();
@@ -842,12 +931,6 @@ __device__ __forceinline__ void pt_phase(const DevView& v, PtWarpSmem* ws, uint3
                 }
             }
             __syncwarp();
-        }
-        // advance the pipeline
-        cur = nxt; nxt = nn; nn = nnn;
-#pragma unroll
-        for (int s = 0; s < PT_PER_LANE; ++s) {
-            idx[s] = idx_n[s]; w[s] = w_n[s]; gid[s] = gid_n[s]; idx_n[s] = idx_nn[s];
         }
     }
     const uint32_t s = warp_sum(n_exposed);
@@ -1338,7 +1421,7 @@ constexpr size_t HT_BYTES = 3 * HT_SIZE * sizeof(uint32_t);
 constexpr int PT_THREADS = 128;  // 4 spans per block: small blocks start (and, on idle hours, retire) quickly
 
 #ifndef ESIM_PT_BLOCKS_PER_SM
-#define ESIM_PT_BLOCKS_PER_SM 6
+#define ESIM_PT_BLOCKS_PER_SM 8
 #endif
 __global__ void __launch_bounds__(PT_THREADS, ESIM_PT_BLOCKS_PER_SM) k_pt(const __grid_constant__ DevView v) {
     KTrace kt; kt.start(v);
@@ -1712,13 +1795,15 @@ void launch_expose(const DevView& v, cudaStream_t s) {
 }
 void launch_pt(const DevView& v, cudaStream_t s) {
     if (v.n_routes == 0) return;
-    // one warp per span of routes, grid-stride over one resident wave: the warps pipeline their loads over the spans they walk
+    // one warp per span of routes
     static int per_sm = 0;
     if (per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pt, PT_THREADS, 0) != cudaSuccess) per_sm = 0;
         if (per_sm <= 0) per_sm = 4;
     }
-    launch_step_kernel(k_pt, blocks_for(v.n_spans, PT_THREADS / 32, wave(v, (uint32_t)per_sm)), PT_THREADS, 0, s, v);
+    // handles that share a device keep to one resident wave between them (their kernels wait for each other)
+    const uint32_t cap = v.share > 1 ? wave(v, (uint32_t)per_sm) : (uint32_t)sm_count() * (uint32_t)per_sm * 8u;
+    launch_step_kernel(k_pt, blocks_for(v.n_spans, PT_THREADS / 32, cap), PT_THREADS, 0, s, v);
 }
 void launch_tail(const DevView& v, cudaStream_t s) {
     launch_step_kernel(k_tail, 1, TAIL_THREADS, HT_BYTES, s, v);

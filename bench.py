@@ -281,9 +281,12 @@ def main():
         run_reference(args, wl, rank, world)
         return
 
-    # rank 0 prints ONE line: keep NCCL's own version banner (NCCL_DEBUG=VERSION) off stdout
+    # rank 0 prints ONE line: NCCL writes its version banner to stdout, so everything before the JSON line goes to stderr
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from epidemicsimulator_b200 import _abi, synthetic_population, shard_population
@@ -553,7 +556,10 @@ def main():
         out.update(extra)
         if not args.no_cpu_baseline and world == 1 and whole is not None:
             out["cpu_baseline"] = cpu_baseline(whole, dict(seed=args.sim_seed), args.cpu_seconds)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     if not parity_ok:

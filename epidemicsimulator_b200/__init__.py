@@ -7,10 +7,11 @@ from ._abi import (SimError, EsimConfig, EsimStepStats, STATS_FIELDS, STATUS_SUS
                    STATUS_INFECTED, STATUS_RECOVERED, STATUS_VACCINATED, MASK_NONE, MASK_PUBLIC_TRANSPORT,
                    MASK_EVERYWHERE, PT_NONE, PT_HOME_TO_WORK, PT_WORK_TO_HOME, NO_ROOM, NONE_U32,
                    FLAG_USES_PT, FLAG_MASK_COMPLIANT, BLDG_HOUSEHOLD, BLDG_WORKPLACE, BLDG_SCHOOL)
-from .population import Population, synthetic_population, shard_population, save_population, load_population
+from .population import (Population, synthetic_population, shard_population, save_population, load_population,
+                         DevicePopulation, device_population)
 
 __all__ = ["Simulator", "DiseaseModel", "Population", "synthetic_population", "shard_population", "save_population",
-           "load_population", "SimError"]
+           "load_population", "DevicePopulation", "device_population", "SimError"]
 
 
 def __getattr__(name):

@@ -67,6 +67,20 @@ def cuda_lib() -> C.CDLL:
     lib.esim_create.argtypes = [C.POINTER(_abi.EsimConfig), C.POINTER(vp)]
     lib.esim_create_multi.argtypes = [C.POINTER(_abi.EsimConfig), C.c_uint32, C.POINTER(C.c_int32), C.POINTER(vp)]
     lib.esim_import_population.argtypes = [vp, C.POINTER(_abi.EsimPopulationSoA)]
+    lib.esim_import_population_device.argtypes = [vp, C.POINTER(_abi.EsimPopulationSoA)]
+    lib.esim_popgen_device_create.argtypes = [C.POINTER(_abi.EsimPopgenParams), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    lib.esim_popgen_device_view.argtypes = [vp, C.POINTER(_abi.EsimPopulationSoA)]
+    lib.esim_popgen_device_view_device.argtypes = [vp, C.POINTER(_abi.EsimPopulationSoA)]
+    lib.esim_popgen_device_area_offsets.argtypes = [vp]
+    lib.esim_popgen_device_area_offsets.restype = _abi.u32p
+    lib.esim_popgen_device_bldg_global.argtypes = [vp]
+    lib.esim_popgen_device_bldg_global.restype = _abi.u32p
+    lib.esim_popgen_device_room_global.argtypes = [vp]
+    lib.esim_popgen_device_room_global.restype = _abi.u32p
+    lib.esim_popgen_device_total_citizens.argtypes = [vp]
+    lib.esim_popgen_device_total_citizens.restype = C.c_uint32
+    lib.esim_popgen_device_destroy.argtypes = [vp]
+    lib.esim_popgen_device_destroy.restype = None
     lib.esim_destroy.argtypes = [vp]
     lib.esim_destroy.restype = None
     lib.esim_step.argtypes = [vp, C.POINTER(_abi.EsimStepStats)]

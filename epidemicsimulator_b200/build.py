@@ -21,7 +21,7 @@ INCLUDE = ROOT / "include"
 CUDA_LIB = PKG / "libesim_b200.so"
 HOST_LIB = PKG / "libesim_host.so"
 
-CUDA_SOURCES = ["esim_kernels.cu", "esim_import.cu", "esim_api.cu"]
+CUDA_SOURCES = ["esim_kernels.cu", "esim_import.cu", "esim_api.cu", "esim_popgen_device.cu"]
 HOST_SOURCES = ["popgen.cpp", "population_io.cpp"]
 
 
@@ -70,7 +70,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h", HOST_LIB] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
-    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
            "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-ccbin", host_compiler(),
            "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(CUDA_LIB)]
     if verbose:
@@ -86,7 +86,7 @@ def build_variant(name: str, defines) -> Path:
     """A/B builds of the CUDA library with other compile-time switches (scripts/kstep_ab.py selects one with ESIM_B200_LIB)."""
     out = PKG / ("libesim_b200_%s.so" % name)
     build_host()
-    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
            "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-ccbin", host_compiler(),
            "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(out)] + ["-D" + d for d in defines]
     cmd += [str(CSRC / s) for s in CUDA_SOURCES] + ["-lcudart", "-ldl", "-L", str(PKG), "-lesim_host", "-Xlinker", "-rpath=$ORIGIN"]

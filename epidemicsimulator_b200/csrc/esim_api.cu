@@ -504,7 +504,7 @@ static void print_ktrace(EsimSim* s) {
     std::vector<unsigned long long> mn(s->ktrace_min.n), mx(s->ktrace_max.n);
     cudaMemcpy(mn.data(), s->ktrace_min.p, s->ktrace_min.bytes(), cudaMemcpyDeviceToHost);
     cudaMemcpy(mx.data(), s->ktrace_max.p, s->ktrace_max.bytes(), cudaMemcpyDeviceToHost);
-    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose/xchg", "pt", "tail", "tail:send", "tail:poll"};
+    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose/xchg", "pt", "tail", "tail:send", "tail:poll", "tail:picks", "tail:epilogue"};
     const uint32_t last = s->steps_done, first = last > KTRACE_STEPS - 2 ? last - (KTRACE_STEPS - 2) : 2;
     // everything relative to the end of slot 0 (k_update / k_step) of the same step
     double run[KTRACE_KERNELS] = {}, b_rel[KTRACE_KERNELS] = {}, e_rel[KTRACE_KERNELS] = {}, wait[KTRACE_KERNELS] = {};
@@ -536,9 +536,8 @@ static void print_ktrace(EsimSim* s) {
 
 void esim_destroy(EsimSim* s) { if (s) print_ktrace(s); delete s; }
 
-int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
-    if (!s) return ESIM_ERR_INVALID_ARGUMENT;
-    if (!s->kid_devices.empty()) return multi_import(s, p);
+// `on_device`: the arrays of `p` are device pointers on the handle's device (esim_import_population_device)
+static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_device) {
     return guarded(s, [&]() -> int {
         if (!p || !p->home_bldg || !p->work_bldg || !p->room || !p->bldg_area || !p->bldg_type || (p->n_rooms && !p->room_bldg))
             throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "population arrays missing"};
@@ -551,7 +550,10 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         if (p->n_shared_bldgs > B || p->n_shared_rooms > R) throw ApiError{ESIM_ERR_INVALID_POPULATION, "shared prefix larger than the arrays"};
         const uint32_t n_pad = (N + 3u) & ~3u;
         const uint32_t n_global = p->n_global_citizens ? p->n_global_citizens : N;
-        const uint32_t shard_lo = p->global_id ? p->global_id[0] : 0u;
+        uint32_t shard_lo = 0u;
+        if (p->global_id) {
+            if (on_device) CK(cudaMemcpy(&shard_lo, p->global_id, 4, cudaMemcpyDeviceToHost)); else shard_lo = p->global_id[0];
+        }
         if ((uint64_t)shard_lo + N > n_global) throw ApiError{ESIM_ERR_INVALID_POPULATION, "global ids exceed n_global_citizens"};
         const uint32_t te = s->cfg.exposed_time, ti = s->cfg.infected_time;
         cudaStream_t st = s->stream;
@@ -571,7 +573,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         auto up = [&](auto& buf, const auto* host, size_t count) {
             buf.alloc(count);
             cleanup.f.push_back([&buf] { buf.release(); });
-            CK(cudaMemcpyAsync(buf.p, host, buf.bytes(), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(buf.p, host, buf.bytes(), cudaMemcpyDefault, st));   // host (pageable or pinned) or device source
         };
         up(r_home, p->home_bldg, N); up(r_work, p->work_bldg, N); up(r_room, p->room, N);
         if (p->global_id) up(r_gid, p->global_id, N);
@@ -580,7 +582,7 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         if (p->timer) up(r_timer, p->timer, N);
         up(r_area, p->bldg_area, B); up(r_btype, p->bldg_type, B);
         s->room_parent.alloc(std::max<uint32_t>(R, 1));
-        if (R) CK(cudaMemcpyAsync(s->room_parent.p, p->room_bldg, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+        if (R) CK(cudaMemcpyAsync(s->room_parent.p, p->room_bldg, (size_t)R * 4, cudaMemcpyDefault, st));
 
         tr.mark("upload raw arrays", st);
         s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad);
@@ -692,8 +694,9 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         CK(cudaMemcpyAsync(s->ctrl.p, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
         tr.mark("thresholds, allocations, memsets", st);
 
-        s->h_bldg_area.assign(p->bldg_area, p->bldg_area + B);
-        if (R) s->h_room_parent.assign(p->room_bldg, p->room_bldg + R);
+        s->h_bldg_area.resize(B); s->h_room_parent.resize(R);
+        CK(cudaMemcpy(s->h_bldg_area.data(), p->bldg_area, (size_t)B * 4, cudaMemcpyDefault));
+        if (R) CK(cudaMemcpy(s->h_room_parent.data(), p->room_bldg, (size_t)R * 4, cudaMemcpyDefault));
         s->n_areas = A;
 
         tr.mark("host copies of area tables");
@@ -744,6 +747,17 @@ int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
         s->finished = false;
         return ESIM_OK;
     });
+}
+
+int esim_import_population(EsimSim* s, const EsimPopulationSoA* p) {
+    if (!s) return ESIM_ERR_INVALID_ARGUMENT;
+    if (!s->kid_devices.empty()) return multi_import(s, p);
+    return import_population(s, p, false);
+}
+int esim_import_population_device(EsimSim* s, const EsimPopulationSoA* p) {
+    if (!s) return ESIM_ERR_INVALID_ARGUMENT;
+    if (!s->kid_devices.empty()) return fail(s, ESIM_ERR_INVALID_ARGUMENT, "a multi-device handle imports from host arrays");
+    return import_population(s, p, true);
 }
 
 // A step is queued (step_enqueue) and then waited for (step_collect), so that a multi-device handle can queue the step on every

@@ -53,7 +53,7 @@ constexpr uint32_t VAX_CHUNK_WORDS = ESIM_VAX_SHARD_DRAWS / 8;        // nibble 
 constexpr uint32_t FEXCH_HEAD      = 8;                               // S,E,I,R,V of step t + 1, building / public-transport exposures of step t, spare
 constexpr uint32_t FEXCH_WORDS     = FEXCH_HEAD + VAX_MAX_CHUNKS * VAX_CHUNK_WORDS;
 
-constexpr uint32_t KTRACE_STEPS = 1024, KTRACE_KERNELS = 6;   // 0 = update / step, 1 = expose or exchange wait, 2 = pt, 3 = tail, 4 = tail: loads -> vector sent, 5 = spare
+constexpr uint32_t KTRACE_STEPS = 1024, KTRACE_KERNELS = 8;   // 0 = update / step, 1 = expose or exchange wait, 2 = pt, 3 = tail, 4 = tail: loads -> vector sent, 5 = tail: poll, 6 = tail: vectors in -> picks done, 7 = tail: epilogue + write-back
 
 // index of the count buffer that holds the infected occupants of step t
 __host__ __device__ inline uint32_t cnt_slot(uint32_t fused, uint32_t t) { return fused ? t % 3u : t & 1u; }

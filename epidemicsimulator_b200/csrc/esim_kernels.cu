@@ -1497,6 +1497,7 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
 
     KTrace ks; ks.enter = 0; ks.begin(v, t, 4);   // timeline slot 4: loads done -> first vector sent
     uint32_t K = 0, accepted = 0, base = 0;
+    KTrace kp6; kp6.enter = 0;
     for (uint32_t round = 0;; ++round) {
         const uint32_t n_nib = chunks * VAX_CHUNK_WORDS, n_words = FEXCH_HEAD + n_nib, tag = (t + 1u) | (round << 16);
         // ---- this shard's marks for the draws [base, base + chunks * VAX_SHARD_DRAWS)
@@ -1575,7 +1576,7 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
                 }
             }
             __syncthreads();
-            if (round == 0u) kx.end(v, t, 1);
+            if (round == 0u) { kx.end(v, t, 1); kp6.begin(v, t, 6); }
         }
         if (round == 0u) {
             if (tid < 5) sm.tally[tid] = sum[tid];          // class counts of step t + 1 as k_step saw them, all shards
@@ -1644,6 +1645,8 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
     }
     if (tid == 0 && !(K > 0 && K == sm.c.n_elig)) sm.accepted = accepted;
     __syncthreads();
+    kp6.end(v, t, 6);
+    KTrace kp7; kp7.enter = 0; kp7.begin(v, t, 7);
     if (v.n_shared_b | v.n_shared_r) {
         // tell the peers that the corrections this tail pushed into their count buffers (if any) are complete: their next k_step
         // waits for it.  Raised before the scalar epilogue so that the flag travels while this block finishes.
@@ -1659,6 +1662,7 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
     if (tid == 0) tail_epilogue<true>(v, sm);
     __syncthreads();
     tail_writeback(v, sm, t);
+    kp7.end(v, t, 7);
 }
 
 // fused pipeline: v.n_update_blocks is the grid of the kernel that left the partial sums (k_step, or k_update in the boot pass)

@@ -83,6 +83,43 @@ int esim_popgen_default_params(EsimPopgenParams* p) {
     return ESIM_OK;
 }
 
+// pass 1 of the generator: households per area, their (one) size, first resident of every area.  Exported because the
+// device-side generator (libesim_b200.so, esim_popgen_device_create) takes these O(n_areas) numbers from here: the only
+// transcendental arithmetic of the generator (the normal draw) then runs in ONE place, with one libm.
+int esim_popgen_area_layout(const EsimPopgenParams* pp, uint32_t* n_hh, uint32_t* hh_size, uint32_t* area_off) {
+    if (!pp || !n_hh || !hh_size || !area_off || pp->n_areas == 0 || pp->min_residents == 0 || pp->max_residents < pp->min_residents)
+        return ESIM_ERR_INVALID_ARGUMENT;
+    const EsimPopgenParams& p = *pp;
+    uint64_t total = 0;
+    area_off[0] = 0;
+    for (uint32_t a = 0; a < p.n_areas; ++a) {
+        Rng r(p.pop_seed, a, 1);
+        long n = std::lround(p.mean_residents + p.sd_residents * r.normal());
+        n = std::max<long>(p.min_residents, std::min<long>(p.max_residents, n));
+        hh_size[a] = 2 + r.below(4);
+        n_hh[a] = (uint32_t)((n + hh_size[a] - 1) / hh_size[a]);  // whole households until >= n (output_area.rs:139-180)
+        total += (uint64_t)n_hh[a] * hh_size[a];
+        if (total > 0xFFFFFFF0ull) return ESIM_ERR_INVALID_ARGUMENT;
+        area_off[a + 1] = (uint32_t)total;
+    }
+    return ESIM_OK;
+}
+
+// the initial infections (simulator_builder.rs:1111-1142): `initial_infected` draws of (uniform area, uniform citizen in it),
+// duplicates possible; writes the citizen indices, returns how many (areas without residents are skipped)
+int esim_popgen_initial_infections(const EsimPopgenParams* pp, const uint32_t* area_off, uint32_t* citizens_out) {
+    if (!pp || !area_off || !citizens_out) return ESIM_ERR_INVALID_ARGUMENT;
+    Rng r(pp->pop_seed, 0xFFFFFFFFull, 4);
+    int count = 0;
+    for (uint32_t k = 0; k < pp->initial_infected; ++k) {
+        const uint32_t a = r.below(pp->n_areas);
+        const uint32_t n = area_off[a + 1] - area_off[a];
+        if (n == 0) continue;
+        citizens_out[count++] = area_off[a] + r.below(n);
+    }
+    return count;
+}
+
 int esim_popgen_create(const EsimPopgenParams* pp, EsimPopgen** out) {
     if (!pp || !out || pp->n_areas == 0 || pp->areas_per_school == 0 || pp->min_residents == 0 ||
         pp->max_residents < pp->min_residents)
@@ -97,18 +134,8 @@ int esim_popgen_create(const EsimPopgenParams* pp, EsimPopgen** out) {
         // ---- pass 1: households and citizens per area -------------------------------------------------
         std::vector<uint32_t> n_hh(A), hh_size(A);
         g->area_off.assign(A + 1, 0);
-        uint64_t total = 0;
-        for (uint32_t a = 0; a < A; ++a) {
-            Rng r(p.pop_seed, a, 1);
-            long n = std::lround(p.mean_residents + p.sd_residents * r.normal());
-            n = std::max<long>(p.min_residents, std::min<long>(p.max_residents, n));
-            hh_size[a] = 2 + r.below(4);
-            n_hh[a] = (uint32_t)((n + hh_size[a] - 1) / hh_size[a]);  // whole households until >= n (output_area.rs:139-180)
-            total += (uint64_t)n_hh[a] * hh_size[a];
-            if (total > 0xFFFFFFF0ull) { delete g; return ESIM_ERR_INVALID_ARGUMENT; }
-            g->area_off[a + 1] = (uint32_t)total;
-        }
-        const uint32_t N = (uint32_t)total;
+        if (esim_popgen_area_layout(&p, n_hh.data(), hh_size.data(), g->area_off.data()) < 0) { delete g; return ESIM_ERR_INVALID_ARGUMENT; }
+        const uint32_t N = g->area_off[A];
         g->home.resize(N); g->work.resize(N); g->room.assign(N, ESIM_NO_ROOM);
         g->age.resize(N); g->occ.resize(N); g->flags.resize(N);
         g->status.assign(N, ESIM_STATUS_SUSCEPTIBLE); g->timer.assign(N, 0);
@@ -283,15 +310,9 @@ int esim_popgen_create(const EsimPopgenParams* pp, EsimPopgen** out) {
 
         // ---- initial infections (simulator_builder.rs:1111-1142): duplicates possible ----------------
         {
-            Rng r(p.pop_seed, 0xFFFFFFFFull, 4);
-            for (uint32_t k = 0; k < p.initial_infected; ++k) {
-                const uint32_t a = r.below(A);
-                const uint32_t n = g->area_off[a + 1] - g->area_off[a];
-                if (n == 0) continue;
-                const uint32_t i = g->area_off[a] + r.below(n);
-                g->status[i] = ESIM_STATUS_INFECTED;
-                g->timer[i] = 0;
-            }
+            std::vector<uint32_t> first(p.initial_infected + 1);
+            const int n_first = esim_popgen_initial_infections(&p, g->area_off.data(), first.data());
+            for (int k = 0; k < n_first; ++k) { g->status[first[k]] = ESIM_STATUS_INFECTED; g->timer[first[k]] = 0; }
         }
     } catch (const std::bad_alloc&) {
         delete g;

@@ -127,17 +127,7 @@ def synthetic_population(n_areas: int = 637, pop_seed: int = 20110327, areas_per
                          cross_area_fraction: float = 0.0, initial_infected: int = 10, **overrides) -> Population:
     """Deterministic census-shaped population (see include/esim_popgen.h for the rules it follows)."""
     lib = host_lib()
-    p = _abi.EsimPopgenParams()
-    _check(lib.esim_popgen_default_params(C.byref(p)))
-    p.n_areas = n_areas
-    p.pop_seed = pop_seed
-    p.areas_per_school = areas_per_school
-    p.cross_area_fraction = cross_area_fraction
-    p.initial_infected = initial_infected
-    for k, v in overrides.items():
-        if not hasattr(p, k):
-            raise TypeError("unknown population parameter %r" % k)
-        setattr(p, k, v)
+    p = _popgen_params(n_areas, pop_seed, areas_per_school, cross_area_fraction, initial_infected, overrides)
     g = C.c_void_p()
     _check(lib.esim_popgen_create(C.byref(p), C.byref(g)))
     try:
@@ -147,6 +137,76 @@ def synthetic_population(n_areas: int = 637, pop_seed: int = 20110327, areas_per
         return _from_soa(s, area_offsets=off)
     finally:
         lib.esim_popgen_destroy(g)
+
+
+def _popgen_params(n_areas, pop_seed, areas_per_school, cross_area_fraction, initial_infected, overrides):
+    p = _abi.EsimPopgenParams()
+    _check(host_lib().esim_popgen_default_params(C.byref(p)))
+    p.n_areas = n_areas
+    p.pop_seed = pop_seed
+    p.areas_per_school = areas_per_school
+    p.cross_area_fraction = cross_area_fraction
+    p.initial_infected = initial_infected
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown population parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+class DevicePopulation:
+    """The population of synthetic_population(), bit for bit, generated on a CUDA device (esim_popgen_device_create): shard
+    `rank` of `world` contiguous output-area ranges (world = 1: everybody).  host() downloads it as a Population;
+    device_soa() hands the device pointers to Simulator.import_device_population (no host round trip)."""
+
+    def __init__(self, n_areas: int = 637, pop_seed: int = 20110327, areas_per_school: int = 25, cross_area_fraction: float = 0.0,
+                 initial_infected: int = 10, rank: int = 0, world: int = 1, device: int = 0, **overrides):
+        from ._lib import cuda_lib
+        self._lib = cuda_lib()
+        self.n_areas, self.rank, self.world, self.device = n_areas, rank, world, device
+        p = _popgen_params(n_areas, pop_seed, areas_per_school, cross_area_fraction, initial_infected, overrides)
+        self._h = C.c_void_p()
+        rc = self._lib.esim_popgen_device_create(C.byref(p), device, rank, world, C.byref(self._h))
+        if rc < 0:
+            raise _abi.SimError(rc, "esim_popgen_device_create")
+        self.n_total = int(self._lib.esim_popgen_device_total_citizens(self._h))
+
+    def host(self) -> Population:
+        v = _abi.EsimPopulationSoA()
+        _check(self._lib.esim_popgen_device_view(self._h, C.byref(v)))
+        off = np.ctypeslib.as_array(self._lib.esim_popgen_device_area_offsets(self._h), shape=(self.n_areas + 1,)).copy()
+        extra = {}
+        if self.world > 1:
+            extra["bldg_global"] = np.ctypeslib.as_array(self._lib.esim_popgen_device_bldg_global(self._h), shape=(v.n_buildings,)).copy()
+            extra["room_global"] = (np.ctypeslib.as_array(self._lib.esim_popgen_device_room_global(self._h), shape=(v.n_rooms,)).copy()
+                                    if v.n_rooms else np.zeros(0, np.uint32))
+        return _from_soa(v, area_offsets=off if self.world == 1 else None, **extra)
+
+    def device_soa(self) -> _abi.EsimPopulationSoA:
+        v = _abi.EsimPopulationSoA()
+        _check(self._lib.esim_popgen_device_view_device(self._h, C.byref(v)))
+        return v
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.esim_popgen_device_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_population(n_areas: int = 637, pop_seed: int = 20110327, areas_per_school: int = 25, cross_area_fraction: float = 0.0,
+                      initial_infected: int = 10, rank: int = 0, world: int = 1, device: int = 0, **overrides) -> Population:
+    """synthetic_population() + shard_population() computed on the GPU; returns this rank's shard as host arrays."""
+    g = DevicePopulation(n_areas, pop_seed, areas_per_school, cross_area_fraction, initial_infected, rank, world, device, **overrides)
+    try:
+        return g.host()
+    finally:
+        g.close()
 
 
 def shard_population(pop: Population, rank: int, world: int) -> Population:

@@ -84,6 +84,14 @@ def pin_population(pop: Population) -> Population:
     return out
 
 
+class _Sizes:
+    """The counts of a population whose arrays stay on the device."""
+
+    def __init__(self, soa):
+        self.n_citizens, self.n_buildings, self.n_rooms = int(soa.n_citizens), int(soa.n_buildings), int(soa.n_rooms)
+        self.n_shards = int(soa.n_shards)
+
+
 class DiseaseModel:
     """sim/src/disease.rs:97-129"""
 
@@ -122,6 +130,13 @@ class Simulator:
         soa = pop.as_soa()
         self._check(self._lib.esim_import_population(self._h, C.byref(soa)))
         self.pop = pop
+
+    def import_device_population(self, dev_pop, host_view: Optional[Population] = None) -> None:
+        """esim_import_population_device: `dev_pop` is a DevicePopulation on this handle's device.  `host_view` (optional) is
+        what state() / building_counts() size their buffers from; without it the sizes come from the device view."""
+        soa = dev_pop.device_soa()
+        self._check(self._lib.esim_import_population_device(self._h, C.byref(soa)))
+        self.pop = host_view if host_view is not None else _Sizes(soa)
 
     def close(self) -> None:
         if getattr(self, "_h", None):

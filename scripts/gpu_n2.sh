@@ -1,14 +1,10 @@
 #!/bin/bash
-# 2-GPU validation in one gpurun --gpus 2 call: GPU tests that need two devices, the torchrun oracle check in both exchange
-# modes, and the bench line at N=2 (weak scaling: the BASELINE per-GPU workload on every rank).
-TAG=${1:-n2}
-STEPS=${STEPS:-960}
+# 2 (or N) GPUs: real ranks against the oracle, then the multi-GPU bench line (BASELINE configs[4] by default).
+# usage: gpurun --gpus 2 --timeout 900 -- 'bash scripts/gpu_n2.sh <tag> <N> [bench args]'
+TAG=${1:-n2}; N=${2:-2}; shift; shift
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus_$TAG.txt
-python -m pytest tests/test_gpu_sharded.py -x -q -m gpu > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_$TAG.log
-for COMM in p2p nccl; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/sharded_check.py --comm $COMM > gpurun_out/sharded_${COMM}_$TAG.log 2>&1
-  echo "sharded_check $COMM rc=$?"; grep sharded_check gpurun_out/sharded_${COMM}_$TAG.log
-done
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29602 bench.py --gpus 2 --steps $STEPS --warmup 24 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
-echo "bench N=2 rc=$?"; tail -c 2500 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/sharded_check.py --comm p2p --areas 400 --cross 0.6 --steps 900 2>&1 | grep -E "sharded_check|MISMATCH|Error|error" | tee gpurun_out/sharded_check_$TAG.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/sharded_check.py --comm nccl --areas 200 --cross 0.6 --steps 600 2>&1 | grep -E "sharded_check|MISMATCH|Error|error" | tee -a gpurun_out/sharded_check_$TAG.log
+timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N "$@" > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+tail -5 gpurun_out/bench_$TAG.err | cut -c1-300; cat gpurun_out/bench_$TAG.json | cut -c1-3000

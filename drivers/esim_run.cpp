@@ -1,6 +1,10 @@
 // esim_run - C++ stand-in for the reference's `run --simulate` mode (run/src/main.rs:290-313) over the C ABI.
 //
 //   esim_run <population.esimpop> [--output_name=<dir/>] [--steps=<n>] [--seed=<u64>] [--device=<ordinal>] [--synthetic=<areas>]
+//            [--gpus=<n> | --devices=<a,b,...>] [--corrected]
+//
+// --gpus / --devices: ONE handle and this one host thread drive several GPUs (esim_create_multi) - the drop-in for the
+// reference's single-process binary on a multi-GPU box; every call below is the same as on one GPU.
 //
 // The reference loads census / OSM data, builds the population in-process and calls `Simulator::simulate(output_name)`
 // (sim/src/simulator.rs:108-127).  Here the population arrives as the binary file a Rust exporter of `SimulatorBuilder`
@@ -27,6 +31,8 @@ int main(int argc, char** argv) {
     uint32_t steps = 0, synthetic = 0;
     uint64_t seed = 0;
     int device = 0;
+    bool corrected = false;
+    std::vector<int32_t> devices;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a.rfind("--output_name=", 0) == 0) output = a.substr(14);
@@ -34,11 +40,18 @@ int main(int argc, char** argv) {
         else if (a.rfind("--seed=", 0) == 0) seed = strtoull(a.c_str() + 7, nullptr, 10);
         else if (a.rfind("--device=", 0) == 0) device = atoi(a.c_str() + 9);
         else if (a.rfind("--synthetic=", 0) == 0) synthetic = (uint32_t)strtoul(a.c_str() + 12, nullptr, 10);
+        else if (a.rfind("--gpus=", 0) == 0) { devices.clear(); for (int d = 0; d < atoi(a.c_str() + 7); ++d) devices.push_back(d); }
+        else if (a.rfind("--devices=", 0) == 0) {
+            devices.clear();
+            for (const char* q = a.c_str() + 10; *q;) { devices.push_back((int32_t)strtol(q, const_cast<char**>(&q), 10)); if (*q == ',') ++q; }
+        }
+        else if (a == "--corrected") corrected = true;
         else if (a[0] != '-') path = a;
         else { fprintf(stderr, "esim_run: unknown option %s\n", a.c_str()); return 2; }
     }
     if (path.empty() && !synthetic) {
-        fprintf(stderr, "usage: esim_run <population.esimpop> [--output_name=<dir/>] [--steps=<n>] [--seed=<u64>] [--device=<n>] [--synthetic=<areas>]\n");
+        fprintf(stderr, "usage: esim_run <population.esimpop> [--output_name=<dir/>] [--steps=<n>] [--seed=<u64>] [--device=<n>] [--synthetic=<areas>] "
+                        "[--gpus=<n> | --devices=<a,b,...>] [--corrected]\n");
         return 2;
     }
     const auto t_total = std::chrono::steady_clock::now();
@@ -64,9 +77,10 @@ int main(int argc, char** argv) {
     esim_default_config(&cfg);
     cfg.seed = seed; cfg.device = device;
     if (steps) cfg.max_time_step = steps;
+    if (corrected) cfg.flags |= ESIM_CFG_CORRECTED;
     EsimSim* sim = nullptr;
-    int rc = esim_create(&cfg, &sim);
-    if (rc < 0) return fail("esim_create", rc, nullptr);
+    int rc = devices.empty() ? esim_create(&cfg, &sim) : esim_create_multi(&cfg, (uint32_t)devices.size(), devices.data(), &sim);
+    if (rc < 0) return fail(devices.empty() ? "esim_create" : "esim_create_multi", rc, nullptr);
     rc = esim_import_population(sim, &pop);
     if (rc < 0) return fail("esim_import_population", rc, sim);
     printf("Finished loading data and Initialising  simulator in %.2f\n",

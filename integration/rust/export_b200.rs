@@ -21,8 +21,11 @@ impl Soa {
     }
 }
 
-/// Walks `output_areas` in index order (INTEGRATION.md section 6 explains the numbering)
-pub fn to_soa(builder: &SimulatorBuilder) -> Soa {
+/// Walks `output_areas` in index order (INTEGRATION.md section 6 explains the numbering).
+/// Reference types used: `OutputArea { citizens: Vec<Citizen>, buildings: Vec<Box<dyn Building + Sync + Send>>, .. }`
+/// (output_area.rs:85-100), `Building::{id, as_any}` (building.rs:125-140), `School::{classes, offices}` (building.rs:444-450),
+/// `Class::get_participants` (building.rs:318, returns an owned Vec), `Citizen` pub fields (citizen.rs:109-135).
+pub fn to_soa(builder: &SimulatorBuilder) -> anyhow::Result<Soa> {
     let areas = &builder.output_areas;
     let mut bldg_offset = vec![0u32; areas.len() + 1];
     for (a, area) in areas.iter().enumerate() { bldg_offset[a + 1] = bldg_offset[a] + area.buildings.len() as u32; }
@@ -30,43 +33,46 @@ pub fn to_soa(builder: &SimulatorBuilder) -> Soa {
                       bldg_type: vec![], room_bldg: vec![], area_first: vec![0], area_codes: vec![] };
     let mut room_of: HashMap<CitizenID, u32> = HashMap::new();
     for (a, area) in areas.iter().enumerate() {
-        let mut ids: Vec<&BuildingID> = area.buildings.keys().collect();
-        ids.sort_by_key(|id| id.building_index());                                 // building.rs:62-67
-        for id in ids {
-            let global = bldg_offset[a] + id.building_index() as u32;
-            let b = &area.buildings[id];
+        // `buildings` is a Vec indexed by BuildingID::building_index (building.rs:62-67, :107): keep that order
+        for (position, b) in area.buildings.iter().enumerate() {
+            anyhow::ensure!(b.id().building_index() == position, "building {} of area {} is filed under index {}", b.id().building_index(), a, position);
+            let global = bldg_offset[a] + position as u32;
             s.bldg_area.push(a as u32);
             if let Some(school) = b.as_any().downcast_ref::<School>() {
                 s.bldg_type.push(2);
                 for class in school.classes() {                                    // building.rs:307-342: classes, then offices
                     let r = s.room_bldg.len() as u32; s.room_bldg.push(global);
-                    for c in class.participants() { room_of.insert(c, r); }
+                    for c in class.get_participants() { room_of.insert(c, r); }    // owned Vec<CitizenID> (building.rs:318)
                 }
                 for office in school.offices() {
                     let r = s.room_bldg.len() as u32; s.room_bldg.push(global);
-                    for c in office { room_of.insert(*c, r); }
+                    for c in office.iter() { room_of.insert(c.clone(), r); }
                 }
             } else if b.as_any().downcast_ref::<Workplace>().is_some() { s.bldg_type.push(1) } else { s.bldg_type.push(0) }
         }
     }
     let cell = |id: &BuildingID| bldg_offset[id.output_area_code().index()] + id.building_index() as u32;
-    for area in areas {
-        let mut cs: Vec<&Citizen> = area.citizens.values().collect();
-        cs.sort_by_key(|c| c.id().global_index());                                 // citizen.rs:51-57
+    // citizen i of the arrays must be CitizenID::global_index() == i (citizen.rs:51-67): that index keys the random stream
+    // and is what esim_read_state returns positions for.  The builder numbers citizens area by area, so walking the areas in
+    // index order and the citizens of an area by global index gives 0, 1, 2, ...; anything else is refused.
+    for area in areas.iter() {
+        let mut cs: Vec<&Citizen> = area.citizens.iter().collect();
+        cs.sort_by_key(|c| c.id().global_index());
         for c in cs {
+            anyhow::ensure!(c.id().global_index() == s.home.len(), "citizens are not numbered area by area");
             s.home.push(cell(&c.household_code));
             s.work.push(cell(&c.workplace_code));
             s.room.push(*room_of.get(&c.id()).unwrap_or(&ffi::ESIM_NO_ROOM));
-            s.flags.push(c.uses_public_transport as u8 | (c.is_mask_compliant as u8) << 1);
+            s.flags.push(c.uses_public_transport as u8 | (c.is_mask_compliant as u8) << 1);   // ESIM_FLAG_USES_PT | ESIM_FLAG_MASK_COMPLIANT
             let (st, t) = match c.disease_status {                                 // disease.rs:36-44
                 DiseaseStatus::Susceptible => (0u8, 0u16), DiseaseStatus::Exposed(t) => (1, t), DiseaseStatus::Infected(t) => (2, t),
                 DiseaseStatus::Recovered => (3, 0), DiseaseStatus::Vaccinated => (4, 0) };
             s.status.push(st); s.timer.push(t);
         }
         s.area_first.push(s.home.len() as u32);
-        s.area_codes.push(CString::new(area.id().code().as_str()).unwrap());       // output_area.rs:42-45
+        s.area_codes.push(CString::new(area.id().code().as_str()).unwrap());       // output_area.rs:42-54
     }
-    s
+    Ok(s)
 }
 
 // ---- the file: 128-byte header, arrays padded to 64 bytes, FNV-1a 64 trailer (population_io.cpp) ------------------------------

@@ -1,5 +1,7 @@
-//! Hand-written from include/esim.h and include/esim_popgen.h (ABI version 1).  Layouts are checked on the C side by
-//! tests/test_abi.py (sizeof / offsetof of every struct against the ctypes mirror); keep the field order identical.
+//! Hand-written from include/esim.h and include/esim_popgen.h (ABI version 2).  Layouts are checked on the C side by
+//! tests/test_abi.py (sizeof / offsetof of every struct against the ctypes mirror), and tests/test_rust_binding.py parses THIS
+//! file: every #[repr(C)] struct must list the fields of its C namesake in the same order with the matching type, and every
+//! function of the extern block must exist in the headers with the same parameters.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int};
 
@@ -9,6 +11,7 @@ pub const ESIM_ERR_NO_DEVICE: c_int = -8;
 pub const ESIM_ERR_IO: c_int = -11;
 pub const ESIM_NO_ROOM: u32 = 0xFFFF_FFFF;
 pub const ESIM_NONE_U32: u32 = 0xFFFF_FFFF;
+pub const ESIM_CFG_CORRECTED: u32 = 0x40;   // opt-in corrected semantics, see include/esim.h (never set for parity with the reference)
 
 #[repr(C)] pub struct EsimSim { _private: [u8; 0] }
 #[repr(C)] pub struct EsimPopulationFile { _private: [u8; 0] }
@@ -52,6 +55,7 @@ extern "C" {
     pub fn esim_abi_version() -> c_int;
     pub fn esim_default_config(cfg: *mut EsimConfig) -> c_int;
     pub fn esim_create(cfg: *const EsimConfig, out: *mut *mut EsimSim) -> c_int;
+    pub fn esim_create_multi(cfg: *const EsimConfig, n_devices: u32, devices: *const i32, out: *mut *mut EsimSim) -> c_int;
     pub fn esim_import_population(sim: *mut EsimSim, pop: *const EsimPopulationSoA) -> c_int;
     pub fn esim_destroy(sim: *mut EsimSim);
     pub fn esim_step(sim: *mut EsimSim, out: *mut EsimStepStats) -> c_int;

@@ -22,15 +22,25 @@ fn check(sim: *mut ffi::EsimSim, rc: i32) -> anyhow::Result<i32> {
 
 impl From<SimulatorBuilder> for Simulator {                 // replaces simulator.rs:601-644
     fn from(builder: SimulatorBuilder) -> Self {
-        let soa = export_b200::to_soa(&builder);            // the arrays of export_b200.rs, kept alive for the call below
+        let soa = export_b200::to_soa(&builder).expect("population cannot be exported");   // kept alive for the call below
         let mut cfg: ffi::EsimConfig = unsafe { std::mem::zeroed() };
         unsafe { ffi::esim_default_config(&mut cfg) };
         let d = &builder.disease_model;                      // disease.rs:97-109
         cfg.exposure_chance = d.exposure_chance; cfg.exposed_time = d.exposed_time as u32; cfg.infected_time = d.infected_time as u32;
         cfg.max_time_step = d.max_time_step as u32; cfg.vaccination_rate = d.vaccination_rate as u32;
-        cfg.mask_effectiveness = d.mask_percentage;
+        cfg.mask_effectiveness = d.mask_effectiveness;      // 0.70 (disease.rs:127) - NOT mask_percentage (0.8, the compliance share,
+                                                            // which only the builder uses: output_area.rs:99,169)
+        cfg.bus_capacity = crate::config::BUS_CAPACITY as u32;                      // config.rs:37
+        // the intervention thresholds are crate-private constants (interventions.rs:50-57, 71-78): esim_default_config holds
+        // the same numbers; if they are ever changed in the crate, set cfg.lockdown_threshold / vaccination_threshold /
+        // mask_pt_threshold / mask_everywhere_threshold here (negative = Option::None)
         let mut handle = std::ptr::null_mut();
-        check(std::ptr::null_mut(), unsafe { ffi::esim_create(&cfg, &mut handle) }).expect("no B200: there is no CPU fallback");
+        // ESIM_GPUS=N: ONE handle drives N GPUs of this machine (esim_create_multi); the caller stays single-threaded like the
+        // reference (run/src/main.rs:290-306) and every call below works unchanged on the multi-device handle
+        let gpus: u32 = std::env::var("ESIM_GPUS").ok().and_then(|v| v.parse().ok()).unwrap_or(1);
+        let rc = if gpus > 1 { unsafe { ffi::esim_create_multi(&cfg, gpus, std::ptr::null(), &mut handle) } }
+                 else { unsafe { ffi::esim_create(&cfg, &mut handle) } };
+        check(std::ptr::null_mut(), rc).expect("no B200: there is no CPU fallback");
         check(handle, unsafe { ffi::esim_import_population(handle, &soa.view()) }).expect("population rejected");
         Simulator { handle, area_code: builder.area_code, output_area_lookup: builder.output_area_lookup,
                     area_codes: soa.area_codes, max_time_step: cfg.max_time_step, n_citizens: soa.home.len() }

@@ -36,14 +36,15 @@ def test_no_cpu_fallback(driver, tmp_path):
 
 
 @pytest.mark.gpu
-def test_driver_matches_the_oracle(driver, tmp_path):
+@pytest.mark.parametrize("extra", [[], ["--devices=0,0"]], ids=["one GPU", "one handle, two shards"])
+def test_driver_matches_the_oracle(driver, tmp_path, extra):
     from oracle.oracle_py import Oracle, default_config
     pop = synthetic_population(n_areas=50, areas_per_school=10, cross_area_fraction=0.3)
     codes = ["E%08d" % (500 + a) for a in range(pop.n_areas)]
     path = tmp_path / "p.esimpop"
     save_population(pop, path, area_codes=codes)
     out = str(tmp_path / "stats") + "/"
-    r = subprocess.run([driver, str(path), "--output_name=" + out, "--steps=400", "--seed=21"], capture_output=True, text=True)
+    r = subprocess.run([driver, str(path), "--output_name=" + out, "--steps=400", "--seed=21"] + extra, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert r.stdout.count("Completed  50 time steps") == 8 and "Starting simulation with 50 areas" in r.stdout
     orc = Oracle(pop, default_config(seed=21, max_time_step=400))

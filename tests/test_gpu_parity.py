@@ -200,6 +200,63 @@ def test_full_size_population_lockstep_with_oracle():
     sim.close(); orc.close()
 
 
+def _peak_lockstep(pop, steps, check_every, **cfg):
+    """Lockstep with the oracle from the state mix of an epidemic's peak (S 30 / E 20 / I 40 / R 3 / V 7 %):
+    trials in nearly every household, contended building counters, vaccination from the first hour."""
+    from bench import peak_mix
+    mix = peak_mix(pop)
+    cfg.setdefault("flags", _abi.CFG_RECORD_BUSES)
+    sim = _sim(mix, **cfg)
+    orc = Oracle(mix, default_config(**cfg))
+    seen = dict(vax=False, pt_exp=False, bld_exp=False, lockdown=False, pt_hours=0)
+    for k in range(steps):
+        alive = sim.step()
+        alive_o, so = orc.step()
+        assert sim.last_stats.as_tuple() == so.as_tuple(), "step %d:\n gpu    %s\n oracle %s" % (k + 1, sim.last_stats.as_dict(), so.as_dict())
+        assert alive == alive_o
+        seen["vax"] |= so.vaccinated_now > 0
+        seen["pt_exp"] |= so.exposures_pt > 0
+        seen["bld_exp"] |= so.exposures_building > 0
+        seen["lockdown"] |= so.lockdown_hours != _abi.NONE_U32
+        seen["pt_hours"] += so.pt_mode != _abi.PT_NONE
+        if (k + 1) % check_every == 0:
+            bg, rg = sim.building_counts()
+            bo, ro = orc.building_counts()
+            assert np.array_equal(bg, bo) and np.array_equal(rg, ro), "step %d: infected occupants differ" % (k + 1)
+            if so.pt_mode != _abi.PT_NONE:
+                ig, ng = sim.buses()
+                io, no = orc.buses()
+                riders = (mix.flags & _abi.FLAG_USES_PT) != 0
+                assert np.array_equal(ig[riders], io[riders]) and np.array_equal(ng[riders], no[riders]), "step %d: buses differ" % (k + 1)
+            _compare_state(sim, orc, k + 1)
+    sim.close(); orc.close()
+    return seen
+
+
+def test_full_size_peak_mix_at_reference_constants():
+    """BASELINE configs[1] (3.45 M citizens) at the reference's constants from the peak mix: the lockdown threshold is crossed at
+    once, so everybody stays where the first hour finds them - trials, vaccination picks and the frozen schedule at full size."""
+    pop = synthetic_population(n_areas=11300, areas_per_school=67)
+    seen = _peak_lockstep(pop, 24, check_every=8, seed=0)
+    assert seen["vax"] and seen["bld_exp"] and seen["lockdown"]
+
+
+def test_full_size_peak_mix_two_days_with_public_transport():
+    """The same population and mix without the lockdown rule, so that the schedule runs: 48 hours with four public-transport
+    hours (buses of 690 000 riders compared rider by rider), work and school hours, vaccination every hour."""
+    pop = synthetic_population(n_areas=11300, areas_per_school=67)
+    seen = _peak_lockstep(pop, 48, check_every=8, seed=0, lockdown_threshold=-1.0)
+    assert seen["vax"] and seen["bld_exp"] and seen["pt_exp"] and seen["pt_hours"] == 4
+
+
+def test_yorkshire_and_humber_size_lockstep():
+    """BASELINE configs[2] (17 246 output areas, ~5.3 M citizens) with every intervention enabled, 48 hours from the peak mix with
+    cross-area workplaces: bit-exact against the oracle."""
+    pop = synthetic_population(n_areas=17246, areas_per_school=100, cross_area_fraction=0.3)
+    seen = _peak_lockstep(pop, 48, check_every=16, seed=2)
+    assert seen["vax"] and seen["bld_exp"] and seen["lockdown"]
+
+
 def test_full_size_run_properties():
     pop = synthetic_population(n_areas=11300, areas_per_school=67)
     sim = _sim(pop, seed=1)

@@ -1312,6 +1312,7 @@ int esim_peer_connect(EsimSim* s, uint32_t rank, uint32_t world, const uint8_t* 
         CK(cudaMemcpyAsync(s->peer_view.p, &pv, sizeof(pv), cudaMemcpyHostToDevice, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         s->v.peer = s->peer_view.p;
+        for (uint32_t p = 0; p < MAX_WORLD; ++p) s->v.mail[p] = pv.mail[p];
         s->v.p2p = 1;
         if (fused) {
             // the fused pipeline over peer-to-peer shards: restart the control block at "step 0" and run the boot pass (its
@@ -1500,6 +1501,7 @@ void multi_connect(EsimSim* s) {
         CK(cudaMemcpyAsync(k->peer_view.p, &pv, sizeof(pv), cudaMemcpyHostToDevice, k->stream));
         k->v.rank = r; k->rank = r;
         k->v.peer = k->peer_view.p;
+        for (uint32_t p = 0; p < MAX_WORLD; ++p) k->v.mail[p] = pv.mail[p];
         k->v.p2p = 1;
         k->fused = true; k->v.fused = 1;
         const uint32_t zero = 0;

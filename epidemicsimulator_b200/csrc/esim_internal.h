@@ -109,6 +109,8 @@ struct Ctrl {
     uint32_t vax_event;      // update_status raised the Vaccination event for step t: the tail of step t takes the snapshot
     uint32_t vax_all_done;   // the whole eligible set has been vaccinated once: choosing all of it again changes nothing
     uint32_t lockdown_event; // corrected mode: update_status raised the Lockdown event: everybody is sent home (simulator.rs:467-479)
+    uint32_t cum[4];         // fused pipeline: cumulative class counts of step t + 1 (#code != 0, >= i_lo, >= e_lo, >= 0x8000), added up by the
+                             // blocks of k_step (boot pass: k_update) as they finish; read and cleared by the tail
 };
 
 struct ModelParams {
@@ -160,6 +162,7 @@ struct DevView {
     uint32_t rank;
     uint32_t n_shared_b, n_shared_r;   // the first cells of the building / room ranges exist on every shard
     const PeerView* peer;        // device memory, valid when p2p
+    uint32_t* mail[MAX_WORLD];   // the mailboxes again, as kernel parameters: the quick tail sends before it has loaded anything else
     uint32_t world;              // number of shards (1 = the whole population is here)
     uint32_t* exch;              // [EXCH_WORDS] second exchange buffer of a sharded step of the three-kernel pipeline
     uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] three-kernel pipeline: candidate citizen of every draw of this step

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <cstddef>
 
 #include "esim_internal.h"
 #include "esim_rng.h"
@@ -104,6 +105,12 @@ struct PeerWait {
         return now - start > v.peer_timeout_ns;
     }
 };
+#ifndef ESIM_POLL_NS
+#define ESIM_POLL_NS 32
+#endif
+#ifndef ESIM_QUICK_SEND_DELAY
+#define ESIM_QUICK_SEND_DELAY 0
+#endif
 // (value, tag) pairs of the fused tail exchange: one 8-byte store / load each, so a pair is never seen half-written
 __device__ __forceinline__ void st_pair_sys(uint32_t* p, uint32_t value, uint32_t tag) {
     asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(value), "r"(tag) : "memory");
@@ -118,7 +125,7 @@ __device__ __forceinline__ uint32_t ld_pair_wait(const DevView& v, const uint32_
         ld_pair_sys(p, value, seen);
         if (seen == tag) return value;
         if (pw.expired(v)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_COMM); return 0u; }
-        __nanosleep(32);
+        __nanosleep(ESIM_POLL_NS);
     }
 }
 // An infected citizen standing in a cell that other shards reference adds itself to their count buffers as well
@@ -203,16 +210,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
     return x;
 }
-__device__ __forceinline__ void wait_blocks_done(const DevView& v, uint32_t expected) {
-    if (threadIdx.x == 0) {
-        uint32_t spins = 0;
-        while (ld_acquire_gpu(&v.ctrl->blocks_done) < expected) {
-            if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_SIMULATION); break; }   // never hang the GPU
-        }
-    }
-    __syncthreads();
-}
-
 // k_update counts cumulatively (#code != 0, #code >= i_lo, #code >= e_lo, #code >= 0x8000) over all n_pad slots, the padding
 // slots counting as vaccinated: turn that into S, E, I, R, V of the n real citizens.
 __device__ __forceinline__ void classes_from_cumulative(const uint32_t* cum, uint32_t n_pad, uint32_t n, uint32_t* out5) {
@@ -320,6 +317,7 @@ __device__ __forceinline__ bool update_phase(const DevView& v, const Ctrl* __res
     }
     __syncthreads();
     if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
+    if (v.fused && threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&v.ctrl->cum[threadIdx.x], s_cnt[threadIdx.x]);   // boot pass, see Ctrl::cum
     return pushed;
 }
 
@@ -707,7 +705,7 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     uint32_t* tq = s_tq[threadIdx.x >> 5];
     if (eager) { if (at_work) step_stream<true, true, P2P>(v, c, tq, tl, pushed); else step_stream<true, false, P2P>(v, c, tq, tl, pushed); }
     else { if (at_work) step_stream<false, true, P2P>(v, c, tq, tl, pushed); else step_stream<false, false, P2P>(v, c, tq, tl, pushed); }
-    // block reduction of the class counts -> tally_partial[block]; successful exposures -> the control block
+    // block reduction of the class counts and of the successful exposures -> the control block
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t r4[4] = {warp_sum(tl.c_exp), warp_sum(tl.c_inf), warp_sum(tl.c_ei), warp_sum(tl.c_vax)};
@@ -719,7 +717,9 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
         if (s) atomicAdd(&v.ctrl->new_exp_bldg, s);
     }
     __syncthreads();
-    if (threadIdx.x < 8) v.tally_partial[blockIdx.x * 8u + threadIdx.x] = threadIdx.x < 4 ? s_cnt[threadIdx.x] : 0u;
+    // four reductions per block into the control block: the tail finds the sums there instead of adding up 592 partial records
+    // on the critical path between two steps (they precede the block's announcement: signal_block_done fences)
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&v.ctrl->cum[threadIdx.x], s_cnt[threadIdx.x]);
     signal_block_done(v, P2P && pushed);
     kt.end(v, kt_t, 0);
 }
@@ -1179,7 +1179,7 @@ __device__ __forceinline__ void tail_epilogue(const DevView& v, TailSmem& sm) {
         c->tally[0] = c->tally[1] = c->tally[2] = c->tally[3] = c->tally[4] = 0;
     }
     c->t = nt;
-    if (FUSED) c->blocks_done = 0;   // see signal_block_done: no producer is running now
+    if (FUSED) { c->blocks_done = 0; c->cum[0] = c->cum[1] = c->cum[2] = c->cum[3] = 0; }   // see signal_block_done: no producer is running now
     c->new_exp_bldg = 0; c->new_exp_pt = 0;
     c->vaccinated_now = accepted_in;
     // a specialised day graph has no public-transport kernel in most slots: if the next hour needs one after all (lockdown
@@ -1192,9 +1192,14 @@ __device__ __forceinline__ void tail_epilogue(const DevView& v, TailSmem& sm) {
 }
 
 // write the control block and the statistics entry back, coalesced (all threads; sm complete)
+// the sticky error word is only written when this tail raised an error itself: a wait for a peer that expired during this tail
+// wrote the device copy directly (PeerWait), and the block's working copy must not wipe that out
+__device__ __forceinline__ bool writes_back(const TailSmem& sm, uint32_t word) {
+    return word != (uint32_t)(offsetof(Ctrl, error) / 4) || sm.c.error != 0u;
+}
 __device__ __forceinline__ void tail_writeback(const DevView& v, TailSmem& sm, uint32_t t) {
     const uint32_t tid = threadIdx.x;
-    if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(v.ctrl)[tid] = reinterpret_cast<const uint32_t*>(&sm.c)[tid];
+    if (tid < sizeof(Ctrl) / 4 && writes_back(sm, tid)) reinterpret_cast<uint32_t*>(v.ctrl)[tid] = reinterpret_cast<const uint32_t*>(&sm.c)[tid];
     if (tid >= 64 && tid < 64 + sizeof(EsimStepStats) / 4 && t - 1 < v.max_steps)
         reinterpret_cast<uint32_t*>(&v.stats[t - 1])[tid - 64] = reinterpret_cast<const uint32_t*>(&sm.stats)[tid - 64];
 }
@@ -1235,7 +1240,9 @@ __device__ __forceinline__ void tail_phase(const DevView& v, uint32_t* ht, TailS
         if (tid < 5) sm.tally[tid] = __ldcg(&v.exch[tid]);
         if (tid == 5) sm.c.new_exp_bldg = __ldcg(&v.exch[5]);
         if (tid == 6) sm.c.new_exp_pt = __ldcg(&v.exch[6]);
-    } else {   // S/E/I/R/V = sum of the per-block partials (8 words per block, 4 used)
+    } else if (FUSED) {   // the blocks of k_step added their cumulative counts up in the control block
+        if (tid < 4) sm.tally[tid] = sm.c.cum[tid];
+    } else {   // S/E/I/R/V = sum of k_update's per-block partials (8 words per block, 4 used)
         uint32_t part = 0;
         for (uint32_t z = tid; z < n_partial_blocks * 8u; z += NT) part += __ldcg(&v.tally_partial[z]);
         // threads tid, tid+8, ... hold the same counter: NT is a multiple of 8
@@ -1469,16 +1476,14 @@ __device__ __forceinline__ uint32_t* mail_ll(uint32_t* mail, uint32_t t, uint32_
     return mail + MAIL_LL + 2u * ((((t & 1u) * 2u + (round & 1u)) * MAX_WORLD + shard) * FEXCH_WORDS);
 }
 
-// part: this thread's share of the per-block partial sums of k_step (threads tid, tid + 8, ... hold the same counter), loaded
-// by the caller together with the control block so that the two memory round trips overlap; sm.c / sm.mail are loaded,
-// sm.tally / sm.fix cleared.  Called by all TAIL_THREADS threads.
-__device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, TailSmem& sm, uint32_t part) {
+// sm.c / sm.mail are loaded, sm.tally / sm.fix cleared.  Called by all TAIL_THREADS threads.
+__device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, TailSmem& sm) {
     constexpr uint32_t NT = TAIL_THREADS;
     uint32_t* keys = dyn_smem;                               // [VHT] eligible owned candidates of this step
     uint32_t* minj = dyn_smem + VHT;                         // [VHT] their first draw index
     uint32_t* nib = dyn_smem + 2 * VHT;                      // [chunks * VAX_CHUNK_WORDS] this shard's marks of the round
     uint32_t* sum = nib + VAX_MAX_CHUNKS * VAX_CHUNK_WORDS;  // [FEXCH_WORDS] sum of the round's vectors over the shards
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t tid = threadIdx.x;
     const uint32_t t = sm.c.t;
     const uint64_t seed = ((uint64_t)v.mp.seed_hi << 32) | v.mp.seed_lo;
     // update_status of step t has already run (previous tail): the programme is active in this step iff vax_some
@@ -1488,13 +1493,9 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
     const uint32_t vax_start = sm.c.vax_event ? t : sm.c.vax_start_step;
     if (vaccinate)
         for (uint32_t h = tid; h < VHT; h += NT) { keys[h] = HT_EMPTY; minj[h] = 0xFFFFFFFFu; }
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    part += __shfl_xor_sync(0xffffffffu, part, 16);
-    if (lane < 8 && part) atomicAdd(&sm.tally[lane], part);
-    __syncthreads();
     if (tid < 8) {   // every one of the eight threads derives the classes itself: no extra barrier
         uint32_t cls[5];
-        classes_from_cumulative(sm.tally, v.n_pad, v.n, cls);
+        classes_from_cumulative(sm.c.cum, v.n_pad, v.n, cls);
         sm.head[tid] = tid < 5 ? cls[tid] : tid == 5 ? sm.c.new_exp_bldg : tid == 6 ? sm.c.new_exp_pt : 0u;
     }
     // chunks of the first round: enough draws for 1.25 x rate + 256 eligible candidates at the eligible share the shards
@@ -1509,7 +1510,6 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
         }
     }
     __syncthreads();
-    if (tid < 8) sm.tally[tid] = 0;   // filled from the summed vectors below
 
     KTrace ks; ks.enter = 0; ks.begin(v, t, 4);   // timeline slot 4: loads done -> first vector sent
     uint32_t K = 0, accepted = 0, base = 0;
@@ -1562,7 +1562,7 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
         __syncthreads();
         // ---- send.  The pairs double as "this shard's count pushes for step t + 1 are complete": every producer block that
         // pushed has fenced system-wide before it announced itself (signal_block_done), and this block has observed all
-        // announcements (wait_blocks_done) or the completion of the grid - no further fence is needed in front of the pairs.
+        // announcements (the poll of Ctrl::blocks_done) or the completion of the grid - no further fence is needed in front of the pairs.
         for (uint32_t h = tid; h < n_words; h += NT) {
             const uint32_t value = h < FEXCH_HEAD ? (round == 0u ? sm.head[h] : 0u) : nib[h - FEXCH_HEAD];
             for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(mail_ll(sm.mail[p], t, round, v.rank) + 2u * h, value, tag);
@@ -1681,36 +1681,123 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
     kp7.end(v, t, 7);
 }
 
-// fused pipeline: v.n_update_blocks is the grid of the kernel that left the partial sums (k_step, or k_update in the boot pass)
+// ---- the tail of an hour without vaccination picks: ONE warp, no block-wide barrier --------------------------------------------
+// Until the vaccination programme starts (and in a run without one) the tail is a handful of scalar decisions on a few counters -
+// yet it sits on the critical path between two steps, and as a 1024-thread block walking through half a dozen barrier-separated
+// phases it took 2.2 us on one GPU and 9.6 us on shards (device timeline, profiles/README.md).  Here warp 0 does all of it: load
+// the control block, (shards: send the 8 head words to every peer, wait for theirs, add them up by shuffles,) statistics entry,
+// update_status, next schedule, write back.  The other 31 warps leave at once.
+template <bool P2P>
+__device__ __forceinline__ void tail_quick(const DevView& v, TailSmem& sm) {
+    const uint32_t lane = threadIdx.x;
+    const uint32_t* gc = reinterpret_cast<const uint32_t*>(v.ctrl);
+    // everything is requested at once: the control block (two words per lane) and, by every lane, the seven words the head is
+    // made of - shards send their head before anything else is looked at
+    uint32_t cw[2];
+#pragma unroll
+    for (uint32_t r = 0; r < 2; ++r) cw[r] = lane + 32u * r < sizeof(Ctrl) / 4 ? __ldcg(gc + lane + 32u * r) : 0u;
+    static_assert(sizeof(Ctrl) / 4 <= 64, "two control-block words per lane");
+    const uint32_t t = __ldcg(&v.ctrl->t);
+    uint32_t cum[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cum[k] = __ldcg(&v.ctrl->cum[k]);
+    const uint32_t exp_b = __ldcg(&v.ctrl->new_exp_bldg), exp_pt = __ldcg(&v.ctrl->new_exp_pt);
+    uint32_t cls[5];
+    classes_from_cumulative(cum, v.n_pad, v.n, cls);   // class counts of step t + 1 as k_step counted them on this shard
+    uint32_t total = 0;
+    if (P2P) {
+        const uint32_t tag = t + 1u, h = lane & 7u;
+        const uint32_t mine = h < 5u ? cls[h] : h == 5u ? exp_b : h == 6u ? exp_pt : 0u;
+        KTrace ks; ks.enter = 0; ks.begin(v, t, 4);
+        if (lane < FEXCH_HEAD)
+            for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(mail_ll(v.mail[p], t, 0u, v.rank) + 2u * lane, mine, tag);
+        ks.end(v, t, 4);
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < 2; ++r)
+        if (lane + 32u * r < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[lane + 32u * r] = cw[r];
+    if (lane < 8) { sm.tally[lane] = 0; sm.fix[lane] = 0; }
+    if (P2P) {
+        const uint32_t tag = t + 1u, h = lane & 7u;
+        KTrace kx; kx.enter = 0; kx.begin(v, t, 1);
+        if (ESIM_QUICK_SEND_DELAY) __nanosleep(ESIM_QUICK_SEND_DELAY);
+        // pair (shard s, word h) is read by lane 8 (s mod 4) + h, shards 4..7 in a second round; both rounds are requested before
+        // the first tag is examined
+        const uint32_t* own = mail_ll(v.mail[v.rank], t, 0u, 0u);
+        uint32_t val[2] = {0u, 0u}, seen[2] = {tag, tag};
+#pragma unroll
+        for (uint32_t r = 0; r < 2; ++r) {
+            const uint32_t shard = (lane >> 3) + 4u * r;
+            if (shard < v.world) ld_pair_sys(own + 2u * (shard * FEXCH_WORDS + h), val[r], seen[r]);
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < 2; ++r) {
+            const uint32_t shard = (lane >> 3) + 4u * r;
+            if (shard < v.world && seen[r] != tag) val[r] = ld_pair_wait(v, own + 2u * (shard * FEXCH_WORDS + h), tag);
+        }
+        total = val[0] + val[1];
+        total += __shfl_xor_sync(0xffffffffu, total, 8);
+        total += __shfl_xor_sync(0xffffffffu, total, 16);
+        kx.end(v, t, 1);
+    }
+    __syncwarp();   // sm.c is complete
+    if (P2P) {
+        if (lane < 5) sm.tally[lane] = total;
+        if (lane == 5) sm.c.new_exp_bldg = total;
+        if (lane == 6) sm.c.new_exp_pt = total;
+    } else if (lane < 5) {
+        sm.tally[lane] = cls[lane];
+    }
+    __syncwarp();
+    if (lane == 0) { tail_record<true>(v, sm); tail_epilogue<true>(v, sm); }   // no programme: no picks
+    __syncwarp();
+    for (uint32_t i = lane; i < sizeof(Ctrl) / 4; i += 32u)
+        if (writes_back(sm, i)) reinterpret_cast<uint32_t*>(v.ctrl)[i] = reinterpret_cast<const uint32_t*>(&sm.c)[i];
+    if (lane < sizeof(EsimStepStats) / 4 && t - 1 < v.max_steps)
+        reinterpret_cast<uint32_t*>(&v.stats[t - 1])[lane] = reinterpret_cast<const uint32_t*>(&sm.stats)[lane];
+    // "No corrections of mine are in flight" (see tail_p2p): the peers' k_step only waits for it while the programme runs, so
+    // this tail only has to say it if its own update_status has just started the programme.
+    if (P2P && (v.n_shared_b | v.n_shared_r) && sm.c.vax_some && lane < v.world && lane != v.rank)
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(v.mail[lane] + MAIL_FLAG_C + v.rank), "r"(t + 1u) : "memory");
+}
+
+// the tail of the fused pipeline (k_tail_fused, k_tail_fused_p2p)
 template <bool P2P>
 __device__ __forceinline__ void tail_fused_body(const DevView& v) {
     KTrace kt; kt.start(v);
     extern __shared__ uint32_t dyn_smem[];
     __shared__ TailSmem sm;
+    if (v.tail_flag_wait) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else pdl_prologue();
+    // finished / abort_graph / t / vax_some are only ever written by a tail: stable since the previous one completed (a tail that
+    // polls is launched once that one has completed, see pdl_prologue_wait_first)
+    if (v.ctrl->finished | v.ctrl->abort_graph) return;    // k_step left without announcing anything either
+    const uint32_t kt_t = v.ctrl->t;
+    // update_status of step t has already run (previous tail): picks are drawn in this step iff the programme is active
+    const bool quick = !(v.ctrl->vax_some != 0 && kt_t != 0u);
+    if (quick && threadIdx.x >= 32u) return;
     if (v.tail_flag_wait) {
-        // finished / abort_graph / t are only ever written by a tail: stable since the previous one completed
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (v.ctrl->finished | v.ctrl->abort_graph) return;    // k_step left without announcing anything either
         KTrace kp; kp.enter = 0;
         if (v.ktrace_min && threadIdx.x == 0) kp.enter = global_ns();   // timeline slot 5: control block read -> counter complete
-        wait_blocks_done(v, v.n_update_blocks);                  // see signal_block_done
-        if (v.ktrace_min) { kp.begin(v, v.ctrl->t, 5); kp.end(v, v.ctrl->t, 5); }
-    } else {
-        pdl_prologue();
-        if (v.ctrl->finished | v.ctrl->abort_graph) return;
+        if (threadIdx.x == 0) {   // see signal_block_done
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(&v.ctrl->blocks_done) < v.n_update_blocks)
+                if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_SIMULATION); break; }   // never hang the GPU
+        }
+        if (quick) __syncwarp(); else __syncthreads();
+        if (v.ktrace_min) { kp.begin(v, kt_t, 5); kp.end(v, kt_t, 5); }
     }
-    const uint32_t kt_t = v.ctrl->t;
     kt.begin(v, kt_t, 3);
-    if (P2P) {
-        // one memory round trip for everything the tail needs before it can send: control block, mailbox pointers, partial sums
+    if (quick) {
+        tail_quick<P2P>(v, sm);
+    } else if (P2P) {
+        // one memory round trip for everything the tail needs before it can send: control block, mailbox pointers
         const uint32_t tid = threadIdx.x;
         if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + tid);
         if (tid >= 64 && tid < 64 + MAX_WORLD) sm.mail[tid - 64] = v.peer->mail[tid - 64];
-        uint32_t part = 0;
-        for (uint32_t z = tid; z < v.n_update_blocks * 8u; z += TAIL_THREADS) part += __ldcg(&v.tally_partial[z]);
-        if (tid >= 32 && tid < 40) { sm.tally[tid - 32] = 0; sm.fix[tid - 32] = 0; }
+        if (tid >= 96 && tid < 104) { sm.tally[tid - 96] = 0; sm.fix[tid - 96] = 0; }
         __syncthreads();
-        tail_p2p(v, dyn_smem, sm, part);
+        tail_p2p(v, dyn_smem, sm);
     } else {
         tail_phase<TAIL_THREADS, true>(v, dyn_smem, sm, v.n_update_blocks);
     }

@@ -32,6 +32,7 @@ Prints ONE JSON line.  Keys beyond the driver's contract:
                     equals the CPU oracle bit for bit (statistics of every step and the per-citizen state).
   weak_scaling_reference (N > 1, weak scaling)  the per-GPU workload on ONE GPU without shards, measured in the same run by
                     rank 0: value(N) / (N x this) is the parallel efficiency on the SAME per-GPU workload.
+  strong_scaling_reference (N > 1, strong scaling)  the WHOLE population on one GPU: value(N) / (N x this) is the efficiency.
   cpu_baseline      the CPU oracle (a port of the reference's push loop, OpenMP over output areas) on a bounded number of
                     steps of the same workload on this box's host cores (N = 1 only).
 
@@ -163,8 +164,10 @@ def algorithmic_bytes(stats, n_citizens, n_cells, shard_fraction=1.0):
     k_update: 4 B state word per citizen + 8 B (position id + count update) per infected citizen + 4 B per cell (zeroing).
     k_expose: 4 B state word per citizen + 8 B (household + workplace ids) per susceptible citizen + 4 B per cell (every
               infected count is needed from HBM once; citizens sharing a household / workplace share the fetch).
-    k_step  : the fused pass = both of the above with the state word read once:
-              4 B per citizen + 8 B per susceptible + 8 B per infected + 8 B per cell (count gathers + zeroing)."""
+    k_step  : the fused pass = both of the above with the state word read once and the household ids read as one id per quad
+              (round 2: 1 B per citizen instead of 4):
+              4 B per citizen + 5 B per susceptible + 8 B per infected + 8 B per cell (count gathers + zeroing).
+              `fused_r01` is the same launches with the round-1 layout's bytes (8 B per susceptible), for comparison only."""
     from epidemicsimulator_b200 import _abi
     f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
     # the recorded statistics are global: a shard holds its share of the susceptible / infected citizens (the shards are
@@ -173,8 +176,9 @@ def algorithmic_bytes(stats, n_citizens, n_cells, shard_fraction=1.0):
     infected = stats[:, f["infected"]] * shard_fraction
     upd = 4.0 * n_citizens + 8.0 * infected + 4.0 * n_cells
     exp = 4.0 * n_citizens + 8.0 * s_before + 4.0 * n_cells
-    fused = 4.0 * n_citizens + 8.0 * s_before + 8.0 * infected + 8.0 * n_cells
-    return upd, exp, fused
+    fused = 4.0 * n_citizens + 5.0 * s_before + 8.0 * infected + 8.0 * n_cells
+    fused_r01 = 4.0 * n_citizens + 8.0 * s_before + 8.0 * infected + 8.0 * n_cells
+    return upd, exp, fused, fused_r01
 
 
 def traffic_from_profile(kernel):
@@ -351,12 +355,15 @@ def main():
         return tm, st, done
 
     def roofline_of(tm, st, p, steps_run, peak, peak_src, share=1.0, traffic=None):
-        _, _, fused_b = algorithmic_bytes(st[:steps_run], p.n_citizens, p.n_buildings + p.n_rooms, share)
+        _, _, fused_b, fused_r01 = algorithmic_bytes(st[:steps_run], p.n_citizens, p.n_buildings + p.n_rooms, share)
         dom_bytes, dom_s = float(fused_b.sum()), tm["k_expose"]
         achieved = dom_bytes / dom_s / 1e9 if dom_s > 0 else 0.0
         return {"bound": "hbm", "kernel": "k_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes / max(steps_run, 1),
-                "avg_launch_us": dom_s / max(steps_run, 1) * 1e6, "citizens": p.n_citizens, "launches": steps_run}
+                "avg_launch_us": dom_s / max(steps_run, 1) * 1e6, "citizens": p.n_citizens, "launches": steps_run,
+                "frac_at_round1_layout_bytes": float(fused_r01.sum()) / dom_s / 1e9 / peak if dom_s > 0 else 0.0,
+                "note": "bytes of the round-2 layout (household ids as one id per quad + one bit per citizen: 5 B instead of 8 B per "
+                        "susceptible citizen); frac_at_round1_layout_bytes divides the round-1 layout's bytes by the same time"}
 
     # ---- warm-up on a throw-away handle (module load, graph capture, clocks) --------------------------------------
     w = max(args.warmup, 3)
@@ -490,6 +497,36 @@ def main():
                 "what": "the per-GPU workload on ONE GPU without shards (rank 0's GPU, same run, same timing, the other ranks idle)",
                 "citizens": one.n_citizens, "value": one.n_citizens * n1 / t1, "ms_per_step": t1 / max(n1, 1) * 1e3,
                 "value_graph_replay": one.n_citizens * ng1 / tg1, "graph_replay_ms_per_step": tg1 / max(ng1, 1) * 1e3}
+        elif wl["scaling"] == "strong":
+            # the WHOLE population on rank 0's GPU, no shards: the denominator of the strong-scaling efficiency
+            from epidemicsimulator_b200.population import DevicePopulation
+            g1 = DevicePopulation(wl["n_areas"], POP_SEED, wl["areas_per_school"], wl["cross_area_fraction"], device=local_rank)
+
+            def single(flags):
+                s1 = Simulator(default_config(flags=flags, **cfg_kwargs))
+                s1.import_device_population(g1)
+                return s1
+            s1 = single(_abi.CFG_FLUSH_L2)
+            s1.run_timed(w)
+            s1.close()
+            s1 = single(_abi.CFG_FLUSH_L2)
+            n1 = s1.run_timed(min(steps_run, 240))
+            t1 = s1.timings()["total"]
+            s1.close()
+            s1 = single(0)
+            s1.run(w)
+            torch.cuda.synchronize()
+            tg0 = time.perf_counter()
+            ng1 = s1.run(min(args.steps, 480))
+            torch.cuda.synchronize()
+            tg1 = time.perf_counter() - tg0
+            s1.close()
+            g1.close()
+            extra["strong_scaling_reference"] = {
+                "what": "the whole population on ONE GPU without shards (rank 0's GPU, same run, same timing, imported straight from the "
+                        "device-side generator; the other ranks idle)",
+                "citizens": n_total, "value": n_total * n1 / t1, "ms_per_step": t1 / max(n1, 1) * 1e3, "steps": n1,
+                "value_graph_replay": n_total * ng1 / tg1, "graph_replay_ms_per_step": tg1 / max(ng1, 1) * 1e3}
     if world > 1:
         dist.barrier()
 
@@ -512,7 +549,7 @@ def main():
                                traffic_from_profile("k_step") if wl["config"] == "baseline" and not args.areas else None)
         else:
             kernel_seconds = {k: tm[k] for k in ("k_update", "k_expose", "k_pt", "k_tail")}
-            upd_b, exp_b, _ = algorithmic_bytes(stats, pop.n_citizens, n_cells, share)
+            upd_b, exp_b, _, _ = algorithmic_bytes(stats, pop.n_citizens, n_cells, share)
             dominant = "k_expose" if tm["k_expose"] >= tm["k_update"] else "k_update"
             dom_bytes = float(exp_b.sum() if dominant == "k_expose" else upd_b.sum())
             dom_s = tm[dominant]

@@ -67,7 +67,7 @@ def nvcc() -> str:
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in CUDA_SOURCES]
     build_host()   # libesim_b200.so links against the host library (sharding for multi-device handles)
-    deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h", HOST_LIB] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
+    deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h", INCLUDE / "esim_popgen_device.h", HOST_LIB] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",

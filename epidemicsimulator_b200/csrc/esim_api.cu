@@ -20,6 +20,7 @@
 
 #include "esim.h"
 #include "esim_popgen.h"
+#include "esim_popgen_device.h"
 #include "esim_import.h"
 #include "esim_internal.h"
 #include "pt_spans.h"
@@ -132,7 +133,7 @@ struct EsimSim {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevView v{};
-    DevBuf<uint32_t> cstate, home_cell, work_cell, room_parent, cnt_all, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
+    DevBuf<uint32_t> cstate, home_cell, work_cell, home_base, room_parent, cnt_all, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
         rec_bus, rec_businf;
     DevBuf<unsigned long long> thr;
     DevBuf<uint4> pt_span;              // public transport: whole routes packed into spans of <= 128 riders (see pt_phase)
@@ -209,7 +210,7 @@ struct EsimSim {
         for (void* m : peer_mappings) cudaIpcCloseMemHandle(m);
         exch.release(); vax_cand.release(); peer_mail.release(); peer_view.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        cstate.release(); home_cell.release(); work_cell.release(); room_parent.release(); cnt_all.release(); tally_partial.release();
+        cstate.release(); home_cell.release(); work_cell.release(); home_base.release(); room_parent.release(); cnt_all.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
         pt_span.release(); pt_seg.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
@@ -585,7 +586,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         if (R) CK(cudaMemcpyAsync(s->room_parent.p, p->room_bldg, (size_t)R * 4, cudaMemcpyDefault, st));
 
         tr.mark("upload raw arrays", st);
-        s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad);
+        s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad); s->home_base.alloc(n_pad / 4);
         is_rider.alloc(n_pad); route_key.alloc(n_pad); d_small.alloc(8);
         cleanup.f.push_back([&] { is_rider.release(); route_key.release(); d_small.release(); keys_in.release(); keys_out.release();
                                   rider_idx.release(); head.release(); temp.release(); });
@@ -595,7 +596,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         raw.home = r_home.p; raw.work = r_work.p; raw.room = r_room.p; raw.global_id = r_gid.p; raw.bldg_area = r_area.p;
         raw.room_bldg = s->room_parent.p; raw.flags = r_flags.p; raw.status = r_status.p; raw.bldg_type = r_btype.p; raw.timer = r_timer.p;
         ImportOut out{};
-        out.n_pad = n_pad; out.cstate = s->cstate.p; out.home_cell = s->home_cell.p; out.work_cell = s->work_cell.p;
+        out.n_pad = n_pad; out.cstate = s->cstate.p; out.home_cell = s->home_cell.p; out.work_cell = s->work_cell.p; out.home_base = s->home_base.p;
         out.is_rider = is_rider.p; out.route_key = route_key.p;
         uint32_t* d_err = d_small.p;        // [0] code, [1] index
         uint32_t* d_count = d_small.p + 4;  // [4] riders, [5] routes
@@ -705,7 +706,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         v.n_routes = n_routes; v.n_riders = n_riders; v.record_buses = rec ? 1u : 0u;
         v.next_has_pt = 1;   // every launch sequence has a public-transport kernel unless a specialised graph says otherwise
         v.has_pt = 1;        // (conservative default: the fused tail then waits for the grid in front of it)
-        v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p;
+        v.cstate = s->cstate.p; v.home_cell = s->home_cell.p; v.work_cell = s->work_cell.p; v.home_base = s->home_base.p;
         v.room_parent = s->room_parent.p; v.cnt[0] = s->cnt_all.p; v.cnt[1] = s->cnt_all.p + s->cnt_stride; v.cnt[2] = s->cnt_all.p + 2 * s->cnt_stride;
         v.fused = s->fused ? 1u : 0u; v.boot = 0; v.thr = s->thr.p;
         v.n_spans = n_spans; v.pt_span = s->pt_span.p; v.pt_seg = s->pt_seg.p;
@@ -733,7 +734,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         v.peer_timeout_ns = s->peer_timeout_ns;
         v.n_update_blocks = update_blocks(v);
 
-        s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() +
+        s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->home_base.bytes() +
                           s->room_parent.bytes() + s->cnt_all.bytes() + s->route_off.bytes() + s->riders.bytes() * 4 +
                           s->rec_bus.bytes() * 2 + s->stats.bytes();
         // fused pipeline: count step 1 and lay out the first schedule (k_update + k_boot_fused), once

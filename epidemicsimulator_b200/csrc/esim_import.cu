@@ -77,6 +77,24 @@ __global__ void __launch_bounds__(256) k_import(ImportRaw r, ImportOut o, uint32
     o.route_key[i] = key;
 }
 
+// household ids of a quad as one id + one bit per citizen (esim_internal.h, CS_HOME_STEP); one thread per quad
+__global__ void __launch_bounds__(256) k_home_quads(ImportOut o, uint32_t n) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (o.n_pad >> 2)) return;
+    const uint4 h4 = reinterpret_cast<const uint4*>(o.home_cell)[q];
+    const uint32_t h[4] = {h4.x, h4.y, h4.z, h4.w};
+    o.home_base[q] = h[0];
+    bool irregular = false;
+    for (uint32_t k = 1; k < 4; ++k) {
+        const uint32_t i = 4u * q + k;
+        if (i >= n) break;                       // padding slots are never looked at
+        const uint32_t d = h[k] - h[k - 1];
+        if (d == 1u) o.cstate[i] |= CS_HOME_STEP;
+        else if (d != 0u) irregular = true;
+    }
+    if (irregular) o.cstate[4u * q] |= CS_HOME_IRREGULAR;
+}
+
 __global__ void __launch_bounds__(256) k_gather_keys(const uint32_t* __restrict__ rider_idx, const unsigned long long* __restrict__ key_of_citizen,
                                                       unsigned long long* __restrict__ keys, uint32_t n_riders) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,6 +141,7 @@ cudaError_t import_convert(const ImportRaw& raw, const ImportOut& out, uint32_t*
     const uint32_t cells = raw.n_bldg > raw.n_rooms ? raw.n_bldg : raw.n_rooms;
     k_check_cells<<<(cells + 255) / 256, 256, 0, s>>>(raw, d_err);
     k_import<<<(out.n_pad + 255) / 256, 256, 0, s>>>(raw, out, d_err);
+    k_home_quads<<<((out.n_pad >> 2) + 255) / 256, 256, 0, s>>>(out, raw.n);
     return cudaGetLastError();
 }
 

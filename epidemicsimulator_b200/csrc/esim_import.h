@@ -18,7 +18,7 @@ struct ImportRaw {   // device copies of the EsimPopulationSoA arrays (nullable 
 
 struct ImportOut {
     uint32_t n_pad;
-    uint32_t *cstate, *home_cell, *work_cell;
+    uint32_t *cstate, *home_cell, *work_cell, *home_base;   // home_base: [n_pad / 4]
     uint8_t* is_rider;                 // [n_pad]
     unsigned long long* route_key;     // [n_pad] (home area << 32 | work area) of riders
 };

@@ -22,6 +22,7 @@ namespace esim {
 //   bit   18     is_mask_compliant           (static, citizen.rs:131)
 //   bit   19     household and workplace stand in the same output area (static; the simulator.rs:324 filter)
 //   bit   20     workplace_code != household_code (static)
+//   bits  21,22  household id pattern of the quad (static, see CS_HOME_STEP)
 //   padding slots hold CS_PADDING (counted as vaccinated by k_update and subtracted again by the tail)
 //
 // With d = time_step - (E - EXPOSURE_BIAS):  d <= exposed_time                     -> Exposed(d)
@@ -38,6 +39,11 @@ constexpr uint32_t CS_USES_PT     = 1u << 17;
 constexpr uint32_t CS_COMPLIANT   = 1u << 18;
 constexpr uint32_t CS_SAME_AREA   = 1u << 19;
 constexpr uint32_t CS_HAS_WORK    = 1u << 20;
+// households in the stream of k_step: citizens are stored in household order, so inside a quad the household id of a citizen
+// is its predecessor's (+ 0 or + 1); k_step reads ONE id per quad (DevView::home_base, 1 byte per citizen instead of 4) and
+// these bits.  A quad whose ids do not follow the pattern is marked and read in full from home_cell.
+constexpr uint32_t CS_HOME_STEP      = 1u << 21;   // citizens 1..3 of a quad: household id = predecessor's + 1 (clear: the same)
+constexpr uint32_t CS_HOME_IRREGULAR = 1u << 22;   // citizen 0 of a quad: read the quad's ids from home_cell
 constexpr uint32_t CS_PADDING     = 0xFFFFu;
 constexpr uint32_t EXPOSURE_BIAS  = 1024;   // > exposed_time + infected_time + 2
 constexpr uint32_t MAX_STEPS      = CS_EXPOSURE - EXPOSURE_BIAS - 1;
@@ -139,6 +145,7 @@ struct DevView {
     uint32_t tail_flag_wait;  // fused tail: poll Ctrl::blocks_done instead of waiting for the k_step grid to drain
     uint32_t* cstate;      // [n_pad]
     const uint32_t* home_cell;   // [n_pad] building id
+    const uint32_t* home_base;   // [n_pad / 4] household id of the first citizen of every quad (see CS_HOME_STEP)
     const uint32_t* work_cell;   // [n_pad] building id, or n_bldg + room id for school members
     const uint32_t* room_parent; // [n_rooms] school building of a room
     uint32_t* cnt[3];      // [n_cells] x 2 (x 3 fused): infected occupants present per building / room.  Step t accumulates into

@@ -432,6 +432,22 @@ __device__ __forceinline__ uint32_t expose_quad(const DevView& v, const uint32_t
     return trial_quad(v, cnt, q, w, k4, n_h, n_w, t, mask_everywhere);
 }
 
+// household ids of a quad from the id of its first citizen and the step bits of the state words (CS_HOME_STEP); a quad that
+// does not follow the pattern (the first citizens of an output area, a hand-built population) is read in full
+#ifndef ESIM_COMPACT_HOME
+#define ESIM_COMPACT_HOME 1   // 0: k_step reads the four household ids of every quad (A/B builds)
+#endif
+__device__ __forceinline__ uint4 home_quad(const DevView& v, uint32_t q, uint32_t base, const uint4 w) {
+    if (!ESIM_COMPACT_HOME || (w.x & CS_HOME_IRREGULAR)) return __ldg(reinterpret_cast<const uint4*>(v.home_cell) + q);
+    uint4 h;
+    h.x = base;
+    h.y = h.x + ((w.y >> 21) & 1u);
+    h.z = h.y + ((w.z >> 21) & 1u);
+    h.w = h.z + ((w.w >> 21) & 1u);
+    return h;
+}
+static_assert(CS_HOME_STEP == 1u << 21, "home_quad shifts by 21");
+
 __device__ __forceinline__ bool any_susceptible(const uint4 w) {
     return is_susceptible(w.x) || is_susceptible(w.y) || is_susceptible(w.z) || is_susceptible(w.w);
 }
@@ -554,7 +570,7 @@ __device__ __forceinline__ void step_stream(const DevView& v, const Ctrl* __rest
     const uint32_t T = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x, lane = lane_id();
     const uint32_t n_quads = v.n_pad >> 2;
     const uint4* __restrict__ cs4 = reinterpret_cast<const uint4*>(v.cstate);
-    const uint4* __restrict__ hc4 = reinterpret_cast<const uint4*>(v.home_cell);
+    const uint32_t* __restrict__ hb = v.home_base;
     const uint4* __restrict__ wc4 = reinterpret_cast<const uint4*>(v.work_cell);
     const uint32_t t = c->t, t1 = t + 1u;
     StepCtx x;
@@ -581,10 +597,11 @@ __device__ __forceinline__ void step_stream(const DevView& v, const Ctrl* __rest
         const bool have0 = q0 < n_quads, have1 = q1 < n_quads;
         const uint4 wa = have0 ? cs4[q0] : pad4;
         const uint4 wb = have1 ? cs4[q1] : pad4;
-        uint4 ha = zero4, ka = zero4, hb = zero4, kb = zero4;
+        uint4 ka = zero4, kb = zero4;
+        uint32_t ba = 0, bb = 0;   // household id of the first citizen of each quad
         if (EAGER) {
-            if (have0) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
-            if (have1) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
+            if (have0) { ba = __ldg(hb + q0); ka = __ldg(wc4 + q0); }
+            if (have1) { bb = __ldg(hb + q1); kb = __ldg(wc4 + q1); }
         }
         if (!zeroed) {
             // the count buffer of step t + 2 (nothing in this launch reads it): behind the first loads, far from the final fence
@@ -594,13 +611,13 @@ __device__ __forceinline__ void step_stream(const DevView& v, const Ctrl* __rest
         const uint32_t w[2][4] = {{wa.x, wa.y, wa.z, wa.w}, {wb.x, wb.y, wb.z, wb.w}};
         const bool sa = any_susceptible(wa), sb = any_susceptible(wb);
         if (!EAGER) {
-            if (sa) { ha = __ldg(hc4 + q0); ka = __ldg(wc4 + q0); }
-            if (sb) { hb = __ldg(hc4 + q1); kb = __ldg(wc4 + q1); }
+            if (sa) { ba = __ldg(hb + q0); ka = __ldg(wc4 + q0); }
+            if (sb) { bb = __ldg(hb + q1); kb = __ldg(wc4 + q1); }
         }
         // ---- apply_exposures of step t: the infected counts of every source of both quads are requested together
         uint32_t n_h[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, n_w[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
-        if (sa) gather_quad<AT_WORK>(x.cnt, w[0], ha, ka, n_h[0], n_w[0]);
-        if (sb) gather_quad<AT_WORK>(x.cnt, w[1], hb, kb, n_h[1], n_w[1]);
+        if (sa) gather_quad<AT_WORK>(x.cnt, w[0], home_quad(v, q0, ba, wa), ka, n_h[0], n_w[0]);
+        if (sb) gather_quad<AT_WORK>(x.cnt, w[1], home_quad(v, q1, bb, wb), kb, n_h[1], n_w[1]);
         uint32_t need = 0;   // bit 4 u + k: the citizen has an infected room-mate somewhere
 #pragma unroll
         for (int u = 0; u < 2; ++u)

@@ -27,8 +27,7 @@
 
 #include <cub/cub.cuh>
 
-#include "esim.h"
-#include "esim_popgen.h"
+#include "esim_popgen_device.h"
 
 namespace {
 

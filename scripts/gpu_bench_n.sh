@@ -9,7 +9,7 @@ d=json.loads([l for l in open('gpurun_out/bench_$TAG.json') if l.startswith('{')
 st=d['config']['steps_executed']
 print('N', d['n_gpus'], 'flushed us/step', round(d['ms_per_step']*1e3,2), 'replay us/step', round(d['graph_replay_ms_per_step']*1e3,2), 'value', '%.4e'%d['value'], 'replay', '%.4e'%d['value_graph_replay'], 'parity', d['parity_checked'])
 print({k: round(v/st*1e6,2) for k,v in d['kernel_seconds'].items()})
-w=d.get('weak_scaling_reference')
-if w: print('1-GPU same workload: flushed', round(w['ms_per_step']*1e3,2), 'replay', round(w['graph_replay_ms_per_step']*1e3,2), 'eff flushed %.3f replay %.3f' % (d['value']/(d['n_gpus']*w['value']), d['value_graph_replay']/(d['n_gpus']*w['value_graph_replay'])))
+w=d.get('weak_scaling_reference') or d.get('strong_scaling_reference')
+if w: print('1-GPU reference (%s): flushed' % ('weak: per-GPU workload' if 'weak_scaling_reference' in d else 'strong: whole population'), round(w['ms_per_step']*1e3,2), 'replay', round(w['graph_replay_ms_per_step']*1e3,2), 'eff flushed %.3f replay %.3f' % (d['value']/(d['n_gpus']*w['value']), d['value_graph_replay']/(d['n_gpus']*w['value_graph_replay'])))
 print('e2e', d['e2e']['seconds'], d['e2e']['setup_seconds'], 'popgen', d['config']['population_seconds'])
 PY

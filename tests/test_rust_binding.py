@@ -9,7 +9,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 LIB_RS = (ROOT / "integration/rust/sim-b200-sys/src/lib.rs").read_text()
 ESIM_H = (ROOT / "include/esim.h").read_text()
-POPGEN_H = (ROOT / "include/esim_popgen.h").read_text()
+POPGEN_H = (ROOT / "include/esim_popgen.h").read_text() + (ROOT / "include/esim_popgen_device.h").read_text()
 
 C_TO_RUST = {"double": "f64", "uint32_t": "u32", "uint64_t": "u64", "int32_t": "i32", "uint8_t": "u8", "uint16_t": "u16", "int": "c_int",
              "const uint32_t*": "*const u32", "const uint8_t*": "*const u8", "const uint16_t*": "*const u16",

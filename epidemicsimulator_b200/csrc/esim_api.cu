@@ -662,7 +662,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         // three count buffers in one allocation (one CUDA IPC handle for peers); sharded handles decide at connect time
         // whether they run fused (esim_peer_connect) or not (esim_comm_init, esim_shard_step_*)
         s->cnt_stride = ((size_t)B + R + 4 + 31) & ~(size_t)31;
-        s->cnt_all.alloc(3 * s->cnt_stride, sharded_pop);
+        s->cnt_all.alloc(3 * s->cnt_stride, sharded_pop || getenv("ESIM_PLAIN_CNT") != nullptr);   // (env: A/B of the allocator, profiles/README.md)
         s->fused = p->n_shards <= 1 && !(s->cfg.flags & ESIM_CFG_UNFUSED) && !getenv("ESIM_UNFUSED");   // (the env switch: the GPU parity suite runs every test on both pipelines)
         if (sharded_pop) { s->peer_mail.alloc(MAIL_WORDS, true); CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st)); }
         s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
@@ -733,6 +733,13 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         v.share = s->share; v.no_pdl = s->no_pdl ? 1u : 0u; v.sync_seq = 0;
         v.peer_timeout_ns = s->peer_timeout_ns;
         v.n_update_blocks = update_blocks(v);
+        {   // streams (state word, workplace id, household id per quad) + the three count buffers against the L2
+            int l2 = 0;
+            CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, s->device));
+            const size_t working_set = (size_t)n_pad * 9 + (size_t)(B + R) * 12;
+            v.pf_next = (l2 > 0 && working_set > (size_t)l2 * 3 / 4) ? 1u : 0u;
+            if (const char* e = getenv("ESIM_STEP_PF_NEXT")) v.pf_next = e[0] == '1';
+        }
 
         s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->home_base.bytes() +
                           s->room_parent.bytes() + s->cnt_all.bytes() + s->route_off.bytes() + s->riders.bytes() * 4 +

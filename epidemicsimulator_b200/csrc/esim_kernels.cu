@@ -513,9 +513,6 @@ __global__ void __launch_bounds__(EXPOSE_THREADS, 4) k_expose(const DevView v) {
 // have been issued - not in front of them, and not at the end of the kernel, where the block's announcement fence
 // (signal_block_done) would have to wait for them (12 % of the stall samples of the round-1 build).
 constexpr int STEP_THREADS = 256;
-#ifndef ESIM_STEP_PF_NEXT
-#define ESIM_STEP_PF_NEXT 0
-#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ---- the trial queue of a warp --------------------------------------------------------------------------------------------
@@ -611,10 +608,11 @@ __device__ __forceinline__ void step_stream(const DevView& v, const Ctrl* __rest
             zeroed = true;
             for (uint32_t z = gtid; z < ((v.n_cells + 3u) >> 2); z += T) cnt_zero[z] = zero4;
         }
-#if ESIM_STEP_PF_NEXT
         // the streams of the NEXT iteration, requested behind this iteration's demand loads (L2 prefetches hold no register):
-        // a cold step is a chain of dependent round trips (stream -> counts) per iteration, this lets the chains overlap
-        {
+        // when the working set does not fit the L2 a step is a chain of dependent HBM round trips (stream -> counts) per
+        // iteration, and this lets the chains overlap (8.4 M citizens: 29.0 -> 27.7 us per launch, replay 25.7 -> 25.2 us per
+        // hour).  With an L2-resident working set the extra requests only cost (3.45 M: replay 12.5 -> 13.2 us): DevView::pf_next.
+        if (v.pf_next) {
             const uint32_t n0 = q0 + 2u * T, n1 = q1 + 2u * T;
             if ((lane & 7u) == 0u) {
                 if (n0 < n_quads) { prefetch_l2(cs4 + n0); if (EAGER) prefetch_l2(wc4 + n0); }
@@ -625,7 +623,6 @@ __device__ __forceinline__ void step_stream(const DevView& v, const Ctrl* __rest
                 if (n1 < n_quads) prefetch_l2(hb + n1);
             }
         }
-#endif
         const uint32_t w[2][4] = {{wa.x, wa.y, wa.z, wa.w}, {wb.x, wb.y, wb.z, wb.w}};
         const bool sa = any_susceptible(wa), sb = any_susceptible(wb);
         if (!EAGER) {

@@ -373,6 +373,13 @@ def main():
     sim.run_timed(w)
     sim.run(w)
     sim.close()
+    # ... and one untimed pass of the end-to-end sequence from pageable arrays: the first one in a process creates the
+    # staged-copy pool (page-locked staging buffers, worker streams) and grows the device memory pool by the export buffers
+    sim = make_sim(pop)
+    sim.run(w)
+    sim.statistics()
+    sim.state(out=Simulator.state_buffers(pop.n_citizens, pinned=False))
+    sim.close()
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -577,7 +584,9 @@ def main():
                     "d2h_bytes_per_step": e2e["d2h"] / max(e2e["steps"], 1), "seconds": e2e["seconds"],
                     "setup_seconds": e2e["setup_seconds"], "run_seconds": e2e["run_seconds"], "readback_seconds": e2e["readback_seconds"],
                     "host_memory": "pageable",
-                    "what": "esim_create + esim_import_population(pageable host SoA)%s + esim_run(%d) + esim_read_stats + esim_read_state" % (
+                    "what": "esim_create + esim_import_population(pageable host SoA)%s + esim_run(%d) + esim_read_stats + esim_read_state "
+                            "into pageable arrays nobody has touched (the library stages pageable transfers through page-locked buffers "
+                            "with a few worker threads, csrc/esim_hostcopy.cu)" % (
                         " + peer set-up (IPC handles, boot pass, graph capture)" if world > 1 else "", args.steps)},
             "e2e_pinned": {"value": n_total * e2e_pin["steps"] / e2e_pin["seconds"], "unit": UNIT, "seconds": e2e_pin["seconds"],
                            "setup_seconds": e2e_pin["setup_seconds"], "run_seconds": e2e_pin["run_seconds"], "host_memory": "page-locked"},

@@ -21,7 +21,7 @@ INCLUDE = ROOT / "include"
 CUDA_LIB = PKG / "libesim_b200.so"
 HOST_LIB = PKG / "libesim_host.so"
 
-CUDA_SOURCES = ["esim_kernels.cu", "esim_import.cu", "esim_api.cu", "esim_popgen_device.cu"]
+CUDA_SOURCES = ["esim_kernels.cu", "esim_import.cu", "esim_hostcopy.cu", "esim_api.cu", "esim_popgen_device.cu"]
 HOST_SOURCES = ["popgen.cpp", "population_io.cpp"]
 
 
@@ -64,21 +64,45 @@ def nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off"]
+OBJ_DIR = PKG / "_obj"   # object files (git- and gpurun-ignored): one per source, so that an edit recompiles one file
+
+
+def _compile_objects(tag: str, defines, force: bool, verbose: bool):
+    """One nvcc -c per source, in parallel; an object is reused while it is newer than its source and every header."""
+    from concurrent.futures import ThreadPoolExecutor
+    OBJ_DIR.mkdir(exist_ok=True)
+    headers = [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h", INCLUDE / "esim_popgen_device.h", Path(__file__)] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
+    jobs, objs = [], []
+    for name in CUDA_SOURCES:
+        src = CSRC / name
+        obj = OBJ_DIR / ("%s%s.o" % (Path(name).stem, tag))
+        objs.append(obj)
+        if force or not _newer(obj, [src] + headers):
+            cmd = [nvcc()] + NVCC_FLAGS + ["-ccbin", host_compiler(), "-I", str(INCLUDE), "-I", str(CSRC)] + ["-D" + d for d in defines]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            jobs.append(cmd + ["-c", str(src), "-o", str(obj)])
+    with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as ex:
+        outs = list(ex.map(_run, jobs))
+    if verbose:
+        print("".join(outs))
+    return objs
+
+
+def _link(objs, out: Path):
+    _run([nvcc(), "-shared", "-ccbin", host_compiler(), "-o", str(out)] + [str(o) for o in objs]
+         + ["-lcudart", "-ldl", "-L", str(PKG), "-lesim_host", "-Xlinker", "-rpath=$ORIGIN"])
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in CUDA_SOURCES]
     build_host()   # libesim_b200.so links against the host library (sharding for multi-device handles)
     deps = srcs + [INCLUDE / "esim.h", INCLUDE / "esim_popgen.h", INCLUDE / "esim_popgen_device.h", HOST_LIB] + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh"))
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
-    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-           "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-ccbin", host_compiler(),
-           "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(CUDA_LIB)]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in srcs] + ["-lcudart", "-ldl", "-L", str(PKG), "-lesim_host", "-Xlinker", "-rpath=$ORIGIN"]
-    out = _run(cmd)
-    if verbose:
-        print(out)
+    _link(_compile_objects("", [], force, verbose), CUDA_LIB)
     return CUDA_LIB
 
 
@@ -86,11 +110,7 @@ def build_variant(name: str, defines) -> Path:
     """A/B builds of the CUDA library with other compile-time switches (scripts/kstep_ab.py selects one with ESIM_B200_LIB)."""
     out = PKG / ("libesim_b200_%s.so" % name)
     build_host()
-    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-           "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-ccbin", host_compiler(),
-           "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(out)] + ["-D" + d for d in defines]
-    cmd += [str(CSRC / s) for s in CUDA_SOURCES] + ["-lcudart", "-ldl", "-L", str(PKG), "-lesim_host", "-Xlinker", "-rpath=$ORIGIN"]
-    _run(cmd)
+    _link(_compile_objects("_" + name, list(defines), True, False), out)
     return out
 
 

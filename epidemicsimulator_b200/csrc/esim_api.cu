@@ -22,6 +22,7 @@
 #include "esim_popgen.h"
 #include "esim_popgen_device.h"
 #include "esim_import.h"
+#include "esim_hostcopy.h"
 #include "esim_internal.h"
 #include "pt_spans.h"
 #include "esim_rng.h"
@@ -133,7 +134,7 @@ struct EsimSim {
     int device = 0;
     cudaStream_t stream = nullptr;
     DevView v{};
-    DevBuf<uint32_t> cstate, home_cell, work_cell, home_base, room_parent, cnt_all, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
+    DevBuf<uint32_t> cstate, home_cell, work_cell, home_base, room_parent, bldg_area, cnt_all, tally_partial, route_off, riders, pt_key, pt_bus, pt_buscnt,
         rec_bus, rec_businf;
     DevBuf<unsigned long long> thr;
     DevBuf<uint4> pt_span;              // public transport: whole routes packed into spans of <= 128 riders (see pt_phase)
@@ -158,7 +159,6 @@ struct EsimSim {
     bool mailbox_private = false;
     Ctrl* h_ctrl = nullptr;             // pinned
     EsimStepStats* h_stat = nullptr;    // pinned, one entry
-    std::vector<uint32_t> h_bldg_area, h_room_parent;
     uint32_t n_areas = 0;
     bool imported = false;
     uint32_t steps_done = 0;            // steps executed (recorded) so far
@@ -210,7 +210,7 @@ struct EsimSim {
         for (void* m : peer_mappings) cudaIpcCloseMemHandle(m);
         exch.release(); vax_cand.release(); peer_mail.release(); peer_view.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        cstate.release(); home_cell.release(); work_cell.release(); home_base.release(); room_parent.release(); cnt_all.release(); tally_partial.release();
+        cstate.release(); home_cell.release(); work_cell.release(); home_base.release(); room_parent.release(); bldg_area.release(); cnt_all.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
         pt_span.release(); pt_seg.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
@@ -561,7 +561,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         Tracer tr;
 
         // ---- raw arrays: one host -> device copy each (asynchronous when the caller's memory is pinned) ----
-        DevBuf<uint32_t> r_home, r_work, r_room, r_gid, r_area;
+        DevBuf<uint32_t> r_home, r_work, r_room, r_gid;
         DevBuf<uint8_t> r_flags, r_status, r_btype, is_rider, head;
         DevBuf<uint16_t> r_timer;
         DevBuf<unsigned long long> route_key, keys_in, keys_out;
@@ -571,19 +571,27 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
             std::vector<std::function<void()>> f;
             ~Cleanup() { for (auto& g : f) g(); }
         } cleanup;
+        // Arrays in pageable host memory (a Rust Vec, a numpy array) go through the staged-copy workers (esim_hostcopy.h).
+        std::vector<CopySeg> staged;
+        auto send = [&](void* dev, const void* src, size_t bytes) {
+            if (!on_device && is_pageable_host(src)) staged.push_back({dev, src, bytes});
+            else CK(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyDefault, st));   // page-locked host or device source
+        };
         auto up = [&](auto& buf, const auto* host, size_t count) {
             buf.alloc(count);
             cleanup.f.push_back([&buf] { buf.release(); });
-            CK(cudaMemcpyAsync(buf.p, host, buf.bytes(), cudaMemcpyDefault, st));   // host (pageable or pinned) or device source
+            send(buf.p, host, buf.bytes());
         };
         up(r_home, p->home_bldg, N); up(r_work, p->work_bldg, N); up(r_room, p->room, N);
         if (p->global_id) up(r_gid, p->global_id, N);
         if (p->flags) up(r_flags, p->flags, N);
         if (p->status) up(r_status, p->status, N);
         if (p->timer) up(r_timer, p->timer, N);
-        up(r_area, p->bldg_area, B); up(r_btype, p->bldg_type, B);
+        up(r_btype, p->bldg_type, B);
+        s->bldg_area.alloc(B); send(s->bldg_area.p, p->bldg_area, (size_t)B * 4);   // kept: the statistics dump reads it back
         s->room_parent.alloc(std::max<uint32_t>(R, 1));
-        if (R) CK(cudaMemcpyAsync(s->room_parent.p, p->room_bldg, (size_t)R * 4, cudaMemcpyDefault, st));
+        if (R) send(s->room_parent.p, p->room_bldg, (size_t)R * 4);
+        if (!staged.empty()) CK(staged_copy(staged.data(), (int)staged.size(), true, s->device, st));
 
         tr.mark("upload raw arrays", st);
         s->cstate.alloc(n_pad); s->home_cell.alloc(n_pad); s->work_cell.alloc(n_pad); s->home_base.alloc(n_pad / 4);
@@ -593,7 +601,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         CK(cudaMemsetAsync(d_small.p, 0, d_small.bytes(), st));
         ImportRaw raw{};
         raw.n = N; raw.n_areas = A; raw.n_bldg = B; raw.n_rooms = R; raw.shard_lo = shard_lo; raw.exposed_time = te; raw.infected_time = ti;
-        raw.home = r_home.p; raw.work = r_work.p; raw.room = r_room.p; raw.global_id = r_gid.p; raw.bldg_area = r_area.p;
+        raw.home = r_home.p; raw.work = r_work.p; raw.room = r_room.p; raw.global_id = r_gid.p; raw.bldg_area = s->bldg_area.p;
         raw.room_bldg = s->room_parent.p; raw.flags = r_flags.p; raw.status = r_status.p; raw.bldg_type = r_btype.p; raw.timer = r_timer.p;
         ImportOut out{};
         out.n_pad = n_pad; out.cstate = s->cstate.p; out.home_cell = s->home_cell.p; out.work_cell = s->work_cell.p; out.home_base = s->home_base.p;
@@ -695,12 +703,7 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         CK(cudaMemcpyAsync(s->ctrl.p, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
         tr.mark("thresholds, allocations, memsets", st);
 
-        s->h_bldg_area.resize(B); s->h_room_parent.resize(R);
-        CK(cudaMemcpy(s->h_bldg_area.data(), p->bldg_area, (size_t)B * 4, cudaMemcpyDefault));
-        if (R) CK(cudaMemcpy(s->h_room_parent.data(), p->room_bldg, (size_t)R * 4, cudaMemcpyDefault));
         s->n_areas = A;
-
-        tr.mark("host copies of area tables");
         DevView& v = s->v;
         v.n = N; v.n_pad = n_pad; v.n_bldg = B; v.n_rooms = R; v.n_cells = B + R;
         v.n_routes = n_routes; v.n_riders = n_riders; v.record_buses = rec ? 1u : 0u;
@@ -1078,11 +1081,16 @@ int esim_read_state(EsimSim* s, EsimStateView* view) {
         if (view->on_pt) { d_on_pt.alloc(n); a.on_pt = d_on_pt.p; }
         if (view->vax_eligible) { d_elig.alloc(n); a.vax_eligible = d_elig.p; }
         CK(export_state(a, s->stream));
-        if (view->status) CK(cudaMemcpyAsync(view->status, d_status.p, n, cudaMemcpyDeviceToHost, s->stream));
-        if (view->timer) CK(cudaMemcpyAsync(view->timer, d_timer.p, n * 2, cudaMemcpyDeviceToHost, s->stream));
-        if (view->current_bldg) CK(cudaMemcpyAsync(view->current_bldg, d_cur.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
-        if (view->on_pt) CK(cudaMemcpyAsync(view->on_pt, d_on_pt.p, n, cudaMemcpyDeviceToHost, s->stream));
-        if (view->vax_eligible) CK(cudaMemcpyAsync(view->vax_eligible, d_elig.p, n, cudaMemcpyDeviceToHost, s->stream));
+        // pageable destinations go through the staged-copy workers (esim_hostcopy.h), page-locked ones straight from the stream
+        std::vector<CopySeg> staged;
+        auto fetch = [&](void* host, const void* dev, size_t bytes) {
+            if (!host) return;
+            if (is_pageable_host(host)) staged.push_back({host, dev, bytes});
+            else CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        };
+        fetch(view->status, d_status.p, n); fetch(view->timer, d_timer.p, n * 2); fetch(view->current_bldg, d_cur.p, n * 4);
+        fetch(view->on_pt, d_on_pt.p, n); fetch(view->vax_eligible, d_elig.p, n);
+        if (!staged.empty()) CK(staged_copy(staged.data(), (int)staged.size(), false, s->device, s->stream));
         CK(cudaStreamSynchronize(s->stream));
         return ESIM_OK;
     });
@@ -1148,14 +1156,18 @@ static void collect_area_exposures(EsimSim* s, const std::vector<EsimStepStats>&
     HostState h;
     download_state(s, h, true);
     const uint32_t B = s->v.n_bldg, T = (uint32_t)st.size();
+    std::vector<uint32_t> h_bldg_area(B), h_room_parent(s->v.n_rooms);   // building -> output area, room -> school
+    CK(cudaMemcpyAsync(h_bldg_area.data(), s->bldg_area.p, (size_t)B * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (s->v.n_rooms) CK(cudaMemcpyAsync(h_room_parent.data(), s->room_parent.p, (size_t)s->v.n_rooms * 4, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
     for (uint32_t i = 0; i < s->v.n; ++i) {
         const uint32_t w = h.cstate[i], e = w & CS_EXPOSURE;
         if (e <= EXPOSURE_BIAS || (w & CS_VIA_PT)) continue;
         const uint32_t x = e - EXPOSURE_BIAS;
         if (x == 0 || x > T) continue;
         uint32_t cell = st[x - 1].at_work ? h.work[i] : h.home[i];
-        if (cell >= B) cell = s->h_room_parent[cell - B];
-        per_area[s->h_bldg_area[cell]][x] += 1;
+        if (cell >= B) cell = h_room_parent[cell - B];
+        per_area[h_bldg_area[cell]][x] += 1;
     }
 }
 

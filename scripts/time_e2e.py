@@ -12,9 +12,11 @@ from epidemicsimulator_b200.simulator import Simulator, default_config, pin_popu
 torch.cuda.init()
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 480
 pop0 = synthetic_population(11300, areas_per_school=67)
-for label, pop in (("pageable", pop0), ("pinned", pin_population(pop0))):
+for label, pop in (("pageable", pop0), ("pageable-fresh-out", pop0), ("pinned", pin_population(pop0))):
     bufs = Simulator.state_buffers(pop.n_citizens, pinned=(label == "pinned"))
     for rep in range(3):
+        if label == "pageable-fresh-out":   # output arrays nobody has touched: the copy takes their page faults
+            bufs = Simulator.state_buffers(pop.n_citizens, pinned=False)
         t = [time.perf_counter()]
         sim = Simulator(default_config()); t.append(time.perf_counter())
         sim.import_population(pop); t.append(time.perf_counter())

@@ -106,6 +106,30 @@ __global__ void __launch_bounds__(256) k_route_heads(const unsigned long long* _
     if (k < n_riders) head[k] = (k == 0 || keys[k] != keys[k - 1]) ? 1 : 0;
 }
 
+// seg of every rider of a packed span (csrc/pt_spans.h: start of its route inside the span | riders of the route << 8); one warp
+// per span, the lanes walk the span's riders and find their route by bisection over the span's routes; the riders of an
+// over-long route (a span of its own) keep 0
+__global__ void __launch_bounds__(256) k_span_seg(const uint4* __restrict__ spans, uint32_t n_spans, const uint32_t* __restrict__ route_off,
+                                                  uint16_t* __restrict__ seg, uint32_t max_riders) {
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (k >= n_spans) return;
+    const uint4 sp = spans[k];   // first rider, riders, first route, routes
+    if (sp.y > max_riders) {
+        for (uint32_t j = lane; j < sp.y; j += 32u) seg[sp.x + j] = 0;
+        return;
+    }
+    for (uint32_t j = lane; j < sp.y; j += 32u) {
+        const uint32_t pos = sp.x + j;
+        uint32_t lo = sp.z, hi = sp.z + sp.w - 1u;   // last route of the span whose first rider is <= pos
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1u) >> 1;
+            if (route_off[mid] <= pos) lo = mid; else hi = mid - 1u;
+        }
+        const uint32_t start = route_off[lo] - sp.x, len = route_off[lo + 1u] - route_off[lo];
+        seg[pos] = (uint16_t)(start | (len << 8));
+    }
+}
+
 __global__ void __launch_bounds__(256) k_export_state(ExportArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -169,6 +193,12 @@ cudaError_t route_sort_and_heads(const ImportOut& out, const uint32_t* rider_idx
     if (e != cudaSuccess) return e;
     k_route_heads<<<(n_riders + 255) / 256, 256, 0, s>>>(keys_out, head, n_riders);
     return cub::DeviceSelect::Flagged(temp, temp_bytes, thrust::counting_iterator<uint32_t>(0), head, route_off, d_count, (int)n_riders, s);
+}
+
+cudaError_t span_fill_seg(const uint4* spans, uint32_t n_spans, const uint32_t* route_off, uint16_t* seg, uint32_t max_riders, cudaStream_t s) {
+    if (n_spans == 0) return cudaSuccess;
+    k_span_seg<<<(n_spans + 7) / 8, 256, 0, s>>>(spans, n_spans, route_off, seg, max_riders);
+    return cudaGetLastError();
 }
 
 cudaError_t export_state(const ExportArgs& a, cudaStream_t s) {

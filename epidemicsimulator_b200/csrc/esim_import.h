@@ -35,6 +35,8 @@ cudaError_t route_select_riders(const ImportOut& out, uint32_t n_pad, uint32_t* 
 cudaError_t route_sort_and_heads(const ImportOut& out, const uint32_t* rider_idx, uint32_t n_riders, unsigned long long* keys_in,
                                  unsigned long long* keys_out, uint32_t* riders_sorted, uint8_t* head, uint32_t* route_off,
                                  uint32_t* d_count, void* temp, size_t temp_bytes, cudaStream_t s);
+// per rider of every span: start of its route inside the span | riders of the route << 8 (0 for the riders of an over-long route)
+cudaError_t span_fill_seg(const uint4* spans, uint32_t n_spans, const uint32_t* route_off, uint16_t* seg, uint32_t max_riders, cudaStream_t s);
 cudaError_t export_state(const ExportArgs& a, cudaStream_t s);
 
 }  // namespace esim

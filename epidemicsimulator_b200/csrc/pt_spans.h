@@ -15,23 +15,30 @@ struct PtSpanRecord {
     uint32_t first_rider, riders, first_route, routes;   // the layout of DevView::pt_span (uint4)
 };
 
-inline void pack_pt_spans(const uint32_t* route_off, uint32_t n_routes, uint32_t max_riders, std::vector<PtSpanRecord>& spans,
-                          std::vector<uint16_t>& seg) {
+// the span records alone (the import computes `seg` on the device from them: esim_import.cu, k_span_seg)
+template <class Vec>
+inline void pack_pt_span_records(const uint32_t* route_off, uint32_t n_routes, uint32_t max_riders, Vec& spans) {
     spans.clear();
-    seg.assign(n_routes ? route_off[n_routes] : 0u, 0);
     uint32_t r = 0;
     while (r < n_routes) {
         const uint32_t first = r, span_off = route_off[r];
-        uint32_t total = route_off[r + 1] - route_off[r];
         ++r;
-        if (total <= max_riders)
-            while (r < n_routes && total + (route_off[r + 1] - route_off[r]) <= max_riders) { total += route_off[r + 1] - route_off[r]; ++r; }
-        spans.push_back(PtSpanRecord{span_off, total, first, r - first});
-        if (total <= max_riders)
-            for (uint32_t q = first; q < r; ++q) {
-                const uint32_t start = route_off[q] - span_off, len = route_off[q + 1] - route_off[q];
-                for (uint32_t j = route_off[q]; j < route_off[q + 1]; ++j) seg[j] = (uint16_t)(start | (len << 8));
-            }
+        if (route_off[r] - span_off <= max_riders)
+            while (r < n_routes && route_off[r + 1] - span_off <= max_riders) ++r;
+        spans.push_back(PtSpanRecord{span_off, route_off[r] - span_off, first, r - first});
+    }
+}
+
+inline void pack_pt_spans(const uint32_t* route_off, uint32_t n_routes, uint32_t max_riders, std::vector<PtSpanRecord>& spans,
+                          std::vector<uint16_t>& seg) {
+    pack_pt_span_records(route_off, n_routes, max_riders, spans);
+    seg.assign(n_routes ? route_off[n_routes] : 0u, 0);
+    for (const PtSpanRecord& sp : spans) {
+        if (sp.riders > max_riders) continue;
+        for (uint32_t q = sp.first_route; q < sp.first_route + sp.routes; ++q) {
+            const uint32_t start = route_off[q] - sp.first_rider, len = route_off[q + 1] - route_off[q];
+            for (uint32_t j = route_off[q]; j < route_off[q + 1]; ++j) seg[j] = (uint16_t)(start | (len << 8));
+        }
     }
 }
 

@@ -163,6 +163,7 @@ struct EsimSim {
     std::vector<void*> peer_mappings;   // cudaIpcOpenMemHandle results
     DevBuf<unsigned long long> ktrace_min, ktrace_max;   // ESIM_KTRACE: device-side timeline of the step kernels
     bool fused = false;                 // one-pass step (k_step + k_tail_fused): single shard and peer-to-peer shards
+    bool l2_persisting = false;         // the count buffers are a persisting access-policy window of the step launches
     size_t cnt_stride = 0;              // words between the three count buffers inside cnt_all
     uint32_t world = 1, rank = 0, n_shared_bldgs = 0, n_shared_rooms = 0;
     uint32_t share = 1;                 // handles of one multi-device handle that run on this device (they wait for each other inside kernels)
@@ -232,6 +233,7 @@ struct EsimSim {
         pt_span.release(); pt_seg.release();
         rec_bus.release(); rec_businf.release(); thr.release(); ctrl.release(); stats.release(); l2_scratch.release();
         if (stream) cudaStreamSynchronize(stream);
+        if (l2_persisting) cudaCtxResetPersistingL2Cache();   // the lines of the count buffers go back to normal
         ktrace_min.release(); ktrace_max.release();
         if (mailbox_private) cudaFreeHost(mailbox); else g_mailboxes.give(mailbox);
         if (stream) cudaStreamDestroy(stream);
@@ -771,6 +773,25 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
             const size_t working_set = (size_t)n_pad * 9 + (size_t)(B + R) * 12;
             v.pf_next = (l2 > 0 && working_set > (size_t)l2 * 3 / 4) ? 1u : 0u;
             if (const char* e = getenv("ESIM_STEP_PF_NEXT")) v.pf_next = e[0] == '1';
+            // The same populations keep their three count buffers in the persisting part of the L2 (DevView::l2_window_bytes):
+            // a third of them is zeroed by every launch and every susceptible citizen gathers two counts, while the streams flow
+            // through the rest of the L2.  Measured at 8.4 M citizens (profiles/README.md, round 2l): k_step 27.3 -> 25.6 us per
+            // launch, graph replay 24.6 -> 23.9 us per hour; extending the window over the state words as well gained nothing
+            // more.  ESIM_L2_PERSIST = 0 / 1 overrides the choice.
+            bool persist = v.pf_next != 0;
+            if (const char* e = getenv("ESIM_L2_PERSIST")) persist = e[0] == '1';
+            int max_persist = 0, max_window = 0;
+            CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, s->device));
+            CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, s->device));
+            const size_t cnt_bytes = s->cnt_all.bytes();
+            v.l2_window_base = nullptr; v.l2_window_bytes = 0;
+            if (persist && cnt_bytes <= (size_t)max_persist && cnt_bytes <= (size_t)max_window) {
+                size_t have = 0;
+                CK(cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize));
+                if (have < cnt_bytes) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, cnt_bytes));
+                v.l2_window_base = s->cnt_all.p; v.l2_window_bytes = cnt_bytes;
+                s->l2_persisting = true;
+            }
         }
 
         s->device_bytes = s->cstate.bytes() + s->home_cell.bytes() + s->work_cell.bytes() + s->home_base.bytes() +

@@ -174,6 +174,10 @@ struct DevView {
     uint32_t* exch;              // [EXCH_WORDS] second exchange buffer of a sharded step of the three-kernel pipeline
     uint32_t* vax_cand;          // [ESIM_VAX_SHARD_DRAWS] three-kernel pipeline: candidate citizen of every draw of this step
     uint32_t pf_next;            // k_step prefetches the next iteration's streams into the L2 (working set above the L2, see step_stream)
+    // host side only (launch_step_kernel): the three count buffers as a persisting access-policy window of every step launch,
+    // 0 bytes = none.  Set when the working set exceeds the L2: the streams then flow through the rest of the L2.
+    const void* l2_window_base;
+    size_t l2_window_bytes;
     uint32_t share;              // handles that share this device and wait for each other inside their kernels (0 / 1 = alone)
     uint32_t no_pdl;             // launch the step kernels without programmatic dependent launch
     uint32_t sync_seq;           // esim_step_timed on peer-to-peer shards: number of the timed step (see MAIL_SYNC), 0 = no barrier

@@ -1915,10 +1915,24 @@ template <class K>
 static void launch_step_kernel(K kernel, uint32_t grid, uint32_t block, size_t smem, cudaStream_t s, const DevView& v) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = v.no_pdl ? 0 : 1;
+    cudaLaunchAttribute attr[2];
+    unsigned n_attr = 0;
+    if (!v.no_pdl) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    if (v.l2_window_bytes) {   // the count buffers stay in the persisting part of the L2 (DevView::l2_window_bytes)
+        attr[n_attr].id = cudaLaunchAttributeAccessPolicyWindow;
+        cudaAccessPolicyWindow& w = attr[n_attr].val.accessPolicyWindow;
+        w.base_ptr = const_cast<void*>(v.l2_window_base);
+        w.num_bytes = v.l2_window_bytes;
+        w.hitRatio = 1.0f;
+        w.hitProp = cudaAccessPropertyPersisting;
+        w.missProp = cudaAccessPropertyStreaming;
+        ++n_attr;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n_attr;
     cudaLaunchKernelEx(&cfg, kernel, v);
 }
 

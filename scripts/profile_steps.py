@@ -19,13 +19,15 @@ ap.add_argument("--steps", type=int, default=48)
 ap.add_argument("--skip", type=int, default=24)
 ap.add_argument("--exposure-chance", type=float, default=0.00055)
 ap.add_argument("--repeat", type=int, default=1)
+ap.add_argument("--flushed", action="store_true", help="timed steps with the L2 flushed before each (the way bench.py's `value` runs) instead of graph replay")
 args = ap.parse_args()
 pop = synthetic_population(args.areas, areas_per_school=67, cross_area_fraction=args.cross)
 for _ in range(args.repeat):
-    sim = Simulator.from_population(pop, default_config(exposure_chance=args.exposure_chance))
+    from epidemicsimulator_b200 import _abi  # noqa: E402
+    sim = Simulator.from_population(pop, default_config(exposure_chance=args.exposure_chance, flags=_abi.CFG_FLUSH_L2 if args.flushed else 0))
     sim.run(args.skip)
     t0 = time.perf_counter()
-    n = sim.run(args.steps)
+    n = sim.run_timed(args.steps) if args.flushed else sim.run(args.steps)
     dt = time.perf_counter() - t0
     print("citizens %d steps %d: %.2f us/step, %.3e citizen-steps/s, last %s" % (
         pop.n_citizens, n, dt / n * 1e6, pop.n_citizens * n / dt, sim.statistics(sim.steps_done - 1, 1)[0][:6].tolist()))

@@ -80,6 +80,22 @@ def test_lockstep_small_fast_epidemic():
     assert all(seen.values()), seen
 
 
+def test_lockstep_with_the_count_buffers_in_the_persisting_l2(monkeypatch):
+    """Populations above the L2 keep their count buffers in the persisting part of the L2 (an access-policy window on every
+    step launch, DevView::l2_window_bytes); ESIM_L2_PERSIST=1 forces it for a small one: same results, single steps and graphs."""
+    monkeypatch.setenv("ESIM_L2_PERSIST", "1")
+    pop = synthetic_population(n_areas=40, areas_per_school=10, cross_area_fraction=0.3, initial_infected=10)
+    seen = _lockstep(pop, 300, exposure_chance=0.02, vaccination_rate=60, seed=7)
+    assert seen["bld_exp"] and seen["pt_exp"]
+    cfg = dict(exposure_chance=0.02, vaccination_rate=60, seed=7)
+    sim = _sim(pop, **cfg)
+    orc = Oracle(pop, default_config(**cfg))
+    assert sim.run(500) == orc.run(500)
+    assert np.array_equal(sim.statistics(), orc.stats())
+    _compare_state(sim, orc, 500)
+    sim.close(); orc.close()
+
+
 def test_lockstep_reference_constants():
     pop = synthetic_population(n_areas=120, areas_per_school=25)
     seen = _lockstep(pop, 240, state_every=24, seed=3)

@@ -85,6 +85,38 @@ def test_multi_handle_on_one_device_matches_oracle(world, cross, tmp_path, monke
     sim.close(); orc.close()
 
 
+@pytest.mark.parametrize("n_areas,cross,shards", [(55000, 0.9, 2), (183300, 0.6, 8)], ids=["configs4_two_shards", "configs3_england56_eight_shards"])
+def test_baseline_multi_gpu_configs_against_the_oracle(n_areas, cross, shards):
+    """BASELINE configs[4] at two shards (2 x 27 500 output areas = 16.8 M citizens, cross-area fraction 0.9) and configs[3]
+    (England scale: 183 300 output areas = 56 M citizens, cross-area fraction 0.6) at eight shards, from the peak mix:
+    k_step_p2p / k_tail_fused_p2p at the sizes the multi-GPU bench runs them - next-iteration prefetch and persisting L2 window on
+    at 8.4 M citizens per shard, hundreds of thousands of shared cells, vaccination picks exchanged every hour - against the
+    oracle of the WHOLE population, nine hours incl. the morning public-transport hour.  (The shards share device 0: same
+    kernels, same exchange, plain device pointers.)"""
+    from bench import peak_mix
+    pop = peak_mix(synthetic_population(n_areas=n_areas, areas_per_school=67, cross_area_fraction=cross))
+    cfg = dict(seed=3, lockdown_threshold=-1.0, flags=_abi.CFG_RECORD_BUSES)
+    sim = _multi(pop, [0] * shards, **cfg)
+    assert sim.fused
+    orc = Oracle(pop, default_config(**cfg))
+    seen_pt = seen_vax = False
+    for k in range(9):
+        alive = sim.step()
+        alive_o, so = orc.step()
+        assert sim.last_stats.as_tuple() == so.as_tuple(), "step %d:\n gpu    %s\n oracle %s" % (k + 1, sim.last_stats.as_dict(), so.as_dict())
+        assert alive == alive_o
+        seen_vax |= so.vaccinated_now > 0
+        if so.pt_mode != _abi.PT_NONE:
+            seen_pt = True
+            ig, ng = sim.buses()
+            io, no = orc.buses()
+            riders = (pop.flags & _abi.FLAG_USES_PT) != 0
+            assert np.array_equal(ig[riders], io[riders]) and np.array_equal(ng[riders], no[riders]), "step %d: buses differ" % (k + 1)
+    assert seen_pt and seen_vax
+    _compare_state(sim, orc, "after 9 steps")
+    sim.close(); orc.close()
+
+
 def _imported_mix(n_areas, s_share, i_share, seed=1):
     """A population in the middle of an epidemic: s_share Susceptible, i_share Infected (all ages of infection), the rest
     Recovered - the vaccination programme starts in the first hour with a small eligible set."""

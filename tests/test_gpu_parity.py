@@ -265,6 +265,16 @@ def test_full_size_peak_mix_two_days_with_public_transport():
     assert seen["vax"] and seen["bld_exp"] and seen["pt_exp"] and seen["pt_hours"] == 4
 
 
+def test_uk67_per_gpu_size_lockstep():
+    """The per-GPU population of BASELINE configs[4] (27 500 output areas, 8.4 M citizens, cross-area fraction 0.9: 750 000
+    public-transport routes) from the peak mix, schedule running, 17 hours with both public-transport hours: the size at which the
+    working set exceeds the L2, i.e. with the next-iteration prefetch and the persisting L2 window of the count buffers switched on
+    by the library itself.  Bit-exact against the oracle, buses compared rider by rider."""
+    pop = synthetic_population(n_areas=27500, areas_per_school=67, cross_area_fraction=0.9)
+    seen = _peak_lockstep(pop, 17, check_every=8, seed=1, lockdown_threshold=-1.0)
+    assert seen["vax"] and seen["bld_exp"] and seen["pt_exp"] and seen["pt_hours"] == 2
+
+
 def test_yorkshire_and_humber_size_lockstep():
     """BASELINE configs[2] (17 246 output areas, ~5.3 M citizens) with every intervention enabled, 48 hours from the peak mix with
     cross-area workplaces: bit-exact against the oracle."""

@@ -66,9 +66,11 @@ struct DevBuf {
         if (!count) return;
         if (plain) CK(cudaMalloc(&p, count * sizeof(T))); else CK(cudaMallocAsync(&p, count * sizeof(T), stream));
     }
+    bool borrowed = false;   // a window into another DevBuf: nothing to free
+    void view(T* base, size_t count) { release(); p = base; n = count; borrowed = true; }
     void release() {
-        if (p) { if (plain) cudaFree(p); else cudaFreeAsync(p, stream); }
-        p = nullptr; n = 0;
+        if (p && !borrowed) { if (plain) cudaFree(p); else cudaFreeAsync(p, stream); }
+        p = nullptr; n = 0; borrowed = false;
     }
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -159,6 +161,9 @@ struct EsimSim {
     DevBuf<unsigned char> l2_scratch;   // ESIM_CFG_FLUSH_L2
     DevBuf<uint32_t> exch, vax_cand;    // sharded runs
     DevBuf<uint32_t> peer_mail;         // peer-to-peer exchange (sharded runs): this shard's mailbox in HBM
+    DevBuf<uint32_t> shared_blk;        // sharded runs: [three count buffers | mailbox] in ONE cudaMalloc block = one CUDA IPC handle and one
+                                        // cudaIpcOpenMemHandle per peer (the opens of all ranks of a box are serialised by the driver: 112 of
+                                        // them took ~45 ms of every rank's set-up at 8 GPUs); cnt_all and peer_mail are windows into it
     DevBuf<PeerView> peer_view;         // pointer tables of the mapped peers
     std::vector<void*> peer_mappings;   // cudaIpcOpenMemHandle results
     DevBuf<unsigned long long> ktrace_min, ktrace_max;   // ESIM_KTRACE: device-side timeline of the step kernels
@@ -227,6 +232,7 @@ struct EsimSim {
         if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
         for (void* m : peer_mappings) cudaIpcCloseMemHandle(m);
         exch.release(); vax_cand.release(); peer_mail.release(); peer_view.release();
+        cnt_all.release(); shared_blk.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         cstate.release(); home_cell.release(); work_cell.release(); home_base.release(); room_parent.release(); bldg_area.release(); cnt_all.release(); tally_partial.release();
         route_off.release(); riders.release(); pt_key.release(); pt_bus.release(); pt_buscnt.release();
@@ -701,9 +707,15 @@ static int import_population(EsimSim* s, const EsimPopulationSoA* p, bool on_dev
         // three count buffers in one allocation (one CUDA IPC handle for peers); sharded handles decide at connect time
         // whether they run fused (esim_peer_connect) or not (esim_comm_init, esim_shard_step_*)
         s->cnt_stride = ((size_t)B + R + 4 + 31) & ~(size_t)31;
-        s->cnt_all.alloc(3 * s->cnt_stride, sharded_pop || getenv("ESIM_PLAIN_CNT") != nullptr);   // (env: A/B of the allocator, profiles/README.md)
+        if (sharded_pop) {
+            s->shared_blk.alloc(3 * s->cnt_stride + MAIL_WORDS, true);   // plain cudaMalloc: exported through CUDA IPC
+            s->cnt_all.view(s->shared_blk.p, 3 * s->cnt_stride);
+            s->peer_mail.view(s->shared_blk.p + 3 * s->cnt_stride, MAIL_WORDS);
+            CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st));
+        } else {
+            s->cnt_all.alloc(3 * s->cnt_stride, getenv("ESIM_PLAIN_CNT") != nullptr);   // (env: A/B of the allocator, profiles/README.md)
+        }
         s->fused = p->n_shards <= 1 && !(s->cfg.flags & ESIM_CFG_UNFUSED) && !getenv("ESIM_UNFUSED");   // (the env switch: the GPU parity suite runs every test on both pipelines)
-        if (sharded_pop) { s->peer_mail.alloc(MAIL_WORDS, true); CK(cudaMemsetAsync(s->peer_mail.p, 0, s->peer_mail.bytes(), st)); }
         s->pt_key.alloc(std::max<uint32_t>(n_riders, 1)); s->pt_bus.alloc(std::max<uint32_t>(n_riders, 1));
         s->pt_buscnt.alloc(std::max<uint32_t>(n_riders, 1));
         const bool rec = (s->cfg.flags & ESIM_CFG_RECORD_BUSES) != 0;
@@ -1322,8 +1334,8 @@ int esim_dump_statistics(EsimSim* s, const char* directory, const char* const* a
 // ---- sharded runs ----------------------------------------------------------------------------------------
 namespace {
 struct PeerInfo {   // what a rank publishes; padded to ESIM_PEER_INFO_BYTES
-    cudaIpcMemHandle_t cnt, mail;
-    uint32_t n_bldg, n_rooms, n_shared_b, n_shared_r, world, device, cnt_stride, fused_ok;
+    cudaIpcMemHandle_t blk;   // EsimSim::shared_blk: the three count buffers, then the mailbox `mail_offset` words further on
+    uint32_t n_bldg, n_rooms, n_shared_b, n_shared_r, world, device, cnt_stride, fused_ok, mail_offset;
 };
 static_assert(sizeof(PeerInfo) <= ESIM_PEER_INFO_BYTES, "peer info does not fit");
 }  // namespace
@@ -1336,10 +1348,11 @@ int esim_peer_info(EsimSim* s, uint8_t info[ESIM_PEER_INFO_BYTES]) {
         if (s->world < 2 || !s->peer_mail.p) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "not a sharded handle"};
         PeerInfo pi;
         std::memset(&pi, 0, sizeof(pi));
-        CK(cudaIpcGetMemHandle(&pi.cnt, s->cnt_all.p));
+        if (!s->shared_blk.p) throw ApiError{ESIM_ERR_INVALID_ARGUMENT, "not a sharded handle"};
+        CK(cudaIpcGetMemHandle(&pi.blk, s->shared_blk.p));
         pi.cnt_stride = (uint32_t)s->cnt_stride;
         pi.fused_ok = 1u;   // peer-to-peer shards always run the fused pipeline
-        CK(cudaIpcGetMemHandle(&pi.mail, s->peer_mail.p));
+        pi.mail_offset = (uint32_t)(s->peer_mail.p - s->shared_blk.p);
         pi.n_bldg = s->v.n_bldg; pi.n_rooms = s->v.n_rooms; pi.n_shared_b = s->n_shared_bldgs; pi.n_shared_r = s->n_shared_rooms;
         pi.world = s->world; pi.device = (uint32_t)s->device;
         std::memset(info, 0, ESIM_PEER_INFO_BYTES);
@@ -1373,11 +1386,10 @@ int esim_peer_connect(EsimSim* s, uint32_t rank, uint32_t world, const uint8_t* 
                 pv.mail[p] = s->peer_mail.p;
                 continue;
             }
-            void *m0 = nullptr, *mm = nullptr;
-            CK(cudaIpcOpenMemHandle(&m0, pi.cnt, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(m0);
-            CK(cudaIpcOpenMemHandle(&mm, pi.mail, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(mm);
+            void* m0 = nullptr;
+            CK(cudaIpcOpenMemHandle(&m0, pi.blk, cudaIpcMemLazyEnablePeerAccess)); s->peer_mappings.push_back(m0);
             for (int k = 0; k < 3; ++k) pv.cnt[k][p] = (uint32_t*)m0 + (size_t)k * pi.cnt_stride;
-            pv.mail[p] = (uint32_t*)mm;
+            pv.mail[p] = (uint32_t*)m0 + pi.mail_offset;
         }
         tr.mark("peer connect: map the peers' buffers");
         s->peer_view.alloc(1);

@@ -189,7 +189,11 @@ cudaError_t staged_copy(const CopySeg* segs, int n_segs, bool to_device, int dev
     const int n_threads = (int)(pieces.size() < (size_t)p.n_workers ? pieces.size() : (size_t)p.n_workers);
     std::vector<std::thread> threads;
     threads.reserve(n_threads);
-    for (int t = 1; t < n_threads; ++t) threads.emplace_back(run_worker, std::ref(p.w[t]), std::ref(job));
+    try {
+        for (int t = 1; t < n_threads; ++t) threads.emplace_back(run_worker, std::ref(p.w[t]), std::ref(job));
+    } catch (...) {
+        // no more threads to be had: the pieces are handed out by a shared counter, the workers that exist take all of them
+    }
     run_worker(p.w[0], job);   // the calling thread is worker 0
     for (auto& t : threads) t.join();
     cudaSetDevice(device);

@@ -187,8 +187,10 @@ def traffic_from_profile(kernel):
     p = ROOT / "profiles" / "traffic.json"
     try:
         table = json.loads(p.read_text())
+        if kernel in table:   # exact name first ("k_step@8p4M" = the capture on the per-GPU population of configs[4])
+            return float(table[kernel]["dram_bytes_per_launch"])
         for name in sorted(table, key=len):
-            if name == kernel or name.startswith(kernel + "_"):
+            if name.startswith(kernel + "_"):
                 return float(table[name]["dram_bytes_per_launch"])
     except Exception:
         pass
@@ -484,7 +486,7 @@ def main():
             big = synthetic_population(27500, POP_SEED, 67, 0.9)
             big_p = pin_population(big)
             tmb, stb, nb = kernel_pass(big_p, leg_steps)
-            extra["roofline_8p4M"] = roofline_of(tmb, stb, big, nb, peak, peak_src)
+            extra["roofline_8p4M"] = roofline_of(tmb, stb, big, nb, peak, peak_src, traffic=traffic_from_profile("k_step@8p4M"))
             extra["roofline_8p4M"]["workload"] = "the per-GPU population of BASELINE configs[4] (27500 output areas, cross-area fraction 0.9), time steps 1..%d" % nb
             del big_p
             mix = pin_population(peak_mix(whole))

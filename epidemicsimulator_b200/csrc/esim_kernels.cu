@@ -128,6 +128,10 @@ __device__ __forceinline__ uint32_t ld_pair_wait(const DevView& v, const uint32_
         __nanosleep(ESIM_POLL_NS);
     }
 }
+// the (value, tag) pairs of shard `shard`'s tail vector of step t, round `round`, inside a mailbox (esim_internal.h, MAIL_LL)
+__device__ __forceinline__ uint32_t* mail_ll(uint32_t* mail, uint32_t t, uint32_t round, uint32_t shard) {
+    return mail + MAIL_LL + 2u * ((((t & 1u) * 2u + (round & 1u)) * MAX_WORLD + shard) * FEXCH_WORDS);
+}
 // An infected citizen standing in a cell that other shards reference adds itself to their count buffers as well
 // (system-scope reductions over NVLink); after the flag exchange every shard holds the global count of its shared cells.
 // `slot` = count buffer of the step being counted; `delta` = +1 (an infected occupant) or -1 (it has just been vaccinated)
@@ -198,12 +202,16 @@ __device__ __forceinline__ void wait_for_peers(const DevView& v, uint32_t flag_b
 // announces the end of its work (barrier, fence, one atomic on Ctrl::blocks_done) and the tail polls that counter; the tail
 // resets it when it writes the control block back (no k_step is running then: the next one waits for the tail to complete).
 // Hours with a public-transport kernel between the two keep the grid dependency (DevView::tail_flag_wait == 0).
-__device__ __forceinline__ void signal_block_done(const DevView& v, bool pushed_to_peer) {
+// Returns true, in thread 0, to the block that announced itself last (every other block's counts and pushes precede its own
+// announcement, so that block may read the sums of the whole grid).
+__device__ __forceinline__ bool signal_block_done(const DevView& v, bool pushed_to_peer) {
     const int any_pushed = __syncthreads_or(pushed_to_peer);   // every thread of the block has issued its writes
+    bool last = false;
     if (threadIdx.x == 0) {
         if (any_pushed) __threadfence_system(); else __threadfence();   // cumulative over the writes observed through the barrier
-        atomicAdd(&v.ctrl->blocks_done, 1u);
+        last = atomicAdd(&v.ctrl->blocks_done, 1u) + 1u == gridDim.x;
     }
+    return last;
 }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t x;
@@ -752,7 +760,27 @@ __device__ __forceinline__ void k_step_body(const DevView& v) {
     // four reductions per block into the control block: the tail finds the sums there instead of adding up 592 partial records
     // on the critical path between two steps (they precede the block's announcement: signal_block_done fences)
     if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&v.ctrl->cum[threadIdx.x], s_cnt[threadIdx.x]);
-    signal_block_done(v, P2P && pushed);
+    const bool last = signal_block_done(v, P2P && pushed);
+    // Peer-to-peer shards, hours whose tail is the one-warp quick tail polling the counter (no public-transport kernel in between,
+    // no vaccination picks): the block that announced itself last sends this shard's head of the tail vector itself, straight
+    // from the sums in the control block.  The peers' tails then find it in their mailboxes ~2 us earlier than if this shard's
+    // tail had to notice the counter, load the control block and send (device timeline, profiles/README.md); the tail only
+    // consumes (tail_quick, `sent_early`).  It cannot have reset the sums yet: it waits for this very head in its own mailbox.
+    if (P2P && threadIdx.x < 32u && v.has_pt == 0u && v.no_pdl == 0u && !(c->vax_some != 0u && kt_t != 0u)) {
+        if (__shfl_sync(0xffffffffu, (uint32_t)last, 0)) {
+            __threadfence();   // the sums of every block precede its announcement
+            const uint32_t lane = threadIdx.x;
+            if (lane < FEXCH_HEAD) {
+                uint32_t cum[4], cls[5];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cum[k] = __ldcg(&v.ctrl->cum[k]);
+                const uint32_t exp_b = __ldcg(&v.ctrl->new_exp_bldg), exp_pt = __ldcg(&v.ctrl->new_exp_pt);
+                classes_from_cumulative(cum, v.n_pad, v.n, cls);
+                const uint32_t mine = lane < 5u ? cls[lane] : lane == 5u ? exp_b : lane == 6u ? exp_pt : 0u;
+                for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(mail_ll(v.mail[p], kt_t, 0u, v.rank) + 2u * lane, mine, kt_t + 1u);
+            }
+        }
+    }
     kt.end(v, kt_t, 0);
 }
 __global__ void __launch_bounds__(STEP_THREADS, 4) k_step(const __grid_constant__ DevView v) { k_step_body<false>(v); }
@@ -1504,10 +1532,6 @@ __global__ void __launch_bounds__(PT_THREADS, ESIM_PT_BLOCKS_PER_SM) k_pt(const 
 constexpr uint32_t VHT = 16384;   // slots of the table of eligible owned candidates of a step (at most rate + one round's surplus)
 constexpr size_t P2P_SMEM = (2 * VHT + VAX_MAX_CHUNKS * VAX_CHUNK_WORDS + FEXCH_WORDS) * sizeof(uint32_t);
 
-__device__ __forceinline__ uint32_t* mail_ll(uint32_t* mail, uint32_t t, uint32_t round, uint32_t shard) {
-    return mail + MAIL_LL + 2u * ((((t & 1u) * 2u + (round & 1u)) * MAX_WORLD + shard) * FEXCH_WORDS);
-}
-
 // sm.c / sm.mail are loaded, sm.tally / sm.fix cleared.  Called by all TAIL_THREADS threads.
 __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, TailSmem& sm) {
     constexpr uint32_t NT = TAIL_THREADS;
@@ -1741,7 +1765,9 @@ __device__ __forceinline__ void tail_quick(const DevView& v, TailSmem& sm) {
         const uint32_t tag = t + 1u, h = lane & 7u;
         const uint32_t mine = h < 5u ? cls[h] : h == 5u ? exp_b : h == 6u ? exp_pt : 0u;
         KTrace ks; ks.enter = 0; ks.begin(v, t, 4);
-        if (lane < FEXCH_HEAD)
+        // a tail that polls k_step's counter finds its head already sent by the block that announced itself last (k_step_body)
+        const bool sent_early = v.tail_flag_wait != 0u;
+        if (lane < FEXCH_HEAD && !sent_early)
             for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(mail_ll(v.mail[p], t, 0u, v.rank) + 2u * lane, mine, tag);
         ks.end(v, t, 4);
     }

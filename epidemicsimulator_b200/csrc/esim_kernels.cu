@@ -1743,21 +1743,46 @@ __device__ __forceinline__ void tail_p2p(const DevView& v, uint32_t* dyn_smem, T
 // phases it took 2.2 us on one GPU and 9.6 us on shards (device timeline, profiles/README.md).  Here warp 0 does all of it: load
 // the control block, (shards: send the 8 head words to every peer, wait for theirs, add them up by shuffles,) statistics entry,
 // update_status, next schedule, write back.  The other 31 warps leave at once.
+// `wait_inside`: this tail polls k_step's counter (DevView::tail_flag_wait) and does so HERE, behind the request for the part of
+// the control block only tails write (everything but the sums, the exposure counts and the counter): that round trip is over when
+// the counter is complete.  On shards whose head k_step has already sent (`sent_early`) nothing else is read from the control
+// block at all - the sums arrive through the mailbox - so the wait for the peers starts the moment the counter is complete.
 template <bool P2P>
-__device__ __forceinline__ void tail_quick(const DevView& v, TailSmem& sm) {
+__device__ __forceinline__ void tail_quick(const DevView& v, TailSmem& sm, const bool wait_inside, const KTrace& kt, const uint32_t kt_t) {
     const uint32_t lane = threadIdx.x;
     const uint32_t* gc = reinterpret_cast<const uint32_t*>(v.ctrl);
-    // everything is requested at once: the control block (two words per lane) and, by every lane, the seven words the head is
-    // made of - shards send their head before anything else is looked at
+    // a first look at the counter: if k_step is long done (a step launched on its own, the timed passes of bench.py) everything is
+    // requested in ONE round trip below, as before; otherwise the stable part goes first and the sums follow the wait
+    bool done = !wait_inside;
+    if (wait_inside) {
+        const uint32_t d = lane == 0 ? ld_acquire_gpu(&v.ctrl->blocks_done) : 0u;
+        done = __shfl_sync(0xffffffffu, d, 0) >= v.n_update_blocks;
+    }
     uint32_t cw[2];
 #pragma unroll
     for (uint32_t r = 0; r < 2; ++r) cw[r] = lane + 32u * r < sizeof(Ctrl) / 4 ? __ldcg(gc + lane + 32u * r) : 0u;
     static_assert(sizeof(Ctrl) / 4 <= 64, "two control-block words per lane");
     const uint32_t t = __ldcg(&v.ctrl->t);
-    uint32_t cum[4];
+    if (!done) {
+        KTrace kp; kp.enter = 0;
+        if (v.ktrace_min && lane == 0) kp.enter = global_ns();   // timeline slot 5: control block requested -> counter complete
+        if (lane == 0) {   // see signal_block_done
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(&v.ctrl->blocks_done) < v.n_update_blocks)
+                if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_SIMULATION); break; }   // never hang the GPU
+        }
+        __syncwarp();
+        if (v.ktrace_min) { kp.begin(v, kt_t, 5); kp.end(v, kt_t, 5); }
+    }
+    kt.begin(v, kt_t, 3);
+    const bool sent_early = P2P && v.tail_flag_wait != 0u;   // the k_step block that announced itself last has sent this shard's head (k_step_body)
+    // the sums of k_step's blocks: complete now.  A single GPU tallies from them, a shard without an early head sends them
+    uint32_t cum[4] = {0u, 0u, 0u, 0u}, exp_b = 0u, exp_pt = 0u;
+    if (!sent_early) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cum[k] = __ldcg(&v.ctrl->cum[k]);
-    const uint32_t exp_b = __ldcg(&v.ctrl->new_exp_bldg), exp_pt = __ldcg(&v.ctrl->new_exp_pt);
+        for (int k = 0; k < 4; ++k) cum[k] = __ldcg(&v.ctrl->cum[k]);
+        exp_b = __ldcg(&v.ctrl->new_exp_bldg); exp_pt = __ldcg(&v.ctrl->new_exp_pt);
+    }
     uint32_t cls[5];
     classes_from_cumulative(cum, v.n_pad, v.n, cls);   // class counts of step t + 1 as k_step counted them on this shard
     uint32_t total = 0;
@@ -1765,8 +1790,6 @@ __device__ __forceinline__ void tail_quick(const DevView& v, TailSmem& sm) {
         const uint32_t tag = t + 1u, h = lane & 7u;
         const uint32_t mine = h < 5u ? cls[h] : h == 5u ? exp_b : h == 6u ? exp_pt : 0u;
         KTrace ks; ks.enter = 0; ks.begin(v, t, 4);
-        // a tail that polls k_step's counter finds its head already sent by the block that announced itself last (k_step_body)
-        const bool sent_early = v.tail_flag_wait != 0u;
         if (lane < FEXCH_HEAD && !sent_early)
             for (uint32_t p = 0; p < v.world; ++p) st_pair_sys(mail_ll(v.mail[p], t, 0u, v.rank) + 2u * lane, mine, tag);
         ks.end(v, t, 4);
@@ -1798,13 +1821,15 @@ __device__ __forceinline__ void tail_quick(const DevView& v, TailSmem& sm) {
         total += __shfl_xor_sync(0xffffffffu, total, 16);
         kx.end(v, t, 1);
     }
-    __syncwarp();   // sm.c is complete
+    __syncwarp();   // sm.c is complete - but for the exposure counts, which k_step may still have been adding to when it was requested
     if (P2P) {
         if (lane < 5) sm.tally[lane] = total;
         if (lane == 5) sm.c.new_exp_bldg = total;
         if (lane == 6) sm.c.new_exp_pt = total;
-    } else if (lane < 5) {
-        sm.tally[lane] = cls[lane];
+    } else {
+        if (lane < 5) sm.tally[lane] = cls[lane];
+        if (lane == 5) sm.c.new_exp_bldg = exp_b;
+        if (lane == 6) sm.c.new_exp_pt = exp_pt;
     }
     __syncwarp();
     if (lane == 0) { tail_record<true>(v, sm); tail_epilogue<true>(v, sm); }   // no programme: no picks
@@ -1834,6 +1859,11 @@ __device__ __forceinline__ void tail_fused_body(const DevView& v) {
     // update_status of step t has already run (previous tail): picks are drawn in this step iff the programme is active
     const bool quick = !(v.ctrl->vax_some != 0 && kt_t != 0u);
     if (quick && threadIdx.x >= 32u) return;
+    if (quick) {
+        tail_quick<P2P>(v, sm, v.tail_flag_wait != 0u, kt, kt_t);   // (polls the counter itself, behind its first loads)
+        kt.end(v, kt_t, 3);
+        return;
+    }
     if (v.tail_flag_wait) {
         KTrace kp; kp.enter = 0;
         if (v.ktrace_min && threadIdx.x == 0) kp.enter = global_ns();   // timeline slot 5: control block read -> counter complete
@@ -1842,13 +1872,11 @@ __device__ __forceinline__ void tail_fused_body(const DevView& v) {
             while (ld_acquire_gpu(&v.ctrl->blocks_done) < v.n_update_blocks)
                 if (++spins > (1u << 24)) { v.ctrl->error = (uint32_t)(-ESIM_ERR_SIMULATION); break; }   // never hang the GPU
         }
-        if (quick) __syncwarp(); else __syncthreads();
+        __syncthreads();
         if (v.ktrace_min) { kp.begin(v, kt_t, 5); kp.end(v, kt_t, 5); }
     }
     kt.begin(v, kt_t, 3);
-    if (quick) {
-        tail_quick<P2P>(v, sm);
-    } else if (P2P) {
+    if (P2P) {
         // one memory round trip for everything the tail needs before it can send: control block, mailbox pointers
         const uint32_t tid = threadIdx.x;
         if (tid < sizeof(Ctrl) / 4) reinterpret_cast<uint32_t*>(&sm.c)[tid] = __ldcg(reinterpret_cast<const uint32_t*>(v.ctrl) + tid);

@@ -530,7 +530,7 @@ static void print_ktrace(EsimSim* s) {
     std::vector<unsigned long long> mn(s->ktrace_min.n), mx(s->ktrace_max.n);
     cudaMemcpy(mn.data(), s->ktrace_min.p, s->ktrace_min.bytes(), cudaMemcpyDeviceToHost);
     cudaMemcpy(mx.data(), s->ktrace_max.p, s->ktrace_max.bytes(), cudaMemcpyDeviceToHost);
-    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose/xchg", "pt", "tail", "tail:send", "tail:poll", "tail:picks", "tail:epilogue"};
+    static const char* nm[KTRACE_KERNELS] = {"update/step", "expose/xchg", "pt", "tail", "tail:send", "tail:poll", "tail:picks/scalar", "tail:epilogue"};
     const uint32_t last = s->steps_done, first = last > KTRACE_STEPS - 2 ? last - (KTRACE_STEPS - 2) : 2;
     // everything relative to the end of slot 0 (k_update / k_step) of the same step
     double run[KTRACE_KERNELS] = {}, b_rel[KTRACE_KERNELS] = {}, e_rel[KTRACE_KERNELS] = {}, wait[KTRACE_KERNELS] = {};

@@ -1832,8 +1832,10 @@ __device__ __forceinline__ void tail_quick(const DevView& v, TailSmem& sm, const
         if (lane == 6) sm.c.new_exp_pt = exp_pt;
     }
     __syncwarp();
+    KTrace k6; k6.enter = 0; k6.begin(v, t, 6);   // timeline slot 6 (quick tail): the scalar part
     if (lane == 0) { tail_record<true>(v, sm); tail_epilogue<true>(v, sm); }   // no programme: no picks
     __syncwarp();
+    k6.end(v, t, 6);
     for (uint32_t i = lane; i < sizeof(Ctrl) / 4; i += 32u)
         if (writes_back(sm, i)) reinterpret_cast<uint32_t*>(v.ctrl)[i] = reinterpret_cast<const uint32_t*>(&sm.c)[i];
     if (lane < sizeof(EsimStepStats) / 4 && t - 1 < v.max_steps)

@@ -11,14 +11,56 @@ What is extracted per run (all are properties of the step rules, independent of 
                          (threshold strictness, interventions.rs:139-148) and the per-hour increments
   v_curve                (hour, vaccinated, recovered) every 100 hours: the with-replacement sampling law of
                          simulator.rs:524-552 and the overwrite of Recovered citizens
+  exposures              shape facts of exposures.json (statistics.rs:113-135,186-199): which top-level keys exist, that the
+                         PublicTransport table is written empty, that an area's series holds only the hours with exposures
+
+A second file, tests/golden/reference_recorded_interventions.json, joins the three recorded runs whose console log is in
+the reference tree as well (matched entry by entry on the StatisticEntry lines the log prints) with the intervention events
+of that log ("Mask wearing status has changed: ... at hour H", "Starting vaccination program at hour: H",
+simulator.rs:455-520): the whole infected series of the run + the logged (kind, hour) list.  Feeding the series through
+InterventionStatus::update_status (interventions.rs:110-184) must give exactly these events at exactly these hours.
 """
 import glob
 import json
 import os
+import re
 import sys
 
 REF = "/root/reference/statistics_results"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "reference_recorded_runs.json")
+OUT_EVENTS = os.path.join(os.path.dirname(OUT), "reference_recorded_interventions.json")
+ROOT = "/root/reference"
+ENTRY = re.compile(r"StatisticEntry \{ time_step: (\d+), susceptible: (\d+), exposed: (\d+), infected: (\d+), recovered: (\d+), "
+                   r"vaccinated: (\d+) \}")
+EVENTS = (("mask", re.compile(r"Mask wearing status has changed: (None|Only Public Transport|Everywhere) at hour (\d+)")),
+          ("vaccination", re.compile(r"Starting vaccination program at hour: (\d+)")),
+          ("lockdown", re.compile(r"Lockdown is enabled at hour (\d+)")))
+
+
+def exposure_facts(path):
+    e = json.load(open(path))
+    areas = e.get("OutputArea", {})
+    return {"keys": sorted(e.keys()), "public_transport_entries": len(e.get("PublicTransport", {})),
+            "areas_with_exposures": len(areas), "building_exposures": sum(sum(v) for v in areas.values()),
+            "zero_entries": sum(1 for v in areas.values() for x in v if x == 0),
+            "longest_series": max((len(v) for v in areas.values()), default=0),
+            "all_all_is_one_series": sorted(e.get("All", {}).keys()) == ["All"]}
+
+
+def logged_runs():
+    """The runs of every log below /root/reference, as (log, [StatisticEntry tuples], [(kind, what, hour)])."""
+    logs = [p for pat in ("logs/**/*.log", "simulation_results/*", "*.log") for p in glob.glob(os.path.join(ROOT, pat), recursive=True)]
+    for lf in sorted(p for p in logs if os.path.isfile(p)):
+        for run in re.split(r"Starting simulation", open(lf, errors="replace").read())[1:]:
+            ents = [tuple(map(int, m.groups())) for m in ENTRY.finditer(run)]
+            evs = []
+            for line in run.splitlines():
+                for kind, pat in EVENTS:
+                    m = pat.search(line)
+                    if m:
+                        evs.append([kind, m.group(1) if kind == "mask" else "", int(m.groups()[-1])])
+            if ents:
+                yield os.path.relpath(lf, ROOT), ents, evs
 
 
 def main():
@@ -46,11 +88,27 @@ def main():
             "peak_infected": max(e["infected"] for e in real), "peak_step": max(real, key=lambda e: e["infected"])["time_step"],
             "last": real[-1],
             "v_curve": [[e["time_step"], e["vaccinated"], e["recovered"], e["susceptible"]] for e in real[::100]],
+            "exposures": exposure_facts(os.path.join(os.path.dirname(path), "exposures.json")),
         }
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     json.dump({"source": "statistics_results/**/global_stats.json of NoSuchThingAsRandom/EpidemicSimulator", "runs": runs},
               open(OUT, "w"), indent=1, sort_keys=True)
     print("wrote", OUT, len(runs), "runs")
+
+    joined = {}
+    for log, ents, evs in logged_runs():
+        for path in sorted(glob.glob(os.path.join(REF, "**", "global_stats.json"), recursive=True)):
+            d = json.load(open(path))
+            by = {e["time_step"]: (e["susceptible"], e["exposed"], e["infected"], e["recovered"], e["vaccinated"]) for e in d}
+            if all(by.get(e[0]) == e[1:] for e in ents):     # every line the log printed is in the dump, number by number
+                real = [e for e in d if sum(v for k, v in e.items() if k != "time_step") > 0]
+                assert [e["time_step"] for e in real] == list(range(1, len(real) + 1))
+                joined[os.path.relpath(os.path.dirname(path), REF)] = {
+                    "log": log, "log_entries_matched": len(ents), "population": runs[os.path.relpath(os.path.dirname(path), REF)]["population"],
+                    "infected": [e["infected"] for e in real], "vaccinated": [e["vaccinated"] for e in real], "events": evs}
+    json.dump({"source": "global_stats.json joined with the console log of the same run", "runs": joined}, open(OUT_EVENTS, "w"),
+              separators=(",", ":"), sort_keys=True)
+    print("wrote", OUT_EVENTS, {k: (v["log"], v["events"]) for k, v in joined.items()})
 
 
 if __name__ == "__main__":

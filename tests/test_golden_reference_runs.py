@@ -79,3 +79,86 @@ def test_vaccination_curve_follows_the_with_replacement_law(york_like_run):
     expect_o = m_o * (1.0 - (1.0 - 85.0 / m_o) ** hours_o)
     got = st[-1, F["vaccinated"]]
     assert abs(expect_o - got) < 6.0 * math.sqrt(expect_o) + 0.01 * expect_o
+
+
+# ---- the intervention state machine against the reference's own console logs ----------------------------------------------
+# tests/golden/reference_recorded_interventions.json joins three recorded runs (global_stats.json) with the console log of the
+# SAME run (matched on every StatisticEntry line the log printed): the infected series per hour and the events the reference
+# logged ("Mask wearing status has changed: X at hour H", "Starting vaccination program at hour: H", "Lockdown is enabled at
+# hour H", simulator.rs:455-520).  Those builds (v1.3, v1.6) carried other threshold CONSTANTS than the tree at hand (masks above
+# 20 % / 40 % infected, vaccination above 30 %, lockdown above 60 % - read off the series at the logged hours); the state machine
+# - strict comparisons, the same threshold on the way down, one mask level per hour, the hour being the time step of the
+# statistics entry the share is taken from (statistics.rs:200-254) - is the one of interventions.rs:110-184, and the oracle's
+# restatement of it must log the same events in the same hours.
+EVENTS = json.loads((Path(__file__).parent / "golden" / "reference_recorded_interventions.json").read_text())["runs"]
+MASK_NAMES = {_abi.MASK_NONE: "None", _abi.MASK_PUBLIC_TRANSPORT: "Only Public Transport", _abi.MASK_EVERYWHERE: "Everywhere"}
+
+
+def replay_interventions(run, **thresholds):
+    import ctypes as C
+    from oracle import oracle_py
+    cfg = default_config()
+    for k, v in thresholds.items():
+        setattr(cfg, k, v)
+    state = (C.c_uint32 * 6)(0, 0, 0, 0, _abi.MASK_NONE, 0)
+    out = []
+    for step, infected in enumerate(run["infected"], start=1):
+        ev = oracle_py.lib().oracle_update_interventions(C.byref(cfg), state, infected / run["population"])
+        # BTreeSet<InterventionsEnabled> iterates Lockdown < Vaccination < MaskWearing (interventions.rs:103-108)
+        out += [["lockdown", "", step]] * bool(ev & 1) + [["vaccination", "", step]] * bool(ev & 2)
+        out += [["mask", MASK_NAMES[state[4]], step]] * bool(ev & 4)
+    return out
+
+
+V16 = dict(mask_pt_threshold=0.2, mask_everywhere_threshold=0.4, vaccination_threshold=0.3, lockdown_threshold=0.6)
+
+
+@pytest.mark.parametrize("name", sorted(EVENTS))
+def test_oracle_state_machine_reproduces_the_logged_intervention_events(name):
+    run = EVENTS[name]
+    assert run["log_entries_matched"] >= 25 and len(run["events"]) >= 5
+    assert replay_interventions(run, **V16) == run["events"]
+
+
+def test_logged_events_pin_strictness_and_the_hour_convention():
+    """What a wrong restatement would get wrong on these series: '<=' for '<', a lower threshold on the way down, taking the share
+    of the previous entry, or two mask levels in one hour."""
+    run = EVENTS["v1.6/1946157112TYPE299"]
+    n, inf = run["population"], run["infected"]
+    hours = {}
+    for k, w, h in run["events"]:
+        hours.setdefault((k, w), h)      # the first event of its kind
+    up, vax, top = hours[("mask", "Only Public Transport")], hours[("vaccination", "")], hours[("mask", "Everywhere")]
+    # the logged hour is the first time step whose own entry is above the threshold (inf[h - 1] is the entry of step h)
+    assert inf[up - 2] / n <= 0.2 < inf[up - 1] / n
+    assert inf[vax - 2] / n <= 0.3 < inf[vax - 1] / n
+    assert inf[top - 2] / n <= 0.4 < inf[top - 1] / n
+    # the first vaccinated citizens are counted in the entry of the following hour (tally precedes interventions, simulator.rs:131-152)
+    assert run["vaccinated"][vax - 1] == 0 < run["vaccinated"][vax]
+    # on the way down the same thresholds apply: 912 = first entry below 40 %, 1015 = first entry below 20 %
+    down = [h for k, w, h in run["events"] if k == "mask" and h > top]
+    assert [inf[h - 2] / n >= t > inf[h - 1] / n for h, t in zip(down, (0.4, 0.2))] == [True, True]
+    # a shifted reading (share of the previous entry) or non-strict thresholds do not reproduce the log
+    shifted = dict(run, infected=[inf[0]] + inf[:-1])
+    assert replay_interventions(shifted, **V16) != run["events"]
+    assert replay_interventions(run, **dict(V16, mask_everywhere_threshold=0.39)) != run["events"]
+
+
+def test_recorded_exposure_dumps_have_the_shape_the_dump_writes():
+    """exposures.json of all eight recorded runs (statistics.rs:113-135,186-199): the PublicTransport table exists and is empty
+    (its insert is commented out), an area's series holds only the hours with at least one exposure, 'All' holds one series,
+    and nobody is exposed twice.  `esim_dump_statistics` writes this shape (tests/test_driver.py compares it with the oracle)."""
+    for name, r in GOLD.items():
+        e = r["exposures"]
+        assert e["keys"] == ["All", "OutputArea", "PublicTransport"], name
+        assert e["public_transport_entries"] == 0 and e["zero_entries"] == 0 and e["all_all_is_one_series"], name
+        assert e["longest_series"] <= r["steps_recorded"], name
+        assert 0 < e["building_exposures"] <= r["population"] - r["initial_infected"] - r["last"]["susceptible"], name
+    pop = synthetic_population(n_areas=12, areas_per_school=4, initial_infected=8)
+    orc = Oracle(pop, default_config(seed=3, exposure_chance=0.02))
+    orc.run(400)
+    series = [orc.area_exposures(a) for a in range(pop.n_areas)]
+    st = orc.stats()
+    orc.close()
+    assert all((s > 0).all() for s in series) and max(len(s) for s in series) <= 400
+    assert sum(int(s.sum()) for s in series) == st[:, F["exposures_building"]].sum() > 0

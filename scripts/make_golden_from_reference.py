@@ -87,6 +87,10 @@ def main():
             "first_infected_growth_step": first_ig, "vaccination_start": vax,
             "peak_infected": max(e["infected"] for e in real), "peak_step": max(real, key=lambda e: e["infected"])["time_step"],
             "last": real[-1],
+            # StatisticEntry::disease_exists (statistics.rs:289-291): the run stops on the first entry without susceptible, exposed
+            # and infected citizens - a single susceptible citizen keeps it going to the last hour
+            "first_step_without_exposed_and_infected": next((e["time_step"] for e in real if e["exposed"] == 0 and e["infected"] == 0), None),
+            "first_step_without_s_e_i": next((e["time_step"] for e in real if e["exposed"] == 0 and e["infected"] == 0 and e["susceptible"] == 0), None),
             "v_curve": [[e["time_step"], e["vaccinated"], e["recovered"], e["susceptible"]] for e in real[::100]],
             "exposures": exposure_facts(os.path.join(os.path.dirname(path), "exposures.json")),
         }

@@ -27,6 +27,31 @@ def test_golden_file_facts():
         assert r["first_infected_growth_step"] - r["first_exposed_step"] == 97, name
 
 
+def test_recorded_runs_stop_by_disease_exists_which_counts_susceptible_citizens():
+    """statistics.rs:289-291 / simulator.rs:108-127: six recorded runs end on the first entry without susceptible, exposed and infected
+    citizens; the Yorkshire & Humber run has nobody exposed or infected from hour 2484 on and still runs to hour 5000 because ONE
+    citizen stays susceptible.  The oracle: the same rule on a population where it can be watched."""
+    ended = 0
+    for name, r in GOLD.items():
+        if r["steps_recorded"] < 5000:
+            assert r["first_step_without_s_e_i"] == r["steps_recorded"] == r["last"]["time_step"], name
+            ended += 1
+    assert ended == 6
+    yh = GOLD["v1.6/viking/2013265923TYPE299"]
+    assert yh["first_step_without_exposed_and_infected"] == 2484 and yh["steps_recorded"] == 5000
+    assert yh["last"]["susceptible"] == 1 and yh["first_step_without_s_e_i"] is None
+    pop = synthetic_population(n_areas=3, areas_per_school=3, initial_infected=3)
+    orc = Oracle(pop, default_config(seed=6, exposure_chance=0.0))    # nobody is ever exposed: the seeds recover, the others stay susceptible
+    assert orc.run(600) == 600
+    st = orc.stats()
+    orc.close()
+    assert st[400, F["infected"]] == 0 and st[400, F["exposed"]] == 0 and st[-1, F["susceptible"]] > 0
+    pop.status[:] = _abi.STATUS_INFECTED                                # nobody susceptible: the run ends with the last recovery
+    orc = Oracle(pop, default_config(seed=6))
+    assert orc.run(600) == 337
+    orc.close()
+
+
 @pytest.fixture(scope="module")
 def york_like_run():
     pop = synthetic_population(n_areas=200, areas_per_school=25)

@@ -13,7 +13,10 @@
 // pinned: (1) Philox4x32-10 against the Random123 known-answer vectors and cuRAND's host generator;
 // (2) the disease timers, the vaccination threshold and the vaccination sampling law against facts extracted
 // from the reference's recorded runs (tests/golden/reference_recorded_runs.json, made by
-// scripts/make_golden_from_reference.py); (3) hand-derived known-answer tests of every rule function.
+// scripts/make_golden_from_reference.py), the intervention state machine against the events the reference logged, the daily
+// exposure signature of the schedule (step 9 to work, 17 home, buses in 8 and 16; move, then expose) and the York epidemic of
+// the v1.6 build as a whole against the recorded dumps (tests/test_recorded_runs_distribution.py);
+// (3) hand-derived known-answer tests of every rule function.
 //
 // Randomness: the reference uses rand 0.8 `thread_rng()` (not reproducible).  The oracle consumes the same
 // counter-based stream as the CUDA kernels, restated here independently:

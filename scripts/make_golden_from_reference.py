@@ -19,6 +19,12 @@ the reference tree as well (matched entry by entry on the StatisticEntry lines t
 of that log ("Mask wearing status has changed: ... at hour H", "Starting vaccination program at hour: H",
 simulator.rs:455-520): the whole infected series of the run + the logged (kind, hour) list.  Feeding the series through
 InterventionStatus::update_status (interventions.rs:110-184) must give exactly these events at exactly these hours.
+
+A third file, tests/golden/reference_recorded_diurnal.json: per run the new exposures (the drop of `susceptible` from one entry to
+the next) summed by hour of day (time_step % 24) over the hours before the first vaccination - the daily signature of
+Citizen::execute_time_step (citizen.rs:168-216: at work in the steps with time_step % 24 in 9..16, on public transport in 8 and
+16) and of the order inside a step (move, then expose: simulator.rs:131-152).  For v1.7.1, whose lockdown was decided during
+work hours, also the exposures per infected-hour before and after that lockdown (see tests/test_recorded_runs_distribution.py).
 """
 import glob
 import json
@@ -29,6 +35,7 @@ import sys
 REF = "/root/reference/statistics_results"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "reference_recorded_runs.json")
 OUT_EVENTS = os.path.join(os.path.dirname(OUT), "reference_recorded_interventions.json")
+OUT_DIURNAL = os.path.join(os.path.dirname(OUT), "reference_recorded_diurnal.json")
 ROOT = "/root/reference"
 ENTRY = re.compile(r"StatisticEntry \{ time_step: (\d+), susceptible: (\d+), exposed: (\d+), infected: (\d+), recovered: (\d+), "
                    r"vaccinated: (\d+) \}")
@@ -45,6 +52,36 @@ def exposure_facts(path):
             "zero_entries": sum(1 for v in areas.values() for x in v if x == 0),
             "longest_series": max((len(v) for v in areas.values()), default=0),
             "all_all_is_one_series": sorted(e.get("All", {}).keys()) == ["All"]}
+
+
+def diurnal_facts(real, n):
+    """New exposures by hour of day before the first vaccination; `real` = the entries of global_stats.json with citizens in them."""
+    vi = next((k for k, e in enumerate(real) if e["vaccinated"] > 0), len(real))
+    profile = [0] * 24
+    for k in range(1, vi):
+        profile[real[k]["time_step"] % 24] += real[k - 1]["susceptible"] - real[k]["susceptible"]
+    out = {"population": n, "hours_counted": max(vi - 1, 0), "new_exposures_by_hour_of_day": profile}
+    # the hour the infected share first exceeds HEAD's lockdown threshold (interventions.rs:74), if vaccination has not begun
+    thr = 0.0034
+    # - only for a build that carried HEAD's thresholds (its vaccination began when the share first exceeded HEAD's 0.005)
+    head_constants = 2 <= vi < len(real) and real[vi - 2]["infected"] / n <= 0.005 < real[vi - 1]["infected"] / n
+    k0 = next((k for k, e in enumerate(real[:vi]) if e["infected"] / n > thr), None)
+    if head_constants and k0 is not None and vi - k0 > 48:
+        work = set(range(9, 17))
+
+        def rate(lo, hi, hours):   # exposures per infected-hour in the entries lo..hi whose hour of day is in `hours`
+            new = inf = 0
+            for k in range(max(lo, 1), hi + 1):
+                if real[k]["time_step"] % 24 in hours:
+                    new += real[k - 1]["susceptible"] - real[k]["susceptible"]
+                    inf += real[k - 1]["infected"]
+            return [new, inf]
+        home = set(range(24)) - work
+        out["lockdown_probe"] = {
+            "threshold": thr, "share_first_above_at_step": real[k0]["time_step"], "hour_of_day": real[k0]["time_step"] % 24,
+            "before_240h_work_hours": rate(k0 - 240, k0 - 1, work), "before_240h_other_hours": rate(k0 - 240, k0 - 1, home),
+            "after_work_hours": rate(k0 + 1, vi - 1, work), "after_other_hours": rate(k0 + 1, vi - 1, home)}
+    return out
 
 
 def logged_runs():
@@ -65,6 +102,7 @@ def logged_runs():
 
 def main():
     runs = {}  # keyed by the run directory below statistics_results/
+    diurnal = {}
     for path in sorted(glob.glob(os.path.join(REF, "**", "global_stats.json"), recursive=True)):
         d = json.load(open(path))
         name = os.path.relpath(os.path.dirname(path), REF)
@@ -81,6 +119,7 @@ def main():
             vax = {"first_vaccinated_step": real[vi]["time_step"], "first_vaccinated": real[vi]["vaccinated"],
                    "infected_share_1_before": real[vi - 1]["infected"] / n, "infected_share_2_before": real[vi - 2]["infected"] / n,
                    "susceptible_1_before": real[vi - 1]["susceptible"], "first_increments": incs}
+        diurnal[name] = diurnal_facts(real, n)
         runs[name] = {
             "population": n, "steps_recorded": len(real), "trailing_empty_entry": d[-1]["susceptible"] == 0 and len(d) == len(real) + 1,
             "initial_infected": i0, "first_recovered_step": first_r, "first_exposed_step": first_e,
@@ -98,6 +137,9 @@ def main():
     json.dump({"source": "statistics_results/**/global_stats.json of NoSuchThingAsRandom/EpidemicSimulator", "runs": runs},
               open(OUT, "w"), indent=1, sort_keys=True)
     print("wrote", OUT, len(runs), "runs")
+    json.dump({"source": "statistics_results/**/global_stats.json: new exposures by time_step % 24 before the first vaccination", "runs": diurnal},
+              open(OUT_DIURNAL, "w"), separators=(",", ":"), sort_keys=True)
+    print("wrote", OUT_DIURNAL)
 
     joined = {}
     for log, ents, evs in logged_runs():

@@ -1,0 +1,195 @@
+"""Distribution tier against the reference's OWN recorded outputs: the eight runs whose global_stats.json is in
+the reference tree (tests/golden/reference_recorded_*.json, extracted by scripts/make_golden_from_reference.py).
+
+The reference cannot be run here, its populations came from census / OSM data the image does not have, and its recorded builds
+carried other constants than the tree at hand, so this is not a seed-to-seed band.  What the recorded runs do give:
+
+* the DAILY SIGNATURE of the step rules, independent of the population: new exposures by hour of day jump in the step with
+  time_step % 24 == 9 (everybody reaches the workplace in that step and is exposed there in the same step: move, then expose),
+  fall through the working day while the susceptible colleagues of an infected citizen are used up, rise in the two
+  public-transport steps (8 and 16: the bus trials come on top of the building trials), and fall back in step 17;
+* the SHAPE of the York epidemic under the v1.6 build's thresholds (masks 20 % / 40 %, vaccination at 30 % with 5000 picks per
+  hour - all read from that build's own console log and dumps): four repeats span peak 89 170 - 104 803 infected in hours
+  689 - 946, extinction in hours 1114 - 1426, 88 330 - 95 944 vaccinated and 101 677 - 109 273 recovered at the end.  The oracle on
+  the synthetic York-shaped population, with ONE free number (the per-contact chance of that build, which nothing records; 0.02
+  reproduces the build's ~110 exposures of the first 97 hours), lands inside that span;
+* one lockdown decided during working hours (v1.7.1, hour 975 = 15 o'clock): see the last test for what it shows about that
+  build and about the two lockdown semantics of this repository.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from epidemicsimulator_b200 import _abi, synthetic_population
+from oracle.oracle_py import Oracle, default_config
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+DIURNAL = json.loads((GOLDEN / "reference_recorded_diurnal.json").read_text())["runs"]
+RUNS = json.loads((GOLDEN / "reference_recorded_runs.json").read_text())["runs"]
+F = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
+
+YORK_V16 = ["v1.6/1946157112TYPE299", "v1.6/viking/1946157112TYPE299", "york_stats_results/v1.6", "york_stats_results/v1.6_copy"]
+V16 = YORK_V16 + ["v1.6/viking/2013265923TYPE299"]          # + Yorkshire & Humber, 3.46 M citizens
+# the v1.6 build's constants: thresholds from its console log (reference_recorded_interventions.json, test_golden_reference_runs.py),
+# 5000 picks per hour from the dumps' first increments
+V16_CONSTANTS = dict(mask_pt_threshold=0.2, mask_everywhere_threshold=0.4, vaccination_threshold=0.3, lockdown_threshold=0.6,
+                     vaccination_rate=5000)
+V16_CHANCE = 0.02                                          # the one free number (see above)
+
+
+def signature(c):
+    """The inequalities every recorded run of a build with public transport satisfies; c = new exposures by time_step % 24."""
+    c = [float(x) for x in c]
+    night = c[0:8] + c[18:24]
+    return {
+        "reaches work in step 9": c[9] >= 2.5 * c[8] and c[9] == max(c),
+        "work hours are 9..16": sum(c[9:17]) / 8 >= 2.0 * sum(night) / len(night),
+        "colleagues are used up through the day": all(c[h] > c[h + 1] for h in range(9, 15)),
+        "outbound buses in step 8": c[8] >= 1.5 * c[7],
+        "return buses in step 16": c[16] >= 1.02 * c[15],      # against a fall of 5 - 10 % per hour before it
+        "home again in step 17": c[17] < 0.5 * c[9] and c[18] <= 1.05 * c[17],
+    }
+
+
+def test_recorded_runs_carry_the_daily_signature_of_the_schedule():
+    for name in V16:
+        c = DIURNAL[name]["new_exposures_by_hour_of_day"]
+        assert sum(c) > 100_000
+        sig = signature(c)
+        assert all(sig.values()), (name, sig, c)
+    # every build, also those before public transport existed (v1.3, v1.5) and the slow v1.7.1 epidemic: the step to work is 9
+    for name, d in DIURNAL.items():
+        c = d["new_exposures_by_hour_of_day"]
+        night = c[0:8] + c[18:24]
+        assert c[9] >= 2.5 * c[8] and sum(c[9:17]) / 8 >= 2.0 * sum(night) / len(night), (name, c)
+    # the check has teeth: read with the hour convention off by one in either direction the recorded series fail it
+    c = DIURNAL[YORK_V16[0]]["new_exposures_by_hour_of_day"]
+    assert not all(signature(c[1:] + c[:1]).values()) and not all(signature(c[-1:] + c[:-1]).values())
+
+
+@pytest.fixture(scope="module")
+def york():
+    return synthetic_population(n_areas=637, areas_per_school=25, cross_area_fraction=0.6, initial_infected=10)
+
+
+def oracle_run(pop, seed, rng_mode, steps=3000, **cfg):
+    o = Oracle(pop, default_config(seed=seed, **cfg), rng_mode=rng_mode)
+    o.run(steps)
+    st = o.stats()
+    o.close()
+    return st
+
+
+def facts(st):
+    s, i, v = (st[:, F[k]].astype(np.int64) for k in ("susceptible", "infected", "vaccinated"))
+    ts = st[:, F["time_step"]].astype(np.int64)
+    vi = int(np.argmax(v > 0)) if (v > 0).any() else len(v)
+    c = [0] * 24
+    for k in range(1, vi):
+        c[int(ts[k]) % 24] += int(s[k - 1] - s[k])
+    return dict(profile=c, peak=int(i.max()), peak_step=int(ts[i.argmax()]), vaccination_step=int(ts[vi]) if vi < len(v) else None,
+                last_step=int(ts[-1]), recovered=int(st[-1, F["recovered"]]), vaccinated=int(v[-1]), susceptible=int(s[-1]),
+                exposed_97=int(st[96, F["exposed"]]))
+
+
+@pytest.fixture(scope="module")
+def oracle_v16(york):
+    """Three runs of the counter-based stream (what the CUDA path reproduces bit for bit) and one of the sequential generator
+    consumed the way the reference consumes rand 0.8, to extinction, under the v1.6 build's constants."""
+    cfg = dict(V16_CONSTANTS, exposure_chance=V16_CHANCE)
+    return [facts(oracle_run(york, seed, 0, **cfg)) for seed in (0, 1, 2)] + [facts(oracle_run(york, 7, 1, **cfg))]
+
+
+def test_oracle_shows_the_recorded_daily_signature(oracle_v16):
+    rec = [DIURNAL[n]["new_exposures_by_hour_of_day"] for n in YORK_V16]
+    for f in oracle_v16:
+        c = f["profile"]
+        sig = signature(c)
+        assert all(sig.values()), (sig, c)
+        # and the sizes of the three jumps lie where the four recorded York repeats put them (their span widened by a quarter)
+        for name, ratio in (("9 over 10", lambda x: x[9] / x[10]), ("8 over 7", lambda x: x[8] / x[7]), ("16 over 15", lambda x: x[16] / x[15])):
+            lo, hi = min(ratio(r) for r in rec), max(ratio(r) for r in rec)
+            assert 0.75 * lo <= ratio(c) <= 1.25 * hi, (name, ratio(c), lo, hi)
+
+
+def test_oracle_epidemic_lies_inside_the_span_of_the_recorded_york_runs(oracle_v16):
+    rec = [RUNS[n] for n in YORK_V16]
+    span = {
+        "peak": [r["peak_infected"] for r in rec],
+        "peak_step": [r["peak_step"] for r in rec],
+        "vaccination_step": [r["vaccination_start"]["first_vaccinated_step"] for r in rec],
+        "last_step": [r["first_step_without_s_e_i"] for r in rec],
+        "recovered": [r["last"]["recovered"] for r in rec],
+        "vaccinated": [r["last"]["vaccinated"] for r in rec],
+    }
+    assert (min(span["peak"]), max(span["peak"])) == (89170, 104803) and (min(span["peak_step"]), max(span["peak_step"])) == (689, 946)
+    for f in oracle_v16:
+        assert f["susceptible"] == 0            # like every recorded v1.6 run: nobody is left susceptible
+        assert 54 <= f["exposed_97"] <= 216     # the calibration: the recorded build had 108 exposed citizens in hour 97
+        for key, values in span.items():
+            lo, hi = min(values), max(values)
+            # the synthetic population is York-shaped, not York: the recorded span widened by 5 % of its centre on both sides
+            pad = 0.05 * (lo + hi) / 2
+            assert lo - pad <= f[key] <= hi + pad, (key, f[key], lo, hi)
+
+
+def test_the_span_constrains_the_contact_chance_to_its_order_of_magnitude(york):
+    """What the comparison above can and cannot tell: ten times the calibrated chance, or a tenth of it, leaves the recorded span."""
+    rec = [RUNS[n] for n in YORK_V16]
+    fast = facts(oracle_run(york, 0, 0, **dict(V16_CONSTANTS, exposure_chance=10 * V16_CHANCE)))
+    assert fast["peak"] > 1.15 * max(r["peak_infected"] for r in rec) and fast["vaccinated"] < 0.85 * min(r["last"]["vaccinated"] for r in rec)
+    assert fast["last_step"] < 0.95 * min(r["first_step_without_s_e_i"] for r in rec)
+    slow = oracle_run(york, 0, 0, steps=1100, **dict(V16_CONSTANTS, exposure_chance=0.1 * V16_CHANCE))
+    i = slow[:, F["infected"]]
+    assert i.argmax() + 1 > 1.1 * max(r["peak_step"] for r in rec)    # still rising when the last recorded run had long peaked
+
+
+def per_infected_hour(st, lo, hi, work):
+    """New exposures per infected citizen and hour over the entries lo..hi whose hour of day is / is not a working hour."""
+    s, i, ts = (st[:, F[k]].astype(np.int64) for k in ("susceptible", "infected", "time_step"))
+    new = inf = 0
+    for k in range(max(lo, 1), min(hi, len(s) - 1) + 1):
+        if (9 <= int(ts[k]) % 24 <= 16) == work:
+            new += int(s[k - 1] - s[k])
+            inf += int(i[k - 1])
+    return new / max(inf, 1)
+
+
+def test_a_lockdown_decided_during_working_hours():
+    """The only recorded lockdown that fell into working hours: v1.7.1 (a build with the thresholds of the tree at hand - its
+    vaccination began exactly above 0.5 %), infected share first above 0.34 % in hour 975 = 15 o'clock.  Before it an infected
+    citizen caused three times as many exposures per working hour as per other hour; after it the daily rhythm is gone and every
+    hour runs at the HOME rate: that build sent its citizens home.  The tree at hand does not - the assignment is commented out
+    ("TODO THIS IS BROKEN", simulator.rs:467-479) and `execute_time_step` only freezes the schedule (citizen.rs:176), so everybody
+    stays at work and the workplace trials go on around the clock.  Parity mode follows the tree at hand; the corrected mode
+    (ESIM_CFG_CORRECTED) is the send-home semantics and reproduces what the recorded run shows."""
+    p = DIURNAL["v1.7.1/1946157112TYPE299"]["lockdown_probe"]
+    assert p["share_first_above_at_step"] == 975 and p["hour_of_day"] == 15
+    rate = lambda key: p[key][0] / p[key][1]
+    work, home = rate("before_240h_work_hours"), rate("before_240h_other_hours")
+    assert 2.5 * home < work < 3.5 * home
+    for key in ("after_work_hours", "after_other_hours"):
+        assert 0.8 * home < rate(key) < 1.25 * home and rate(key) < 0.5 * work
+
+    pop = synthetic_population(n_areas=120, areas_per_school=25, cross_area_fraction=0.6, initial_infected=40)
+    base = dict(seed=3, exposure_chance=0.004, vaccination_threshold=-1.0, mask_pt_threshold=2.0, mask_everywhere_threshold=2.0)
+    free = oracle_run(pop, steps=900, rng_mode=0, lockdown_threshold=-1.0, **base)
+    i, ts = free[:, F["infected"]].astype(float), free[:, F["time_step"]]
+    # a threshold the infected share first exceeds at 15 o'clock
+    k0 = next(k for k in range(300, len(i)) if ts[k] % 24 == 15 and i[k] > i[:k].max() and i[k] / pop.n_citizens > 0.01)
+    threshold = (i[k0] + i[:k0].max()) / 2 / pop.n_citizens
+    after = {}
+    for mode, flags in (("parity", 0), ("corrected", _abi.CFG_CORRECTED)):
+        st = oracle_run(pop, steps=int(ts[k0]) + 130, rng_mode=0, lockdown_threshold=threshold, flags=flags, **base)
+        locked = st[:, F["lockdown_hours"]] != _abi.NONE_U32
+        assert int(st[int(np.argmax(locked)), F["time_step"]]) == int(ts[k0]) and locked[int(np.argmax(locked)):].all()
+        w0, h0 = per_infected_hour(st, k0 - 240, k0 - 1, True), per_infected_hour(st, k0 - 240, k0 - 1, False)
+        assert w0 > 3 * h0
+        after[mode] = (per_infected_hour(st, k0 + 1, k0 + 120, True) / h0, per_infected_hour(st, k0 + 1, k0 + 120, False) / h0)
+    # both semantics lose the daily rhythm ...
+    for a, b in after.values():
+        assert 0.7 < a / b < 1.4
+    # ... the tree at hand keeps the workplace trials going (well above the home rate), sending home drops to the home rate
+    assert min(after["parity"]) > 1.8 and max(after["corrected"]) < 1.25 and min(after["corrected"]) > 0.5

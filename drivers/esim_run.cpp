@@ -9,8 +9,8 @@
 // The reference loads census / OSM data, builds the population in-process and calls `Simulator::simulate(output_name)`
 // (sim/src/simulator.rs:108-127).  Here the population arrives as the binary file a Rust exporter of `SimulatorBuilder`
 // writes (include/esim_popgen.h) - or, with --synthetic, from the deterministic generator - and
-// the loop below is `simulate`: steps in chunks of DEBUG_ITERATION_PRINT (sim/src/config.rs:34) with the reference's
-// progress line, then `dump_to_file`.  Everything per time step runs in libesim_b200.so; there is no CPU path.
+// the loop below is `simulate`: the reference's progress line after the time steps 1, 51, 101, ... (DEBUG_ITERATION_PRINT,
+// sim/src/config.rs:34), then `dump_to_file`.  Everything per time step runs in libesim_b200.so; there is no CPU path.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,12 +18,34 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "esim.h"
 #include "esim_popgen.h"
 
 static int fail(const char* what, int code, EsimSim* sim) {
     fprintf(stderr, "esim_run: %s failed (%d): %s\n", what, code, esim_last_error(sim) ? esim_last_error(sim) : "");
     return 1;
+}
+
+// get_memory_usage (config.rs:42-47): the program size of /proc/self/statm in whole MB, printed in GB with two decimals
+static std::string memory_usage() {
+    unsigned long pages = 0;
+    if (FILE* f = fopen("/proc/self/statm", "r")) {
+        if (fscanf(f, "%lu", &pages) != 1) pages = 0;
+        fclose(f);
+    }
+    const unsigned long mb = pages * (unsigned long)sysconf(_SC_PAGESIZE) / 1024 / 1024;
+    char buf[32];
+    snprintf(buf, sizeof buf, "%.2f GB", (double)mb / 1024.0);
+    return buf;
+}
+
+// the line of simulator.rs:118-121: "Completed {: >3} time steps, in: {: >6} seconds  Statistics: {:?},   Memory usage: {}"
+static void print_progress(uint32_t steps, double seconds, const EsimStepStats& st) {
+    printf("Completed %3u time steps, in: %6.2f seconds  Statistics: StatisticEntry { time_step: %u, susceptible: %u, exposed: %u, "
+           "infected: %u, recovered: %u, vaccinated: %u },   Memory usage: %s\n",
+           steps, seconds, st.time_step, st.susceptible, st.exposed, st.infected, st.recovered, st.vaccinated, memory_usage().c_str());
 }
 
 int main(int argc, char** argv) {
@@ -46,6 +68,12 @@ int main(int argc, char** argv) {
             for (const char* q = a.c_str() + 10; *q;) { devices.push_back((int32_t)strtol(q, const_cast<char**>(&q), 10)); if (*q == ',') ++q; }
         }
         else if (a == "--corrected") corrected = true;
+        else if (a == "--progress-line-selftest") {   // prints the progress line for a fixed entry (needs no device; tests/test_driver.py)
+            EsimStepStats st{};
+            st.time_step = 1; st.susceptible = 197591; st.exposed = 3; st.infected = 9;
+            print_progress(50, 0.03, st);
+            return 0;
+        }
         else if (a[0] != '-') path = a;
         else { fprintf(stderr, "esim_run: unknown option %s\n", a.c_str()); return 2; }
     }
@@ -87,22 +115,24 @@ int main(int argc, char** argv) {
            std::chrono::duration<double>(std::chrono::steady_clock::now() - t_total).count());
     printf("Starting simulation with %u areas\n", pop.n_areas);
 
-    // Simulator::simulate: the progress line every DEBUG_ITERATION_PRINT steps (simulator.rs:118-121)
+    // Simulator::simulate (simulator.rs:108-127): `for time_step in 0..max_time_step { if !step()? { break } if time_step % 50 == 0
+    // { println!(..) } }` - the progress line follows the time steps 1, 51, 101, ... while the disease exists, always says
+    // "Completed  50 time steps" and prints the entry with the derived Debug of StatisticEntry (statistics.rs:206-215) and the
+    // memory figure of config.rs:42-47.  The loop stays on the device between two lines.
     constexpr uint32_t DEBUG_ITERATION_PRINT = 50;
     auto t_chunk = std::chrono::steady_clock::now();
     uint32_t done = 0;
     int alive = 1;
     while (alive == 1 && done < cfg.max_time_step) {
         uint32_t n = 0;
-        alive = esim_run(sim, DEBUG_ITERATION_PRINT, &n);
+        alive = esim_run(sim, done == 0 ? 1u : DEBUG_ITERATION_PRINT, &n);
         if (alive < 0) return fail("esim_run", alive, sim);
         done += n;
         if (n == 0) break;
         EsimStepStats st;
-        if (esim_read_stats(sim, done - 1, 1, &st) == 1) {
+        if (alive == 1 && (done - 1) % DEBUG_ITERATION_PRINT == 0 && esim_read_stats(sim, done - 1, 1, &st) == 1) {
             const auto now = std::chrono::steady_clock::now();
-            printf("Completed %3u time steps, in: %6.2f seconds  Statistics: Hour: %u, Susceptible: %u, Exposed: %u, Infected: %u, Recovered: %u, Vaccinated: %u\n",
-                   n, std::chrono::duration<double>(now - t_chunk).count(), st.time_step, st.susceptible, st.exposed, st.infected, st.recovered, st.vaccinated);
+            print_progress(DEBUG_ITERATION_PRINT, std::chrono::duration<double>(now - t_chunk).count(), st);
             t_chunk = now;
         }
     }

@@ -21,6 +21,25 @@ from .population import Population
 DEBUG_ITERATION_PRINT = 50  # sim/src/config.rs:34
 
 
+def memory_usage() -> str:
+    """get_memory_usage (config.rs:42-47): the program size of /proc/self/statm in whole MB, as GB with two decimals."""
+    import os
+    try:
+        with open("/proc/self/statm") as f:
+            pages = int(f.read().split()[0])
+    except (OSError, ValueError, IndexError):
+        pages = 0
+    return "%.2f GB" % ((pages * os.sysconf("SC_PAGE_SIZE") // 1024 // 1024) / 1024.0)
+
+
+def progress_line(seconds: float, entry) -> str:
+    """The line of simulator.rs:118-121 - "Completed {: >3} time steps, in: {: >6} seconds  Statistics: {:?},   Memory usage: {}" -
+    with the derived Debug of StatisticEntry (statistics.rs:206-215); `entry` = one row of statistics()."""
+    return ("Completed %3d time steps, in: %6s seconds  Statistics: StatisticEntry { time_step: %d, susceptible: %d, exposed: %d, "
+            "infected: %d, recovered: %d, vaccinated: %d },   Memory usage: %s" % (
+                (DEBUG_ITERATION_PRINT, "%.2f" % seconds) + tuple(int(x) for x in entry[:6]) + (memory_usage(),)))
+
+
 def default_config(**overrides) -> _abi.EsimConfig:
     """DiseaseModel::covid() + default intervention thresholds (disease.rs:118-129, interventions.rs:50-57,71-78)."""
     cfg = _abi.EsimConfig()
@@ -182,21 +201,27 @@ class Simulator:
         self._check(self._lib.esim_run_timed(self._h, int(max_steps), C.byref(n)))
         return int(n.value)
 
+    def _run_alive(self, max_steps: int):
+        """esim_run: (steps executed, True while the disease exists)."""
+        n = C.c_uint32(0)
+        rc = self._check(self._lib.esim_run(self._h, int(max_steps), C.byref(n)))
+        return int(n.value), rc == 1
+
     def simulate(self, output_name: Optional[str] = None, area_codes=None, verbose: bool = True) -> None:
-        """Simulator::simulate (simulator.rs:108-127): until the disease is eradicated or max_time_step, then dump."""
+        """Simulator::simulate (simulator.rs:108-127): until the disease is eradicated or max_time_step, then dump.  The
+        reference prints its progress line after the time steps 1, 51, 101, ... (loop index % 50 == 0) while the disease
+        exists; the loop stays on the device between two lines."""
         start = time.time()
         done = 0
         while done < self.cfg.max_time_step:
-            n = self.run(min(DEBUG_ITERATION_PRINT, self.cfg.max_time_step - done))
+            n, alive = self._run_alive(1 if done == 0 else DEBUG_ITERATION_PRINT)
             done += n
             if n == 0:
                 break
-            if verbose:
-                st = self.statistics(done - 1, 1)
-                print("Completed %3d time steps, in: %6s seconds  Statistics: %s" % (
-                    DEBUG_ITERATION_PRINT, "%.2f" % (time.time() - start), dict(zip(_abi.STATS_FIELDS[:6], st[0][:6]))))
+            if verbose and alive and (done - 1) % DEBUG_ITERATION_PRINT == 0:
+                print(progress_line(time.time() - start, self.statistics(done - 1, 1)[0]))
                 start = time.time()
-            if n < DEBUG_ITERATION_PRINT:
+            if not alive:
                 break
         if output_name is not None:
             self.dump_statistics(output_name, area_codes)

@@ -54,22 +54,28 @@ impl Simulator {
         Ok(check(self.handle, unsafe { ffi::esim_step(self.handle, &mut s) })? == 1)
     }
 
-    /// simulator.rs:108-127: the loop stays on the device between two progress lines
+    /// simulator.rs:108-127: the progress line follows the time steps 1, 51, 101, ... (loop index % DEBUG_ITERATION_PRINT == 0)
+    /// while the disease exists; the loop stays on the device between two lines
     pub fn simulate(&mut self, output_name: String) -> anyhow::Result<()> {
         let mut start_time = Instant::now();
         let mut done = 0u32;
         while done < self.max_time_step {
             let mut n = 0u32;
-            let alive = check(self.handle, unsafe { ffi::esim_run(self.handle, DEBUG_ITERATION_PRINT as u32, &mut n) })?;
+            let chunk = if done == 0 { 1 } else { DEBUG_ITERATION_PRINT as u32 };
+            let alive = check(self.handle, unsafe { ffi::esim_run(self.handle, chunk, &mut n) })? == 1;
             done += n;
-            if n > 0 {
+            if n == 0 { break; }
+            if alive && (done - 1) % DEBUG_ITERATION_PRINT as u32 == 0 {
                 let mut last = ffi::EsimStepStats::default();
                 check(self.handle, unsafe { ffi::esim_read_stats(self.handle, done - 1, 1, &mut last) })?;
-                println!("Completed {: >3} time steps, in: {: >6} seconds  Statistics: {:?},   Memory usage: {}",
-                         n, format!("{:.2}", start_time.elapsed().as_secs_f64()), last, get_memory_usage()?);
+                // the derived Debug of the reference's StatisticEntry (statistics.rs:206-215)
+                let entry = format!("StatisticEntry {{ time_step: {}, susceptible: {}, exposed: {}, infected: {}, recovered: {}, vaccinated: {} }}",
+                                    last.time_step, last.susceptible, last.exposed, last.infected, last.recovered, last.vaccinated);
+                println!("Completed {: >3} time steps, in: {: >6} seconds  Statistics: {},   Memory usage: {}",
+                         DEBUG_ITERATION_PRINT, format!("{:.2}", start_time.elapsed().as_secs_f64()), entry, get_memory_usage()?);
                 start_time = Instant::now();
             }
-            if alive == 0 || n == 0 { break; }
+            if !alive { break; }
         }
         let dir = CString::new(output_name).context("output name")?;
         let codes: Vec<*const c_char> = self.area_codes.iter().map(|c| c.as_ptr()).collect();

@@ -9,7 +9,7 @@
 // The reference loads census / OSM data, builds the population in-process and calls `Simulator::simulate(output_name)`
 // (sim/src/simulator.rs:108-127).  Here the population arrives as the binary file a Rust exporter of `SimulatorBuilder`
 // writes (include/esim_popgen.h) - or, with --synthetic, from the deterministic generator - and
-// the loop below is `simulate`: the reference's progress line after the time steps 1, 51, 101, ... (DEBUG_ITERATION_PRINT,
+// the loop below is `simulate`: the reference's progress line for the time steps 1, 51, 101, ... (DEBUG_ITERATION_PRINT,
 // sim/src/config.rs:34), then `dump_to_file`.  Everything per time step runs in libesim_b200.so; there is no CPU path.
 #include <chrono>
 #include <cstdio>
@@ -116,25 +116,26 @@ int main(int argc, char** argv) {
     printf("Starting simulation with %u areas\n", pop.n_areas);
 
     // Simulator::simulate (simulator.rs:108-127): `for time_step in 0..max_time_step { if !step()? { break } if time_step % 50 == 0
-    // { println!(..) } }` - the progress line follows the time steps 1, 51, 101, ... while the disease exists, always says
-    // "Completed  50 time steps" and prints the entry with the derived Debug of StatisticEntry (statistics.rs:206-215) and the
-    // memory figure of config.rs:42-47.  The loop stays on the device between two lines.
+    // { println!(..) } }` - the reference's progress lines show the entries of the time steps 1, 51, 101, ... while the disease
+    // exists, always say "Completed  50 time steps" and print the entry with the derived Debug of StatisticEntry
+    // (statistics.rs:206-215) and the memory figure of config.rs:42-47.  Here the loop stays on the device for
+    // DEBUG_ITERATION_PRINT steps at a time, so the line of time step 50 k + 1 is printed when that chunk returns.
     constexpr uint32_t DEBUG_ITERATION_PRINT = 50;
     auto t_chunk = std::chrono::steady_clock::now();
     uint32_t done = 0;
     int alive = 1;
     while (alive == 1 && done < cfg.max_time_step) {
         uint32_t n = 0;
-        alive = esim_run(sim, done == 0 ? 1u : DEBUG_ITERATION_PRINT, &n);
+        alive = esim_run(sim, DEBUG_ITERATION_PRINT, &n);
         if (alive < 0) return fail("esim_run", alive, sim);
-        done += n;
         if (n == 0) break;
-        EsimStepStats st;
-        if (alive == 1 && (done - 1) % DEBUG_ITERATION_PRINT == 0 && esim_read_stats(sim, done - 1, 1, &st) == 1) {
+        EsimStepStats st;   // the first entry of the chunk: done is a multiple of DEBUG_ITERATION_PRINT here
+        if (esim_read_stats(sim, done, 1, &st) == 1 && (st.susceptible | st.exposed | st.infected) != 0) {   // disease_exists()
             const auto now = std::chrono::steady_clock::now();
             print_progress(DEBUG_ITERATION_PRINT, std::chrono::duration<double>(now - t_chunk).count(), st);
             t_chunk = now;
         }
+        done += n;
     }
     rc = esim_dump_statistics(sim, output.c_str(), codes.empty() ? nullptr : codes.data());
     if (rc < 0) return fail("esim_dump_statistics", rc, sim);

@@ -209,18 +209,21 @@ class Simulator:
 
     def simulate(self, output_name: Optional[str] = None, area_codes=None, verbose: bool = True) -> None:
         """Simulator::simulate (simulator.rs:108-127): until the disease is eradicated or max_time_step, then dump.  The
-        reference prints its progress line after the time steps 1, 51, 101, ... (loop index % 50 == 0) while the disease
-        exists; the loop stays on the device between two lines."""
+        reference's progress lines show the entries of the time steps 1, 51, 101, ... (loop index % 50 == 0) while the disease
+        exists; here the loop stays on the device for 50 steps at a time, so the line of time step 50 k + 1 is printed when
+        that chunk returns."""
         start = time.time()
         done = 0
         while done < self.cfg.max_time_step:
-            n, alive = self._run_alive(1 if done == 0 else DEBUG_ITERATION_PRINT)
-            done += n
+            n, alive = self._run_alive(DEBUG_ITERATION_PRINT)
             if n == 0:
                 break
-            if verbose and alive and (done - 1) % DEBUG_ITERATION_PRINT == 0:
-                print(progress_line(time.time() - start, self.statistics(done - 1, 1)[0]))
-                start = time.time()
+            if verbose:
+                entry = self.statistics(done, 1)[0]     # the first entry of the chunk: `done` is a multiple of 50 here
+                if any(int(x) for x in entry[1:4]):     # StatisticEntry::disease_exists (statistics.rs:289-291)
+                    print(progress_line(time.time() - start, entry))
+                    start = time.time()
+            done += n
             if not alive:
                 break
         if output_name is not None:

@@ -54,27 +54,27 @@ impl Simulator {
         Ok(check(self.handle, unsafe { ffi::esim_step(self.handle, &mut s) })? == 1)
     }
 
-    /// simulator.rs:108-127: the progress line follows the time steps 1, 51, 101, ... (loop index % DEBUG_ITERATION_PRINT == 0)
-    /// while the disease exists; the loop stays on the device between two lines
+    /// simulator.rs:108-127: the reference's progress lines show the entries of the time steps 1, 51, 101, ... (loop index %
+    /// DEBUG_ITERATION_PRINT == 0) while the disease exists; the loop stays on the device for DEBUG_ITERATION_PRINT steps at a
+    /// time, so the line of time step 50 k + 1 is printed when that chunk returns
     pub fn simulate(&mut self, output_name: String) -> anyhow::Result<()> {
         let mut start_time = Instant::now();
         let mut done = 0u32;
         while done < self.max_time_step {
             let mut n = 0u32;
-            let chunk = if done == 0 { 1 } else { DEBUG_ITERATION_PRINT as u32 };
-            let alive = check(self.handle, unsafe { ffi::esim_run(self.handle, chunk, &mut n) })? == 1;
-            done += n;
+            let alive = check(self.handle, unsafe { ffi::esim_run(self.handle, DEBUG_ITERATION_PRINT as u32, &mut n) })? == 1;
             if n == 0 { break; }
-            if alive && (done - 1) % DEBUG_ITERATION_PRINT as u32 == 0 {
-                let mut last = ffi::EsimStepStats::default();
-                check(self.handle, unsafe { ffi::esim_read_stats(self.handle, done - 1, 1, &mut last) })?;
+            let mut first = ffi::EsimStepStats::default();   // the first entry of the chunk: `done` is a multiple of 50 here
+            check(self.handle, unsafe { ffi::esim_read_stats(self.handle, done, 1, &mut first) })?;
+            if first.susceptible != 0 || first.exposed != 0 || first.infected != 0 {   // StatisticEntry::disease_exists
                 // the derived Debug of the reference's StatisticEntry (statistics.rs:206-215)
                 let entry = format!("StatisticEntry {{ time_step: {}, susceptible: {}, exposed: {}, infected: {}, recovered: {}, vaccinated: {} }}",
-                                    last.time_step, last.susceptible, last.exposed, last.infected, last.recovered, last.vaccinated);
+                                    first.time_step, first.susceptible, first.exposed, first.infected, first.recovered, first.vaccinated);
                 println!("Completed {: >3} time steps, in: {: >6} seconds  Statistics: {},   Memory usage: {}",
                          DEBUG_ITERATION_PRINT, format!("{:.2}", start_time.elapsed().as_secs_f64()), entry, get_memory_usage()?);
                 start_time = Instant::now();
             }
+            done += n;
             if !alive { break; }
         }
         let dir = CString::new(output_name).context("output name")?;

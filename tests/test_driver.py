@@ -77,9 +77,9 @@ def test_progress_line_is_the_reference_s(driver):
         assert line.startswith(REFERENCE_LINE) and re.fullmatch(r"\d+\.\d\d GB", line[len(REFERENCE_LINE):]), line
 
 
-def test_simulate_prints_after_the_time_steps_1_51_101(capsys):
-    """The reference's loop prints when its 0-based index is a multiple of 50, i.e. after the time steps 1, 51, 101, ..., and not
-    for the step in which the disease disappeared (simulator.rs:114-121)."""
+def test_simulate_prints_the_lines_of_the_time_steps_1_51_101(capsys):
+    """The reference's loop prints when its 0-based index is a multiple of 50, i.e. the entries of the time steps 1, 51, 101, ...,
+    and not for the step in which the disease disappeared (simulator.rs:114-121)."""
     from types import SimpleNamespace
     from epidemicsimulator_b200.simulator import Simulator
 
@@ -95,7 +95,9 @@ def test_simulate_prints_after_the_time_steps_1_51_101(capsys):
             return n, self.done < self.dies_at
 
         def statistics(self, first=0, count=None):
-            return np.array([[first + 1, 100, 1, 2, 3, 4, 0, 0]], dtype=np.uint32)
+            assert first < self.done
+            alive = first + 1 < self.dies_at
+            return np.array([[first + 1, 100 * alive, 1 * alive, 2 * alive, 3, 4, 0, 0]], dtype=np.uint32)
 
         def dump_statistics(self, directory, area_codes=None):
             self.dumped = directory
@@ -106,11 +108,11 @@ def test_simulate_prints_after_the_time_steps_1_51_101(capsys):
         __del__ = close
 
     for max_steps, dies_at, expected in ((400, 10**9, [1, 51, 101, 151, 201, 251, 301, 351]), (400, 151, [1, 51, 101]),
-                                         (400, 120, [1, 51, 101]), (51, 10**9, [1, 51]), (1, 10**9, [1])):
+                                         (400, 120, [1, 51, 101]), (51, 10**9, [1, 51]), (1, 10**9, [1]), (400, 1, [])):
         sim = Fake(max_steps, dies_at)
         sim.simulate("out/")
         lines = capsys.readouterr().out.splitlines()
         assert [int(ln.split("time_step: ")[1].split(",")[0]) for ln in lines] == expected, (max_steps, dies_at, lines)
         assert all(ln.startswith("Completed  50 time steps, in: ") for ln in lines)
-        assert sim.dumped == "out/" and sim.calls[0] == 1 and all(c == 50 for c in sim.calls[1:])
+        assert sim.dumped == "out/" and all(c == 50 for c in sim.calls)
         assert sim.done == min(max_steps, dies_at)

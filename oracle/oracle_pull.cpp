@@ -241,6 +241,7 @@ extern "C" {
 
 int pull_create(const EsimConfig* cfg, const EsimPopulationSoA* p, PullShard** out) {
     if (!cfg || !p || !out) return ESIM_ERR_INVALID_ARGUMENT;
+    if (cfg->flags & ESIM_CFG_CORRECTED) return ESIM_ERR_INVALID_ARGUMENT;   // the pull model states the parity rules only
     PullShard* s = new PullShard();
     s->cfg = *cfg;
     s->n = p->n_citizens; s->B = p->n_buildings; s->Rn = p->n_rooms;

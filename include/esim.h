@@ -91,7 +91,9 @@ typedef struct EsimSim EsimSim; /* opaque: owns device memory, streams, graphs, 
  * Model constants.  In the reference these are compile-time: DiseaseModel::covid()
  * (sim/src/disease.rs:118-129), InterventionThresholds::default() (sim/src/interventions.rs:71-78),
  * MaskStatus::get_threshold (interventions.rs:50-57), BUS_CAPACITY (sim/src/config.rs:37).
- * esim_default_config() fills in exactly those values.
+ * esim_default_config() fills in exactly those values.  esim_create refuses what the packed state word and the tail's
+ * pick table cannot hold (ESIM_ERR_INVALID_ARGUMENT, limits beside the fields); everything the reference's tree and its
+ * recorded builds used lies inside, except the 5000 picks per hour of the recorded v1.6 build.
  */
 typedef struct EsimConfig {
     double   exposure_chance;           /* 0.00055 */
@@ -100,11 +102,11 @@ typedef struct EsimConfig {
     double   vaccination_threshold;     /* 0.005  ; negative = Option::None */
     double   mask_pt_threshold;         /* 0.001   */
     double   mask_everywhere_threshold; /* 0.0022  */
-    uint32_t exposed_time;              /* 96   */
+    uint32_t exposed_time;              /* 96   ; exposed_time + infected_time < 1022 (both are u16 in the reference) */
     uint32_t infected_time;             /* 336  */
-    uint32_t max_time_step;             /* 5000 */
-    uint32_t vaccination_rate;          /* 85*18 = 1530 */
-    uint32_t bus_capacity;              /* 20   */
+    uint32_t max_time_step;             /* 5000 ; 1 .. 31742 (u16 in the reference) */
+    uint32_t vaccination_rate;          /* 85*18 = 1530 ; at most 4000 picks per hour (u16 in the reference) */
+    uint32_t bus_capacity;              /* 20   ; positive */
     uint32_t flags;                     /* ESIM_CFG_*  */
     uint64_t seed;                      /* key of the counter-based Philox4x32-10 stream */
     int32_t  device;                    /* CUDA device ordinal */

@@ -24,7 +24,8 @@ A third file, tests/golden/reference_recorded_diurnal.json: per run the new expo
 the next) summed by hour of day (time_step % 24) over the hours before the first vaccination - the daily signature of
 Citizen::execute_time_step (citizen.rs:168-216: at work in the steps with time_step % 24 in 9..16, on public transport in 8 and
 16) and of the order inside a step (move, then expose: simulator.rs:131-152).  For v1.7.1, whose lockdown was decided during
-work hours, also the exposures per infected-hour before and after that lockdown (see tests/test_recorded_runs_distribution.py).
+work hours, also the exposures per infected-hour before and after that lockdown, and before and after masks became compulsory
+everywhere (see tests/test_recorded_runs_distribution.py).
 """
 import glob
 import json
@@ -81,6 +82,22 @@ def diurnal_facts(real, n):
             "threshold": thr, "share_first_above_at_step": real[k0]["time_step"], "hour_of_day": real[k0]["time_step"] % 24,
             "before_240h_work_hours": rate(k0 - 240, k0 - 1, work), "before_240h_other_hours": rate(k0 - 240, k0 - 1, home),
             "after_work_hours": rate(k0 + 1, vi - 1, work), "after_other_hours": rate(k0 + 1, vi - 1, home)}
+        # MaskStatus::Everywhere under HEAD's thresholds (interventions.rs:50-57,150-181), replayed on the recorded series
+        kind, ke = 0, None
+        for k, e in enumerate(real[:k0 + 1]):
+            share = e["infected"] / n
+            if kind == 0 and 0.001 < share:
+                kind = 1
+            elif kind == 1 and share < 0.001:
+                kind = 0
+            elif kind == 1 and 0.0022 < share:
+                kind, ke = 2, k
+                break
+        if ke is not None and k0 - ke >= 24 and ke >= 96:
+            out["mask_probe"] = {
+                "everywhere_decided_at_step": real[ke]["time_step"], "lockdown_decided_at_step": real[k0]["time_step"],
+                "before_96h_work_hours": rate(ke - 95, ke, work), "after_work_hours": rate(ke + 1, k0, work),
+                "before_96h_other_hours": rate(ke - 95, ke, home), "after_other_hours": rate(ke + 1, k0, home)}
     return out
 
 

@@ -193,3 +193,37 @@ def test_a_lockdown_decided_during_working_hours():
         assert 0.7 < a / b < 1.4
     # ... the tree at hand keeps the workplace trials going (well above the home rate), sending home drops to the home rate
     assert min(after["parity"]) > 1.8 and max(after["corrected"]) < 1.25 and min(after["corrected"]) > 0.5
+
+
+def work_hour_rate(st, lo, hi):
+    return per_infected_hour(st, lo, hi, True)
+
+
+def test_masks_everywhere_did_not_halve_workplace_transmission():
+    """Citizen::expose hands MaskStatus::None to the COMPLIANT citizens and the global status to everybody else
+    (citizen.rs:228-232): with 80 % compliance and an effectiveness of 0.7, masks everywhere cut transmission by 0.2 x 0.7 = 14 %,
+    where protecting the compliant would cut it by 56 %.  The recorded v1.7.1 run (thresholds of the tree at hand) made masks
+    compulsory everywhere in hour 926 and locked down in hour 975: over the working hours in between an infected citizen caused
+    as many exposures per hour as over the four days before - the inverted rule is what that build ran.  The oracle shows both
+    sizes: parity mode (the inverted rule) against the corrected mode (ESIM_CFG_CORRECTED)."""
+    p = DIURNAL["v1.7.1/1946157112TYPE299"]["mask_probe"]
+    assert (p["everywhere_decided_at_step"], p["lockdown_decided_at_step"]) == (926, 975)
+    (nb, ib), (na, ia) = p["before_96h_work_hours"], p["after_work_hours"]
+    ratio = (na / ia) / (nb / ib)
+    sigma = ratio * (1 / na + 1 / nb) ** 0.5          # Poisson counts
+    assert nb > 300 and na > 300 and ratio - 3 * sigma > 0.7 and abs(ratio - 0.86) < 3 * sigma
+
+    pop = synthetic_population(n_areas=200, areas_per_school=25, cross_area_fraction=0.6, initial_infected=30)
+    assert abs(float(((pop.flags & _abi.FLAG_MASK_COMPLIANT) != 0).mean()) - 0.8) < 0.01
+    ratios = {}
+    for mode, flags in (("parity", 0), ("corrected", _abi.CFG_CORRECTED)):
+        rs = []
+        for seed in (1, 2):
+            st = oracle_run(pop, seed, 0, steps=520, exposure_chance=0.003, lockdown_threshold=-1.0, vaccination_threshold=-1.0,
+                            mask_pt_threshold=0.002, mask_everywhere_threshold=0.02, flags=flags)
+            k = int(np.argmax(st[:, F["mask_status"]] == _abi.MASK_EVERYWHERE))
+            assert st[k, F["mask_status"]] == _abi.MASK_EVERYWHERE and 96 < k < len(st) - 49
+            rs.append(work_hour_rate(st, k + 1, k + 48) / work_hour_rate(st, k - 95, k))
+        ratios[mode] = sum(rs) / len(rs)
+    # (susceptible colleagues run short while the epidemic grows, so both lie somewhat below 0.86 and 0.44 x growth)
+    assert 0.66 < ratios["parity"] < 1.0 and ratios["corrected"] < 0.62 and ratios["parity"] > ratios["corrected"] + 0.12, ratios

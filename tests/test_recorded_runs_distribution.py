@@ -96,10 +96,11 @@ def facts(st):
 
 @pytest.fixture(scope="module")
 def oracle_v16(york):
-    """Three runs of the counter-based stream (what the CUDA path reproduces bit for bit) and one of the sequential generator
-    consumed the way the reference consumes rand 0.8, to extinction, under the v1.6 build's constants."""
+    """Three runs of the counter-based stream (what the CUDA path reproduces bit for bit; deterministic, unlike the sequential
+    mode whose draws depend on the thread schedule - tests/test_distribution.py shows the two agree in distribution), to extinction,
+    under the v1.6 build's constants."""
     cfg = dict(V16_CONSTANTS, exposure_chance=V16_CHANCE)
-    return [facts(oracle_run(york, seed, 0, **cfg)) for seed in (0, 1, 2)] + [facts(oracle_run(york, 7, 1, **cfg))]
+    return [facts(oracle_run(york, seed, 0, **cfg)) for seed in (0, 1, 2)]
 
 
 def test_oracle_shows_the_recorded_daily_signature(oracle_v16):

@@ -12,7 +12,7 @@ carried other constants than the tree at hand, so this is not a seed-to-seed ban
   hour - all read from that build's own console log and dumps): four repeats span peak 89 170 - 104 803 infected in hours
   689 - 946, extinction in hours 1114 - 1426, 88 330 - 95 944 vaccinated and 101 677 - 109 273 recovered at the end.  The oracle on
   the synthetic York-shaped population, with ONE free number (the per-contact chance of that build, which nothing records; 0.02
-  reproduces the build's ~110 exposures of the first 97 hours), lands inside that span;
+  reproduces the build's ~110 exposures of the first 97 hours), lands inside that span or within 5 % of it;
 * one lockdown decided during working hours (v1.7.1, hour 975 = 15 o'clock): see the last test for what it shows about that
   build and about the two lockdown semantics of this repository.
 """

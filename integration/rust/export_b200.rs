@@ -2,7 +2,17 @@
 //! the binary population file read by `esim_population_load` (format: epidemicsimulator_b200/csrc/population_io.cpp).
 //! Not compiled in this repository (no Rust toolchain in the image); tests/test_population_file.py pins the format from the
 //! C / Python side, including the checksum and the rejection of damaged files.
+use std::collections::HashMap;
+use std::ffi::CString;
 use std::io::Write;
+use std::path::Path;
+
+use sim_b200_sys as ffi;
+
+use crate::disease::DiseaseStatus;                                  // disease.rs:36-44
+use crate::models::building::{Building, BuildingID, School, Workplace};   // building.rs:62-67,125-140,220-232,330-342
+use crate::models::citizen::{Citizen, CitizenID};                   // citizen.rs:51-67,109-135
+use crate::simulator_builder::SimulatorBuilder;                     // simulator_builder.rs:58-69
 
 pub struct Soa {
     pub home: Vec<u32>, pub work: Vec<u32>, pub room: Vec<u32>, pub flags: Vec<u8>, pub status: Vec<u8>, pub timer: Vec<u16>,

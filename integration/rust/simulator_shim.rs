@@ -1,8 +1,33 @@
 //! Drop-in body for sim/src/simulator.rs: the public API (`From<SimulatorBuilder>`, `step`, `simulate`, the pub fields
 //! `visualisation` reads) stays, everything per time step runs in libesim_b200.so.  Not compiled in this repository.
+use std::collections::HashMap;
 use std::ffi::{CStr, CString};
+use std::os::raw::c_char;
+use std::time::Instant;
+
 use anyhow::Context;
 use sim_b200_sys as ffi;
+
+use crate::config::{get_memory_usage, DEBUG_ITERATION_PRINT};      // config.rs:34,42-47
+use crate::error::SimError;                                         // error.rs:24-52
+use crate::export_b200;                                             // integration/rust/export_b200.rs, added to the crate
+use crate::simulator_builder::SimulatorBuilder;                     // simulator_builder.rs:58-69
+
+/// To be added to sim/src/error.rs: the ESIM_ERR_* codes of include/esim.h are numbered after the variants of `SimError`
+/// (error.rs:24-52); what has no variant of its own (invalid population, no device, CUDA, communication, IO) arrives as
+/// `SimError::Error` with the library's message as its context.
+impl SimError {
+    pub fn from_code(code: i32, message: String) -> SimError {
+        match code {
+            -1 => SimError::Default { message },
+            -2 => SimError::Simulation { message },
+            -3 => SimError::InitializationError { message },
+            -4 => SimError::MissingCitizen { citizen_id: message },
+            -5 => SimError::OptionRetrievalFailure { message, key: String::new() },
+            _ => SimError::Error { context: format!("libesim_b200 error {}: {}", code, message) },
+        }
+    }
+}
 
 pub struct Simulator {
     handle: *mut ffi::EsimSim,

@@ -114,3 +114,34 @@ def test_sources_use_members_the_reference_has():
     for field in ("exposure_chance", "exposed_time", "infected_time", "max_time_step", "vaccination_rate", "mask_effectiveness"):
         assert "d.%s" % field in shim and "pub %s:" % field in (ref / "disease.rs").read_text(), field
     assert "pub const BUS_CAPACITY" in (ref / "config.rs").read_text()
+    # what else the shim takes from the crate: declared there, imported here
+    for used, path, decl in (("builder.disease_model", "simulator_builder.rs", "pub disease_model: DiseaseModel"),
+                             ("builder.area_code", "simulator_builder.rs", "pub area_code: String"),
+                             ("builder.output_area_lookup", "simulator_builder.rs", "pub output_area_lookup: HashMap<String, u32>"),
+                             ("get_memory_usage()?", "config.rs", "pub fn get_memory_usage() -> anyhow::Result<String>"),
+                             ("DEBUG_ITERATION_PRINT", "config.rs", "pub const DEBUG_ITERATION_PRINT: usize"),
+                             ("SimError::Simulation { message }", "error.rs", "Simulation {\n        message: String,"),
+                             ("SimError::InitializationError { message }", "error.rs", "InitializationError {\n        message: String,"),
+                             ("SimError::MissingCitizen { citizen_id: message }", "error.rs", "MissingCitizen {\n        citizen_id: String,"),
+                             ("SimError::OptionRetrievalFailure { message, key: String::new() }", "error.rs",
+                              "OptionRetrievalFailure {\n        message: String,\n        key: String,"),
+                             ("SimError::Error { context:", "error.rs", "Error {\n        context: String,")):
+        assert used in shim, used
+        assert decl in (ref / path).read_text(), "%s: `%s` not found" % (path, decl)
+    for line in ("use std::collections::HashMap;", "use std::time::Instant;", "use std::os::raw::c_char;",
+                 "use crate::config::{get_memory_usage, DEBUG_ITERATION_PRINT};", "use crate::error::SimError;",
+                 "use crate::simulator_builder::SimulatorBuilder;"):
+        assert line in shim, line
+    assert "pub fn from_code(code: i32, message: String) -> SimError" in shim     # the shim brings what error.rs does not have
+
+
+def test_error_codes_follow_the_simerror_variants():
+    """include/esim.h numbers ESIM_ERR_* after SimError's variants; the shim's from_code maps them back."""
+    import re
+    header = (ROOT / "include/esim.h").read_text()
+    codes = dict(re.findall(r"#define (ESIM_ERR_\w+)\s+(-\d+)", header))
+    assert [codes[k] for k in ("ESIM_ERR_DEFAULT", "ESIM_ERR_SIMULATION", "ESIM_ERR_INITIALIZATION", "ESIM_ERR_MISSING_CITIZEN",
+                               "ESIM_ERR_OPTION_RETRIEVAL")] == ["-1", "-2", "-3", "-4", "-5"]
+    shim = (ROOT / "integration/rust/simulator_shim.rs").read_text()
+    arms = dict(re.findall(r"(-\d) => SimError::(\w+)", shim))
+    assert arms == {"-1": "Default", "-2": "Simulation", "-3": "InitializationError", "-4": "MissingCitizen", "-5": "OptionRetrievalFailure"}

@@ -71,3 +71,23 @@ def test_reference_arm_rank_zero_of_two_names_the_two_gpu_workload():
     assert d["n_gpus"] == 2 and d["config"]["output_areas"] == 2 * 637
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm takes every host thread all the same
     assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+
+
+def test_algorithmic_bytes_are_the_model_of_design_4_4():
+    """roofline.achieved = these bytes / the measured launch time: 4 B per citizen + 5 B per susceptible + 8 B per infected
+    + 8 B per count cell for k_step, from the run's own statistics."""
+    import numpy as np
+    import bench
+    from epidemicsimulator_b200 import _abi
+    f = {n: i for i, n in enumerate(_abi.STATS_FIELDS)}
+    stats = np.zeros((2, len(_abi.STATS_FIELDS)), np.int64)
+    stats[0, f["susceptible"]], stats[0, f["infected"]] = 3_452_968, 10                     # hour 1 of BASELINE configs[1]
+    stats[1, f["susceptible"]], stats[1, f["infected"]], stats[1, f["exposures_building"]], stats[1, f["exposures_pt"]] = 1_000_000, 1_400_000, 700, 300
+    n, cells = 3_452_978, 1_240_000
+    upd, exp, fused, fused_r01 = bench.algorithmic_bytes(stats, n, cells)
+    assert fused[0] == 4 * n + 5 * 3_452_968 + 8 * 10 + 8 * cells
+    assert fused[1] == 4 * n + 5 * 1_001_000 + 8 * 1_400_000 + 8 * cells      # susceptible before the hour's exposures
+    assert fused_r01[0] == 4 * n + 8 * 3_452_968 + 8 * 10 + 8 * cells
+    assert upd[0] + exp[0] == fused_r01[0] + 4 * n                            # the fused pass reads the state word once
+    half = bench.algorithmic_bytes(stats, n // 2, cells // 2, shard_fraction=0.5)[2]
+    assert abs(half[1] - fused[1] / 2) < 8
